@@ -1,0 +1,131 @@
+/*
+ * pantas_aug.h -- C ABI of libpantas_aug.so, the B200 (sm_100a) implementation
+ * of pantas' `augment` hot loop.
+ *
+ * The reference has no FFI for this path: its boundary is a process contract
+ * (pantas:132 runs `python3 scripts/alignments_augmentation_from_gaf.py GAF GFA`).
+ * This ABI is what a ctypes binding inside that script binds instead of running
+ * the per-line Python loop; each entry point cites the reference code it
+ * replaces (REF:n = scripts/alignments_augmentation_from_gaf.py line n).
+ * INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C types only; no C++ exceptions cross the boundary;
+ *   - every function returns 0 on success or a negative PT_ERR_* code;
+ *     pt_last_error() gives the text of the last failure on that context;
+ *   - DATA errors (a record on which the reference would raise, or input the
+ *     device parser refuses to guess at) are sticky on the device and are
+ *     reported by pt_error(); counters are meaningless after one;
+ *   - a context belongs to one GPU and one host thread at a time;
+ *   - "dev" pointers are device pointers on the context's GPU, 16-byte aligned.
+ *
+ * Result layout (pt_export_dense / pt_export_side), N = n_nodes, E = n_edges:
+ *   sums   int64[3N + E + 4] = [ NC(N) | IL0adj(N) | OLadj(N) | RC(E) | rej, n_lines, 0, 0 ]
+ *          IL[v][0]      = NC[v] + IL0adj[v]        (REF:298-305, 335-342)
+ *          OL[v][len(v)] = NC[v] + OLadj[v]         (REF:306-313, 344-351)
+ *   stamps int64[2N]         = [ first-touch stamp of IL[v][0] | of OL[v][len(v)] ]
+ *          (INT64_MAX = never touched).  A stamp is (file byte offset of the
+ *          path step << 2) | e and reproduces Python dict insertion order.
+ *   novel  uint64[3 * n_novel]  rows {key = from_idx << 32 | to_idx, count, stamp}
+ *          links absent from the GFA (REF:426-427), unordered
+ *   sparse uint64[3 * n_sparse] rows {key = idx << 32 | dir << 31 | (pos + 2^30), count, stamp}
+ *          deletion-derived IL (dir 0) / OL (dir 1) keys (REF:281-297, 317-333), unordered
+ * sums add and stamps min across shards/ranks; side rows merge by key.
+ */
+#ifndef PANTAS_AUG_H
+#define PANTAS_AUG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pt_ctx pt_ctx;
+
+#define PT_ABI_VERSION 1
+
+/* API status codes (negative).  Data error codes (positive) are in pt_error(). */
+#define PT_ERR_CUDA (-1)      /* a CUDA runtime call failed */
+#define PT_ERR_ARG (-2)       /* bad argument */
+#define PT_ERR_STATE (-3)     /* call out of order (e.g. no graph set) */
+#define PT_ERR_NOMEM (-4)     /* allocation failed */
+#define PT_ERR_NODEVICE (-5)  /* no CUDA device / wrong architecture */
+
+/* Data error codes reported by pt_error() (see line_core.cuh):
+ *   1..19  the reference raises on this record (IndexError/ValueError/KeyError/assert)
+ *   20..39 input relies on Python behaviour the device parser does not model
+ *   40..   internal capacity (novel-edge / sparse table full) */
+
+int pt_abi_version(void);
+const char* pt_strerror(int code);      /* API or data code -> static text */
+
+/* Create / destroy a context on CUDA device `device`.  Fails with
+ * PT_ERR_NODEVICE unless the device is compute capability 10.x. */
+int pt_create(int device, pt_ctx** out);
+void pt_destroy(pt_ctx* ctx);
+const char* pt_last_error(pt_ctx* ctx);
+
+/* Run all work of this context on an existing CUDA stream (a cudaStream_t,
+ * e.g. torch.cuda.current_stream().cuda_stream).  Default: a private stream. */
+int pt_set_stream(pt_ctx* ctx, void* cuda_stream);
+
+/* Replaces REF:121-126 (nodes_info) and the implicit key set of REF:421.
+ * node_len[i] is the sequence length of node id (min_id + i), 0xFFFFFFFF where
+ * no such S line exists.  edge_keys[e] = from_idx << 32 | to_idx for the e-th
+ * DISTINCT (from, to) pair of the GFA's L lines, in first-occurrence order.
+ * Pointers may be host or device memory; the library copies.
+ * novel_cap / sparse_cap: slots of the side tables (0 = default). */
+int pt_set_graph(pt_ctx* ctx, const uint32_t* node_len, uint64_t n_nodes, uint32_t min_id,
+                 const uint64_t* edge_keys, uint64_t n_edges, uint64_t novel_cap, uint64_t sparse_cap);
+
+/* Zero all counters, stamps, side tables and the sticky error (graph stays). */
+int pt_reset_counts(pt_ctx* ctx);
+
+/* Replaces the loop REF:138-371 for the records in gaf_dev[0, nbytes).
+ * The chunk must start at a line start and end at a line end or at EOF;
+ * gaf_dev must be 16-byte aligned and readable up to nbytes rounded up to 16.
+ * file_offset = byte offset of gaf_dev[0] in the whole GAF (stamps use it, so
+ * results do not depend on how the file was chunked or sharded).
+ * mapq_thr = argv[2] of the reference (default 20, REF:113).
+ * Asynchronous: returns after enqueueing on the context's stream. */
+int pt_process_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, uint64_t file_offset,
+                     int64_t mapq_thr);
+
+/* Same, from HOST memory (pinned for full speed): copies through two
+ * library-owned device staging buffers so the copy of one chunk overlaps the
+ * kernels of the previous one.  nbytes <= pt_stage_bytes().  Returns a ticket
+ * >= 0; the host buffer may be reused once pt_wait_copy(ticket) returns. */
+int64_t pt_process_host(pt_ctx* ctx, const uint8_t* gaf_host, uint64_t nbytes, uint64_t file_offset,
+                        int64_t mapq_thr);
+int pt_wait_copy(pt_ctx* ctx, int64_t ticket);
+int pt_set_stage_bytes(pt_ctx* ctx, uint64_t bytes);   /* before first pt_process_host */
+uint64_t pt_stage_bytes(pt_ctx* ctx);
+
+int pt_sync(pt_ctx* ctx);
+
+/* Sticky data error: *code = 0 if none, else the code and the file byte offset
+ * of the first (lowest offset) offending record.  Synchronises. */
+int pt_error(pt_ctx* ctx, uint64_t* bad_offset, int* code);
+
+/* After the last chunk: compacts the side tables.  Synchronises. */
+int pt_finalize(pt_ctx* ctx, uint64_t* n_novel, uint64_t* n_sparse);
+
+/* Write results into caller-owned DEVICE buffers (layout above).  The caller
+ * (Python, torch tensors) then reduces across ranks: REF has no counterpart,
+ * see DESIGN.md "multi-GPU". */
+int pt_export_dense(pt_ctx* ctx, int64_t* sums_dev, uint64_t sums_len, int64_t* stamps_dev, uint64_t stamps_len);
+int pt_export_side(pt_ctx* ctx, uint64_t* novel_dev, uint64_t novel_rows, uint64_t* sparse_dev, uint64_t sparse_rows);
+
+/* CUDA-event timer on the context's stream (bench.py). */
+int pt_timer_start(pt_ctx* ctx);
+int pt_timer_stop(pt_ctx* ctx, float* ms);     /* synchronises on the stop event */
+
+/* Counters for reports: kernel launches since create, records that took the
+ * long-line path, tiles processed. */
+int pt_stats(pt_ctx* ctx, uint64_t* kernel_launches, uint64_t* deferred_lines, uint64_t* tiles);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANTAS_AUG_H */

@@ -1,0 +1,176 @@
+"""`pantas augment` -- host driver with the reference's argv / stdout / stderr.
+
+Mirrors main() of /root/reference/scripts/alignments_augmentation_from_gaf.py
+(REF:110-427): same positional arguments ``gaf gfa [thr=20]``, the augmented GFA
+on stdout, the same four progress lines on stderr, and on malformed input a
+non-zero exit with nothing on stdout.  The per-line loop REF:138-371 runs on the
+GPU through include/pantas_aug.h; there is no CPU fallback.
+
+Multi-GPU: launch under torchrun (one process per GPU); each rank parses its
+byte range of the GAF, rank 0 writes the GFA.  Or set PANTAS_GPUS=N and the
+driver re-launches itself that way.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+from .counts import Counts, FlatResult
+from .errors import PantasDataError, UnsupportedInput
+from .gfa import Graph, load_graph, write_augmented
+from .shard import shard_bounds
+
+
+def _last_newline(arr: np.ndarray, n: int) -> int:
+    """Index of the last '\\n' in arr[:n], -1 if none."""
+    w = 1 << 12
+    hi = n
+    while hi > 0:
+        lo = max(0, hi - w)
+        nz = np.flatnonzero(arr[lo:hi] == 10)
+        if nz.size:
+            return lo + int(nz[-1])
+        hi = lo
+        w *= 4
+    return -1
+
+
+def stream_gaf_range(engine, gaf_file: str, lo: int, hi: int, thr: int) -> None:
+    """Feed records starting in [lo, hi) of the file to the engine, double-buffered
+    through two pinned host buffers (file read || H2D || kernels)."""
+    import torch
+
+    stage = engine.stage_bytes
+    bufs = [torch.empty(stage, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    views = [b.numpy() for b in bufs]
+    tickets = [None, None]
+    carry = np.zeros(0, dtype=np.uint8)
+    k = 0
+    pos = lo                      # file offset of the first byte not yet handed to the engine
+    with open(gaf_file, "rb", buffering=0) as f:
+        f.seek(lo)
+        remaining = hi - lo
+        while remaining > 0 or carry.size:
+            if tickets[k] is not None:
+                engine.wait_copy(tickets[k])
+            v = views[k]
+            c = carry.size
+            if c:
+                v[:c] = carry
+            want = min(stage - c, remaining)
+            got = 0
+            while got < want:
+                r = f.readinto(memoryview(v[c + got:c + want]))
+                if not r:
+                    break
+                got += r
+            if got < want:
+                remaining = got           # file shorter than expected
+            remaining -= got
+            n = c + got
+            if n == 0:
+                break
+            if remaining > 0:
+                cut = _last_newline(v, n) + 1
+                if cut <= 0:
+                    raise UnsupportedInput(f"GAF record longer than the {stage >> 20} MiB staging buffer "
+                                           "(raise PANTAS_STAGE_MB)")
+            else:
+                cut = n
+            carry = v[cut:n].copy()
+            tickets[k] = engine.process_host(bufs[k].data_ptr(), cut, pos, thr)
+            pos += cut
+            k ^= 1
+    engine.sync()
+
+
+def augment_file(graph: Graph, gaf_file: str, thr: int = 20, device: int = 0, lo: int | None = None,
+                 hi: int | None = None, engine=None):
+    """GAF loop on one GPU over [lo, hi) of the file -> (engine, error word)."""
+    from .engine import AugmentEngine
+
+    eng = engine or AugmentEngine(device)
+    if eng.graph is not graph:
+        eng.set_graph(graph)
+    size = os.path.getsize(gaf_file)
+    stream_gaf_range(eng, gaf_file, 0 if lo is None else lo, size if hi is None else hi, thr)
+    return eng
+
+
+def _distributed_env():
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    return ws, int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def main(argv, out=None, err=None) -> int:
+    out = out or sys.stdout
+    err = err or sys.stderr
+    gaf_file = argv[0]
+    gfa_file = argv[1]
+    thr = int(argv[2]) if len(argv) > 2 else 20           # REF:113
+    world, rank, local_rank = _distributed_env()
+
+    print("Read GFA", file=err) if rank == 0 else None    # REF:120
+    graph = load_graph(gfa_file)
+    print("Augmentation by GAF alignments", file=err) if rank == 0 else None   # REF:134
+
+    from .engine import AugmentEngine
+
+    if world == 1:
+        eng = AugmentEngine(int(os.environ.get("PANTAS_DEVICE", "0")))
+        eng.set_graph(graph)
+        augment_file(graph, gaf_file, thr, engine=eng)
+        eng.check_data_error()
+        flat: FlatResult = eng.export()
+    else:
+        import torch
+        import torch.distributed as dist
+
+        from .dist import ERR_NONE, allreduce_results, reduce_error
+
+        torch.cuda.set_device(local_rank)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        eng = AugmentEngine(local_rank)
+        eng.set_graph(graph)
+        b = shard_bounds(gaf_file, world)
+        augment_file(graph, gaf_file, thr, engine=eng, lo=b[rank], hi=b[rank + 1])
+        word = ERR_NONE
+        try:
+            eng.check_data_error()
+        except (PantasDataError, UnsupportedInput) as e:
+            word = (e.offset << 8) | e.code
+        word = reduce_error(word, eng.tdev)
+        if word != ERR_NONE:
+            code, off = word & 0xFF, word >> 8
+            text = eng.lib.pt_strerror(code).decode()
+            exc = PantasDataError if code < 20 else UnsupportedInput
+            raise exc(f"GAF byte offset {off}: {text}", code, off)
+        sums, stamps, novel, sparse = eng.export_device()
+        flat = allreduce_results(sums, stamps, novel, sparse, graph.n_nodes, graph.n_edges)
+        if rank != 0:
+            return 0
+
+    counts = Counts.from_flat(flat)
+    print(f"Rejected alignments: {counts.rej}", file=err)  # REF:375
+    print("Annotating GFA", file=err)                      # REF:376
+    write_augmented(gfa_file, graph, counts, out)
+    return 0
+
+
+def cli(argv=None) -> int:
+    argv = sys.argv[1:] if argv is None else argv
+    gpus = int(os.environ.get("PANTAS_GPUS", "1"))
+    if gpus > 1 and "WORLD_SIZE" not in os.environ:
+        import subprocess
+
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1",
+               "--nnodes=1", f"--nproc-per-node={gpus}", "-m", "pantas_b200.augment"] + list(argv)
+        return subprocess.call(cmd)
+    return main(argv)
+
+
+if __name__ == "__main__":
+    sys.exit(cli())

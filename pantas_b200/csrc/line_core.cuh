@@ -1,0 +1,507 @@
+// line_core.cuh -- one GAF record -> counter events, as an O(1)-state stream.
+//
+// This is the B200 formulation of the reference's per-line body
+//   /root/reference/scripts/alignments_augmentation_from_gaf.py:142-363   (REF:n)
+// The reference materialises token lists, an op list, per-node op slices
+// (`align`), the cleared/compacted copy (`final_align`) and then makes three
+// passes over it (NC, IL/OL, RC).  One GPU thread owns one record here, so
+// nothing is materialised: the path column and the cs string are walked once,
+// in lock step, with a one-node look-ahead (is this the last path node?) and a
+// one-node look-behind (was that the last *surviving* node?), and every
+// counter update is emitted as an event into a Sink:
+//
+//   sink.lookup(id, idx, len)           node id -> dense index + length  (REF:214)
+//   sink.count_node(idx)                NC[idx] += 1                     (REF:263-269)
+//   sink.dense(idx, il, ol, stamp)      IL[idx][0] += il, OL[idx][len] += ol, stored as
+//                                       (il - 1), (ol - 1) relative to NC (REF:298-313,335-351)
+//   sink.sparse(idx, dir, pos, stamp)   IL/OL[idx][pos] += 1 for deletion-derived keys
+//                                                                        (REF:281-297,317-333)
+//   sink.edge(from, to, stamp)          RC[(from,to)] += 1               (REF:357-363)
+//   sink.reject()                       rej += 1                         (REF:144-146)
+//   sink.error(code, file_offset)       the reference would raise / input not modelled
+//
+// `stamp` = (file byte offset of the path step) * 4 + e orders first insertions
+// exactly like Python's dict insertion order does:
+// e = 0 for the j == 0 deletion key, 1 for the dense key, 2 for the j == last
+// deletion key.
+//
+// The same header is compiled by nvcc into the kernels (augment_kernels.cu) and
+// by g++ into tests/hostsim (a TEST harness that lets the CPU-only container
+// fuzz this logic against the oracle; it is not part of the shipped library).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PT_HD __host__ __device__ __forceinline__
+#else
+#define PT_HD inline
+#endif
+
+namespace pt {
+
+// Error codes < 20: the reference raises on this record (nothing on stdout).
+// Codes >= 20: the reference would go on, relying on behaviour we refuse to
+// guess at (DESIGN.md "documented deviations"); codes >= 40: capacity.
+enum : int {
+    PT_OK = 0,
+    PT_E_COLUMNS = 1,      // < 12 whitespace separated columns   (IndexError REF:143)
+    PT_E_MAPQ = 2,         // int(tokens[11]) fails               (ValueError REF:143)
+    PT_E_COORD = 3,        // int(tokens[6..8]) fails             (ValueError REF:151-153)
+    PT_E_NO_DV = 4,        // no dv:f:<digit> tag                 (ValueError REF:179)
+    PT_E_EMPTY_PATH = 5,   // assert len(nodes) > 0               (REF:197)
+    PT_E_UNKNOWN_NODE = 6, // KeyError                            (REF:214)
+    PT_E_CS_SHORT = 7,     // cigar_vals[0] on an empty list      (IndexError REF:227)
+    PT_U_TILDE = 20,       // '~' op: reference reuses a stale length
+    PT_U_NON_ASCII = 21,   // byte >= 0x80 (Unicode whitespace/digits not modelled)
+    PT_U_BARE_CR = 22,     // lone '\r' (universal-newline line break)
+    PT_U_BIG_INT = 23,     // integer beyond the device range
+    PT_U_UNDERSCORE = 24,  // int("1_0") is valid Python
+    PT_U_POSITION = 25,    // IL/OL position outside the 31-bit key field
+    PT_X_NOVEL_FULL = 40,  // novel-edge table full
+    PT_X_SPARSE_FULL = 41, // sparse IL/OL table full
+    PT_X_DEFER_FULL = 42,  // long-line list full
+};
+
+enum : int { LINE_DONE = 0, LINE_DEFER = 1 };
+
+// str.isspace() for ASCII (str.split() / str.strip() / regex \s):
+// \t \n \v \f \r, 0x1c..0x1f, space
+PT_HD bool is_ws(uint32_t c) {
+    return c == 0x20u || (c - 0x09u) <= 4u || (c - 0x1cu) <= 3u;
+}
+PT_HD bool is_digit(uint32_t c) { return (c - 0x30u) <= 9u; }
+PT_HD bool is_cs_op(uint32_t c) {
+    return c == ':' || c == '*' || c == '-' || c == '+' || c == '=' || c == '~';
+}
+
+// Fractional digits of the exact midpoint between the double nearest 0.1 and
+// the next double above it: float(s) > 0.1  <=>  decimal(s) > 0.1000000000000000124900090...
+// (the tie rounds to even, i.e. down to 0.1, so equality is "not greater").
+// REF:179.  57 digits.
+PT_HD uint32_t dv_midpoint_digit(int k) {
+    const char* m = "100000000000000012490009027033011079765856266021728515625";
+    return k < 57 ? (uint32_t)(m[k] - '0') : 0u;
+}
+
+struct LineCtx {
+    const uint8_t* s;   // base of the addressable bytes
+    int lim;            // bytes [0, lim) are addressable
+    bool lim_final;     // true: the data really ends at lim (end of chunk)
+    int64_t base_off;   // file offset of s[0]
+};
+
+// [+-]?[0-9]+  -> 1 ok, 0 ValueError, PT_U_* if Python accepts what we do not
+PT_HD int parse_py_int(const uint8_t* s, int a, int b, int64_t& out) {
+    int q = a;
+    bool neg = false;
+    if (q < b && (s[q] == '+' || s[q] == '-')) { neg = s[q] == '-'; q++; }
+    if (q >= b) return 0;
+    int64_t v = 0;
+    int sig = 0;
+    for (; q < b; q++) {
+        uint32_t c = s[q];
+        if (!is_digit(c)) return (c == '_' && q > a && q + 1 < b) ? PT_U_UNDERSCORE : 0;
+        if (sig || c != '0') sig++;
+        if (sig > 18) return PT_U_BIG_INT;
+        v = v * 10 + (int64_t)(c - '0');
+    }
+    out = neg ? -v : v;
+    return 1;
+}
+
+// Streaming reader of the cs difference string, REF:154-167 + parse_cigar REF:10-37.
+struct OpReader {
+    const uint8_t* s;
+    int q, end;          // unread part of the cs token (stream mode)
+    int n_pre;           // ops held in registers (absent tag / exactly-two-op case)
+    int i_pre;
+    uint8_t pre_op[2];
+    int64_t pre_len[2];
+
+    // the cs token with every "cs:Z:" removed (.replace("cs:Z:", ""), REF:158)
+    PT_HD bool next_char(uint32_t& c) {
+        while (q < end) {
+            if (s[q] == 'c' && q + 5 <= end && s[q + 1] == 's' && s[q + 2] == ':' && s[q + 3] == 'Z' &&
+                s[q + 4] == ':') {
+                q += 5;
+                continue;
+            }
+            c = s[q];
+            return true;
+        }
+        return false;
+    }
+
+    // one (op, len) from the string; 1 ok, 0 exhausted, PT_U_BIG_INT
+    PT_HD int parse_one(uint8_t& op, int64_t& len) {
+        uint32_t c;
+        for (;;) {                       // text before the first operator is ignored (curr_op is None)
+            if (!next_char(c)) return 0;
+            q++;
+            if (is_cs_op(c)) break;
+        }
+        op = (uint8_t)c;
+        int64_t count = 0, val = 0;
+        int sig = 0;
+        bool alldig = true;
+        while (next_char(c)) {
+            if (is_cs_op(c)) break;
+            q++;
+            count++;
+            if (is_digit(c)) {
+                if (sig || c != '0') sig++;
+                if (sig <= 15) val = val * 10 + (int64_t)(c - '0');
+            } else {
+                alldig = false;
+            }
+        }
+        if (op == '*') len = 1;                          // REF:28-29
+        else if (alldig && count > 0) {                  // REF:31-32
+            if (sig > 15) return PT_U_BIG_INT;
+            len = val;
+        } else len = count;                              // REF:33-34
+        return 1;
+    }
+
+    PT_HD int fetch(uint8_t& op, int64_t& len) {
+        if (i_pre < n_pre) {
+            op = pre_op[i_pre];
+            len = pre_len[i_pre];
+            i_pre++;
+            return 1;
+        }
+        if (n_pre) return 0;
+        return parse_one(op, len);
+    }
+};
+
+// A surviving node whose IL/OL events wait until we know whether another
+// surviving node follows it (i != len(final_align) - 1, REF:290,306,326,336).
+struct Pending {
+    bool valid;
+    bool is_first;       // i == 0 in final_align
+    bool first_del, last_del;
+    uint32_t idx, len;
+    int64_t n_count;     // ops that are neither '-' nor '*' in the compacted slice
+    int64_t first_len, last_len;
+    uint64_t stamp;      // file offset of the step << 2
+};
+
+template <class Sink>
+PT_HD void flush_pending(const Pending& p, bool is_last, bool rev, Sink& sink) {
+    const bool not_first = !p.is_first, not_last = !is_last;
+    // which end condition guards which dictionary (REF:280-353)
+    const bool il_cond = rev ? not_last : not_first;
+    const bool ol_cond = rev ? not_first : not_last;
+    int64_t il_touch = il_cond ? p.n_count : 0;
+    int64_t ol_touch = ol_cond ? p.n_count : 0;
+    if (!rev) {
+        if (p.first_del && not_first) {                                   // REF:282-289
+            if (p.first_len == 0) il_touch++;                             // same key as the dense one
+            else sink.sparse(p.idx, 0, p.first_len, p.stamp | 0u);
+        }
+        if (p.last_del && not_last)                                       // REF:290-297
+            sink.sparse(p.idx, 1, (int64_t)p.len - p.last_len - 1, p.stamp | 2u);
+    } else {
+        if (p.first_del && not_first)                                     // REF:318-325
+            sink.sparse(p.idx, 1, (int64_t)p.len - 1 - p.first_len, p.stamp | 0u);
+        if (p.last_del && not_last) {                                     // REF:326-333
+            if (p.last_len == 0) il_touch++;
+            else sink.sparse(p.idx, 0, p.last_len, p.stamp | 2u);
+        }
+    }
+    sink.dense(p.idx, il_touch, ol_touch, p.stamp | 1u);
+}
+
+// One path piece starting at s[pq] == sep (REF:187,191).  Only canonical decimal
+// ids can name a node (the host refuses graphs with any other S id), so every
+// other spelling is the reference's KeyError.
+template <class Sink>
+PT_HD bool read_piece(const uint8_t* s, int& pq, int b5, uint32_t sep, Sink& sink, uint32_t& idx, uint32_t& len,
+                      int& at) {
+    pq++;
+    at = pq;
+    uint64_t id = 0;
+    int nd = 0;
+    bool ok = true;
+    while (pq < b5 && s[pq] != sep) {
+        const uint32_t c = s[pq];
+        if (!is_digit(c)) ok = false;
+        if (nd < 11) id = id * 10 + (c - '0');
+        nd++;
+        pq++;
+    }
+    if (nd == 0 || nd > 10 || (nd > 1 && s[at] == '0')) ok = false;
+    if (ok) ok = sink.lookup(id, idx, len);
+    return ok;
+}
+
+// Process the record starting at s[p].  Returns LINE_DEFER (nothing emitted)
+// when the record runs past `lim` and lim is not the end of the data.
+template <class Sink>
+PT_HD int process_line(const LineCtx& cx, int p, int64_t thr, Sink& sink) {
+    const uint8_t* s = cx.s;
+    const int lim = cx.lim;
+    const int64_t line_off = cx.base_off + p;
+
+    // ---- tokens 0..11 of line.strip().split()  (REF:142)
+    int q = p;
+    int a5 = 0, b5 = 0, a6 = 0, b6 = 0, a7 = 0, b7 = 0, a8 = 0, b8 = 0, a11 = 0, b11 = 0;
+    for (int t = 0; t < 12; t++) {
+        while (q < lim && s[q] != '\n' && is_ws(s[q])) q++;
+        if (q >= lim) {
+            if (!cx.lim_final) return LINE_DEFER;
+            sink.error(PT_E_COLUMNS, line_off);
+            return LINE_DONE;
+        }
+        if (s[q] == '\n') { sink.error(PT_E_COLUMNS, line_off); return LINE_DONE; }
+        const int a = q;
+        while (q < lim && !is_ws(s[q])) q++;
+        if (q >= lim && !cx.lim_final) return LINE_DEFER;
+        if (t == 5) { a5 = a; b5 = q; }
+        else if (t == 6) { a6 = a; b6 = q; }
+        else if (t == 7) { a7 = a; b7 = q; }
+        else if (t == 8) { a8 = a; b8 = q; }
+        else if (t == 11) { a11 = a; b11 = q; }
+    }
+
+    // ---- MAPQ filter, unmapped filter (REF:143-148)
+    int64_t mapq;
+    int r = parse_py_int(s, a11, b11, mapq);
+    if (r != 1) { sink.error(r == 0 ? PT_E_MAPQ : r, line_off); return LINE_DONE; }
+    if (mapq < thr) { sink.reject(); return LINE_DONE; }
+    if (b5 - a5 == 1 && s[a5] == '*') return LINE_DONE;
+
+    // ---- path length / start / end (REF:151-153)
+    int64_t plen, start, pend;
+    r = parse_py_int(s, a6, b6, plen);
+    if (r != 1) { sink.error(r == 0 ? PT_E_COORD : r, line_off); return LINE_DONE; }
+    r = parse_py_int(s, a7, b7, start);
+    if (r != 1) { sink.error(r == 0 ? PT_E_COORD : r, line_off); return LINE_DONE; }
+    r = parse_py_int(s, a8, b8, pend);
+    if (r != 1) { sink.error(r == 0 ? PT_E_COORD : r, line_off); return LINE_DONE; }
+    const int64_t end_rel = plen - pend;
+
+    // ---- tags: first "cs:" (to the end of its token) and first "dv:f:<digit>"
+    //      (REF:154-160, 172-180).  Both regexes run over " ".join(tokens[12:]);
+    //      neither pattern contains whitespace, so a left-to-right scan of the
+    //      rest of the line finds the same matches.
+    int c0 = -1, c1 = -1, d0 = -1;
+    {
+        int t = q;
+        for (;;) {
+            if (t >= lim) {
+                if (!cx.lim_final) return LINE_DEFER;
+                break;
+            }
+            const uint32_t c = s[t];
+            if (c == '\n') break;
+            if (c0 >= 0 && c1 < 0 && is_ws(c)) c1 = t;
+            if (c == 'c' && c0 < 0) {
+                if (t + 3 > lim && !cx.lim_final) return LINE_DEFER;
+                if (t + 3 <= lim && s[t + 1] == 's' && s[t + 2] == ':') c0 = t;
+            } else if (c == 'd' && d0 < 0) {
+                if (t + 6 > lim && !cx.lim_final) return LINE_DEFER;
+                if (t + 6 <= lim && s[t + 1] == 'v' && s[t + 2] == ':' && s[t + 3] == 'f' && s[t + 4] == ':' &&
+                    is_digit(s[t + 5]))
+                    d0 = t + 5;
+            }
+            if (c0 >= 0 && c1 >= 0 && d0 >= 0) break;
+            t++;
+        }
+        if (c0 >= 0 && c1 < 0) c1 = t;      // token ran to the end of the line
+    }
+
+    // ---- dv filter: float(dv) > 0.1 -> skip (REF:172-180), exact on the decimal text
+    if (d0 < 0) { sink.error(PT_E_NO_DV, line_off); return LINE_DONE; }
+    {
+        int t = d0;
+        bool int_nonzero = false;
+        while (t < lim && is_digit(s[t])) { int_nonzero |= (s[t] != '0'); t++; }
+        if (t >= lim && !cx.lim_final) return LINE_DEFER;
+        bool greater = int_nonzero;
+        if (!greater && t + 1 < lim && s[t] == '.' && is_digit(s[t + 1])) {
+            t++;
+            int k = 0;
+            int cmp = 0;                   // sign of (fraction - midpoint) so far
+            while (t < lim && is_digit(s[t])) {
+                if (cmp == 0) {
+                    const uint32_t fd = s[t] - '0', md = dv_midpoint_digit(k);
+                    cmp = fd > md ? 1 : (fd < md ? -1 : 0);
+                }
+                k++;
+                t++;
+            }
+            if (t >= lim && !cx.lim_final) return LINE_DEFER;
+            if (cmp == 0)                  // remaining midpoint digits vs implicit zeros
+                for (; k < 57; k++)
+                    if (dv_midpoint_digit(k) != 0) { cmp = -1; break; }
+            greater = cmp > 0;
+        } else if (!greater && t + 1 >= lim && !cx.lim_final && t < lim && s[t] == '.') {
+            return LINE_DEFER;
+        }
+        if (greater) return LINE_DONE;
+    }
+
+    // ---- cs ops (REF:154-167)
+    OpReader ops;
+    ops.s = s;
+    ops.n_pre = 0;
+    ops.i_pre = 0;
+    ops.pre_op[0] = ops.pre_op[1] = 0;
+    ops.pre_len[0] = ops.pre_len[1] = 0;
+    int64_t start_pos = start;
+    if (c0 < 0) {                                   // cigar = "*" -> [('*', 1)]  (REF:160)
+        ops.q = ops.end = 0;
+        ops.n_pre = 1;
+        ops.pre_op[0] = '*';
+        ops.pre_len[0] = 1;
+    } else {
+        ops.q = c0;
+        ops.end = c1;
+        int nops = 0;
+        uint32_t c;
+        while (ops.next_char(c)) { nops += is_cs_op(c) ? 1 : 0; ops.q++; }
+        ops.q = c0;
+        if (nops == 2) {                            // cigar_clipping, REF:40-50,164-167
+            int r0 = ops.parse_one(ops.pre_op[0], ops.pre_len[0]);
+            int r1 = ops.parse_one(ops.pre_op[1], ops.pre_len[1]);
+            if (r0 != 1 || r1 != 1) { sink.error(PT_U_BIG_INT, line_off); return LINE_DONE; }
+            ops.n_pre = 2;
+            if (ops.pre_op[0] == '+' && ops.pre_op[1] == ':') {
+                start_pos += ops.pre_len[0];
+                ops.pre_op[0] = ops.pre_op[1];
+                ops.pre_len[0] = ops.pre_len[1];
+                ops.n_pre = 1;
+            } else if (ops.pre_op[0] == ':' && ops.pre_op[1] == '+') {
+                ops.n_pre = 1;
+            }
+        } else if (nops == 0) {
+            ops.q = ops.end;                        // empty op list
+        }
+    }
+
+    // ---- path decode (REF:185-197) fused with the merge walk (REF:205-255),
+    //      clear_align/compact_align (REF:63-107) and the three accumulations.
+    const bool rev = s[a5] != '>';
+    const uint32_t sep = rev ? '<' : '>';
+    int pq = a5;
+    while (pq < b5 && s[pq] != sep) pq++;           // split(sep)[1:] drops the first piece
+    if (pq >= b5) { sink.error(PT_E_EMPTY_PATH, line_off); return LINE_DONE; }
+
+    uint32_t cur_idx = 0, cur_len = 0, nxt_idx = 0, nxt_len = 0;
+    int cur_at = 0, nxt_at = 0;
+    bool have_nxt = false;
+
+
+    if (!read_piece(s, pq, b5, sep, sink, cur_idx, cur_len, cur_at)) { sink.error(PT_E_UNKNOWN_NODE, cx.base_off + cur_at); return LINE_DONE; }
+
+    bool head_valid = false;
+    uint8_t head_op = 0;
+    int64_t head_rem = 0;
+
+    Pending pend_node;
+    pend_node.valid = false;
+    pend_node.is_first = false;
+    pend_node.first_del = pend_node.last_del = false;
+    pend_node.idx = pend_node.len = 0;
+    pend_node.n_count = pend_node.first_len = pend_node.last_len = 0;
+    pend_node.stamp = 0;
+    bool any_survivor = false;
+    bool first_node = true;
+
+    for (;;) {
+        // look ahead to the next *distinct* piece (consecutive duplicates collapse, REF:188)
+        have_nxt = false;
+        while (pq < b5) {
+            if (!read_piece(s, pq, b5, sep, sink, nxt_idx, nxt_len, nxt_at)) { sink.error(PT_E_UNKNOWN_NODE, cx.base_off + nxt_at); return LINE_DONE; }
+            if (nxt_idx != cur_idx) { have_nxt = true; break; }
+        }
+
+        int64_t L = (int64_t)cur_len;
+        if (first_node) L -= start_pos;                 // REF:215-216
+        if (!have_nxt) L = L - end_rel + 1;             // REF:217-218
+        first_node = false;
+
+        if (L > 0) {
+            int nP = 0, nQ = 0;
+            uint8_t p0_op = 0, qlast_op = 0, first_op = 0;
+            int64_t qlast_len = 0, first_len = 0, n_count = 0;
+            while (L > 0) {
+                if (!head_valid) {
+                    int fr = ops.fetch(head_op, head_rem);
+                    if (fr == 0) {
+                        if (nP == 0) { sink.error(PT_E_CS_SHORT, line_off); return LINE_DONE; }  // REF:227
+                        break;                                                                   // REF:252-255
+                    }
+                    if (fr != 1) { sink.error(fr, line_off); return LINE_DONE; }
+                    head_valid = true;
+                }
+                if (head_op == '~') { sink.error(PT_U_TILDE, line_off); return LINE_DONE; }
+                int64_t take;
+                if (L <= head_rem) {                    // REF:234-243
+                    take = L;
+                    head_rem -= L;
+                    if (head_rem == 0) head_valid = false;
+                    L = 0;
+                } else {                                // REF:244-251
+                    take = head_rem;
+                    L -= head_rem;
+                    head_valid = false;
+                }
+                // compact_align as a running fold (REF:63-94)
+                bool push = false;
+                int64_t push_len = take;
+                if (nP == 0) {
+                    p0_op = head_op;
+                    push = head_op != '*';
+                } else if (nQ == 0) {
+                    push = true;
+                    push_len = take + 1;
+                } else if (head_op == qlast_op || head_op == '*') {
+                    qlast_len += take;
+                } else {
+                    push = true;
+                }
+                if (push) {
+                    if (nQ == 1) { first_op = qlast_op; first_len = qlast_len; }
+                    qlast_op = head_op;
+                    qlast_len = push_len;
+                    nQ++;
+                    if (head_op != '-' && head_op != '*') n_count++;
+                }
+                nP++;
+            }
+            if (nQ == 1) { first_op = qlast_op; first_len = qlast_len; }
+            const bool dropped = (nP == 1 && (p0_op == '-' || p0_op == '+'));   // REF:101-102
+            if (!dropped) {
+                const uint64_t stamp = (uint64_t)(cx.base_off + cur_at) << 2;
+                if (pend_node.valid) {
+                    flush_pending(pend_node, false, rev, sink);
+                    if (rev) sink.edge(cur_idx, pend_node.idx, stamp);          // REF:357-363
+                    else sink.edge(pend_node.idx, cur_idx, stamp);
+                }
+                sink.count_node(cur_idx);                                       // REF:263-269
+                pend_node.valid = true;
+                pend_node.is_first = !any_survivor;
+                pend_node.idx = cur_idx;
+                pend_node.len = cur_len;
+                pend_node.n_count = n_count;
+                pend_node.first_del = nQ > 0 && first_op == '-';
+                pend_node.last_del = nQ > 0 && qlast_op == '-';
+                pend_node.first_len = first_len;
+                pend_node.last_len = qlast_len;
+                pend_node.stamp = stamp;
+                any_survivor = true;
+            }
+        }
+        if (!have_nxt) break;
+        cur_idx = nxt_idx;
+        cur_len = nxt_len;
+        cur_at = nxt_at;
+    }
+    if (pend_node.valid) flush_pending(pend_node, true, rev, sink);
+    return LINE_DONE;
+}
+
+}  // namespace pt

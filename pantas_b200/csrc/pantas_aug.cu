@@ -1,0 +1,874 @@
+// pantas_aug.cu -- sm_100a kernels + C ABI (include/pantas_aug.h) for pantas `augment`.
+//
+// Replaces the per-line loop of the reference,
+//   /root/reference/scripts/alignments_augmentation_from_gaf.py:138-371   (REF:n)
+// Data flow on the device (DESIGN.md has the full picture):
+//
+//   GAF bytes in HBM --cp.async.bulk (TMA 1-D)--> shared-memory tile (64 KB + look-ahead)
+//     phase 1, whole CTA : 128-bit LDS scan of the tile for '\n' (line starts this
+//                          tile owns), '\r' and non-ASCII bytes
+//     phase 2, 1 thread / record : pt::process_line (line_core.cuh) walks the path
+//                          column and the cs string out of shared memory and emits
+//                          RED.ADD.64 / ATOM.MIN.64 into
+//                            NodeRec[idx]   {len, NC, IL0 stamp, OL stamp}   32 B = 1 sector / node
+//                            il_adj/ol_adj  rare corrections (ends of a read, multi-op nodes)
+//                            EdgeSlot[]     64-bit-key open addressing, home slot = from_idx << shift
+//                                           (neighbouring nodes -> neighbouring slots, so a read's
+//                                           steps probe consecutive sectors)
+//                            novel / sparse 64-bit-key open-addressing side tables (CAS insert)
+//   records longer than the look-ahead window go to a list and are redone from
+//   global memory by augment_deferred_kernel (same code, different byte source).
+//
+// No tensor cores: nothing here is a contraction.  No CPU fallback: every entry
+// point fails if the device is not sm_100.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/pantas_aug.h"
+#include "line_core.cuh"
+
+namespace {
+
+constexpr uint64_t KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint64_t STAMP_UNSET = 0x7FFFFFFFFFFFFFFFull;   // INT64_MAX: exported as int64, reduced with MIN
+constexpr uint32_t LEN_ABSENT = 0xFFFFFFFFu;
+
+struct __align__(32) NodeRec {
+    uint32_t len;
+    uint32_t pad;
+    unsigned long long nc;
+    unsigned long long il_stamp;
+    unsigned long long ol_stamp;
+};
+struct __align__(16) EdgeSlot {
+    unsigned long long key;
+    unsigned long long count;
+};
+struct __align__(32) SideSlot {
+    unsigned long long key;
+    unsigned long long count;
+    unsigned long long stamp;
+    unsigned long long pad;
+};
+
+// device scalars (unsigned long long each)
+enum { SC_REJ = 0, SC_LINES, SC_ERR, SC_NOVEL_USED, SC_SPARSE_USED, SC_DEFERRED_TOTAL, SC_TILES, SC_TILE_NEXT, SC_NDEFER, SC_COUNT = 16 };
+
+struct Tables {
+    NodeRec* nodes;
+    long long* il_adj;
+    long long* ol_adj;
+    EdgeSlot* edges;
+    uint32_t* edge_idx;
+    SideSlot* novel;
+    SideSlot* sparse;
+    unsigned long long* sc;
+    unsigned long long* deferred;
+    uint64_t n_nodes;
+    uint64_t edge_cap;
+    uint64_t novel_mask;
+    uint64_t sparse_mask;
+    uint64_t deferred_cap;
+    uint32_t min_id;
+    uint32_t edge_shift;
+};
+
+__device__ __forceinline__ uint64_t mix64(uint64_t h) {
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+    return h;
+}
+
+__device__ __forceinline__ void report_error(const Tables& T, int code, int64_t off) {
+    atomicMin(&T.sc[SC_ERR], ((unsigned long long)off << 8) | (unsigned long long)code);
+}
+
+// insert-or-increment in a 64-bit-key open-addressing table (linear probing, CAS claim)
+__device__ __forceinline__ void side_add(SideSlot* tab, uint64_t mask, unsigned long long* used, uint64_t key,
+                                         uint64_t stamp, const Tables& T, int full_code) {
+    uint64_t h = mix64(key) & mask;
+    for (uint64_t probes = 0; probes <= mask; probes++) {
+        unsigned long long k = *(volatile unsigned long long*)&tab[h].key;
+        if (k == KEY_EMPTY) {
+            k = atomicCAS(&tab[h].key, KEY_EMPTY, (unsigned long long)key);
+            if (k == KEY_EMPTY) {
+                unsigned long long n = atomicAdd(used, 1ull);
+                if (n * 4 >= (mask + 1) * 3) report_error(T, full_code, (int64_t)(stamp >> 2));
+                k = key;
+            }
+        }
+        if (k == key) {
+            atomicAdd(&tab[h].count, 1ull);
+            atomicMin(&tab[h].stamp, (unsigned long long)stamp);
+            return;
+        }
+        h = (h + 1) & mask;
+    }
+    report_error(T, full_code, (int64_t)(stamp >> 2));
+}
+
+struct DevSink {
+    const Tables& T;
+    uint32_t rej;
+    __device__ __forceinline__ explicit DevSink(const Tables& t) : T(t), rej(0) {}
+
+    __device__ __forceinline__ bool lookup(uint64_t id, uint32_t& idx, uint32_t& len) {
+        if (id < T.min_id) return false;
+        const uint64_t d = id - T.min_id;
+        if (d >= T.n_nodes) return false;
+        const uint32_t l = __ldg(&T.nodes[d].len);
+        if (l == LEN_ABSENT) return false;
+        idx = (uint32_t)d;
+        len = l;
+        return true;
+    }
+    __device__ __forceinline__ void count_node(uint32_t idx) { atomicAdd(&T.nodes[idx].nc, 1ull); }
+    __device__ __forceinline__ void dense(uint32_t idx, int64_t il, int64_t ol, uint64_t stamp) {
+        if (il != 1) atomicAdd((unsigned long long*)&T.il_adj[idx], (unsigned long long)(il - 1));
+        if (ol != 1) atomicAdd((unsigned long long*)&T.ol_adj[idx], (unsigned long long)(ol - 1));
+        // first-touch stamps: look (L2, always current), write only when we are earlier
+        const ulonglong2 st = __ldcg(reinterpret_cast<const ulonglong2*>(&T.nodes[idx].il_stamp));
+        if (il > 0 && stamp < st.x) atomicMin(&T.nodes[idx].il_stamp, (unsigned long long)stamp);
+        if (ol > 0 && stamp < st.y) atomicMin(&T.nodes[idx].ol_stamp, (unsigned long long)stamp);
+    }
+    __device__ __forceinline__ void sparse(uint32_t idx, int dir, int64_t pos, uint64_t stamp) {
+        const int64_t bias = 1ll << 30;
+        if (pos < -bias || pos >= bias) { report_error(T, pt::PT_U_POSITION, (int64_t)(stamp >> 2)); return; }
+        const uint64_t key = ((uint64_t)idx << 32) | ((uint64_t)dir << 31) | (uint64_t)(pos + bias);
+        side_add(T.sparse, T.sparse_mask, &T.sc[SC_SPARSE_USED], key, stamp, T, pt::PT_X_SPARSE_FULL);
+    }
+    __device__ __forceinline__ void edge(uint32_t a, uint32_t b, uint64_t stamp) {
+        const uint64_t key = ((uint64_t)a << 32) | b;
+        uint64_t i = (uint64_t)a << T.edge_shift;
+        for (;;) {
+            const unsigned long long k = __ldg(&T.edges[i].key);
+            if (k == key) { atomicAdd(&T.edges[i].count, 1ull); return; }
+            if (k == KEY_EMPTY) break;
+            if (++i == T.edge_cap) i = 0;
+        }
+        side_add(T.novel, T.novel_mask, &T.sc[SC_NOVEL_USED], key, stamp, T, pt::PT_X_NOVEL_FULL);
+    }
+    __device__ __forceinline__ void reject() { rej++; }
+    __device__ __forceinline__ void error(int code, int64_t off) { report_error(T, code, off); }
+};
+
+// ---------------------------------------------------------------- TMA helpers
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// 1-D bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------- main kernel
+
+struct ChunkArgs {
+    const uint8_t* gaf;
+    uint64_t nbytes;
+    int64_t file_off;
+    int64_t thr;
+    uint32_t tile;       // bytes per tile, multiple of 16
+    uint32_t over;       // look-ahead bytes after the tile, multiple of 16
+    uint32_t list_cap;   // line-start slots in shared memory
+    uint32_t n_tiles;
+};
+
+__device__ __forceinline__ void defer_line(const Tables& T, uint64_t chunk_pos, int64_t file_off) {
+    const unsigned long long j = atomicAdd(&T.sc[SC_NDEFER], 1ull);
+    if (j < T.deferred_cap) T.deferred[j] = chunk_pos;
+    else report_error(T, pt::PT_X_DEFER_FULL, file_off + (int64_t)chunk_pos);
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) augment_tiles_kernel(ChunkArgs A, Tables T) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t s_nlines;
+    __shared__ uint32_t s_tile;
+
+    const int tid = threadIdx.x;
+    uint8_t* buf = smem;                                      // [16 + tile + over]
+    const uint32_t buf_bytes = 16u + A.tile + A.over;
+    uint32_t* list = reinterpret_cast<uint32_t*>(smem + ((buf_bytes + 127u) & ~127u));
+
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+
+    DevSink sink(T);
+    const uint64_t nbytes16 = (A.nbytes + 15ull) & ~15ull;
+    uint32_t parity = 0;
+    unsigned long long my_lines = 0, my_tiles = 0;
+
+    for (;;) {
+        if (tid == 0) {
+            s_tile = (uint32_t)atomicAdd(&T.sc[SC_TILE_NEXT], 1ull);
+            s_nlines = 0;
+        }
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= A.n_tiles) break;
+
+        const uint64_t t0 = (uint64_t)tile * A.tile;
+        const uint64_t t1 = min(t0 + A.tile, A.nbytes);             // owned line starts are in [t0, t1)
+        const uint64_t lo = tile ? t0 - 16 : 0;
+        const uint64_t hi = min(t0 + A.tile + A.over, nbytes16);     // loaded bytes [lo, hi)
+        const uint32_t skip = tile ? 0u : 16u;                       // buffer position 16 == byte t0
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(hi - lo);
+            mbar_expect_tx(&mbar, bytes);
+            tma_load_1d(buf + skip, A.gaf + lo, bytes, &mbar);
+        }
+        mbar_wait(&mbar, parity);
+        parity ^= 1;
+
+        // ---- phase 1: cooperative scan of [t0 - 1, t1) for line starts, CR, non-ASCII
+        {
+            const uint32_t owned = (uint32_t)(t1 - t0);
+            const uint32_t v_end = (16u + owned + 15u) >> 4;
+            if (tile == 0 && tid == 0 && A.nbytes > 0) {
+                const uint32_t j = atomicAdd(&s_nlines, 1u);
+                if (j < A.list_cap) list[j] = 16u; else defer_line(T, 0, A.file_off);
+            }
+            for (uint32_t v = tid + (tile ? 0u : 1u); v < v_end; v += THREADS) {
+                const uint4 q4 = *reinterpret_cast<const uint4*>(buf + 16u * v);
+                const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
+                const uint64_t v_abs = t0 + 16ull * v - 16ull;      // file-chunk position of the vector
+                const bool tail = v_abs + 16 > A.nbytes;            // bytes past the chunk end are garbage
+                uint32_t any_hi = (w[0] | w[1] | w[2] | w[3]) & 0x80808080u;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t a = w[k] & 0x7F7F7F7Fu;
+                    // 0x80 in every byte whose low 7 bits are in [0x0A, 0x0D]
+                    uint32_t m = (a + 0x76767676u) & ~(a + 0x72727272u) & 0x80808080u;
+                    while (m) {
+                        const int byte = (__ffs(m) - 1) >> 3;
+                        m &= m - 1;
+                        const uint32_t x = 16u * v + 4u * k + byte;        // buffer position
+                        const uint64_t abs_pos = v_abs + 4u * k + byte;
+                        if (abs_pos >= A.nbytes) continue;
+                        const uint32_t c = (w[k] >> (8 * byte)) & 0xFFu;
+                        if (c == '\n') {
+                            if (x + 1 >= 16u && abs_pos + 1 < t1) {
+                                const uint32_t j = atomicAdd(&s_nlines, 1u);
+                                if (j < A.list_cap) list[j] = x + 1;
+                                else defer_line(T, abs_pos + 1, A.file_off);
+                            }
+                        } else if (c == '\r' && x >= 16u) {
+                            if (abs_pos + 1 < A.nbytes && buf[x + 1] != '\n')
+                                report_error(T, pt::PT_U_BARE_CR, A.file_off + (int64_t)abs_pos);
+                        }
+                    }
+                }
+                if (any_hi) {
+                    if (!tail && v >= 1) report_error(T, pt::PT_U_NON_ASCII, A.file_off + (int64_t)v_abs);
+                    else
+                        for (int b = 0; b < 16; b++)
+                            if (v_abs + b < A.nbytes && 16u * v + b >= 16u && buf[16u * v + b] >= 0x80)
+                                report_error(T, pt::PT_U_NON_ASCII, A.file_off + (int64_t)(v_abs + b));
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: one thread per record
+        {
+            const uint32_t total = s_nlines;
+            const uint32_t nl = min(total, A.list_cap);
+            if (tid == 0) { my_lines += total; my_tiles++; }
+            pt::LineCtx cx;
+            cx.s = buf;
+            cx.lim = (int)(16u + (uint32_t)(min(hi, A.nbytes) - t0));
+            cx.lim_final = (hi >= A.nbytes);
+            cx.base_off = A.file_off + (int64_t)t0 - 16;
+            for (uint32_t l = tid; l < nl; l += THREADS) {
+                const uint32_t p = list[l];
+                if (pt::process_line(cx, (int)p, A.thr, sink) == pt::LINE_DEFER)
+                    defer_line(T, t0 + p - 16u, A.file_off);
+            }
+        }
+        __syncthreads();   // every read of buf / list / s_nlines is done before the next tile lands
+    }
+
+    // rejected-record count: warp reduce, one RED per warp
+    uint32_t r = sink.rej;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if ((tid & 31) == 0 && r) atomicAdd(&T.sc[SC_REJ], (unsigned long long)r);
+    if (tid == 0) {
+        if (my_lines) atomicAdd(&T.sc[SC_LINES], my_lines);
+        if (my_tiles) atomicAdd(&T.sc[SC_TILES], my_tiles);
+    }
+}
+
+// Records that did not fit a tile's look-ahead window: same logic, bytes from global memory.
+__global__ void __launch_bounds__(128) augment_deferred_kernel(ChunkArgs A, Tables T) {
+    DevSink sink(T);
+    const unsigned long long n = min(T.sc[SC_NDEFER], (unsigned long long)T.deferred_cap);
+    for (unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; j < n;
+         j += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint64_t a = T.deferred[j];
+        pt::LineCtx cx;
+        cx.s = A.gaf + a;
+        const uint64_t rest = A.nbytes - a;
+        cx.lim = rest > 0x7fffffffull ? 0x7fffffff : (int)rest;
+        cx.lim_final = true;
+        cx.base_off = A.file_off + (int64_t)a;
+        pt::process_line(cx, 0, A.thr, sink);
+    }
+    uint32_t r = sink.rej;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if ((threadIdx.x & 31) == 0 && r) atomicAdd(&T.sc[SC_REJ], (unsigned long long)r);
+}
+
+// After both kernels of a chunk: fold the per-chunk scalars.
+__global__ void end_chunk_kernel(Tables T) {
+    T.sc[SC_DEFERRED_TOTAL] += min(T.sc[SC_NDEFER], (unsigned long long)T.deferred_cap);
+    T.sc[SC_NDEFER] = 0;
+    T.sc[SC_TILE_NEXT] = 0;
+}
+
+// ---------------------------------------------------------------- graph build / reset / export
+
+__global__ void init_nodes_kernel(NodeRec* nodes, const uint32_t* len, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        NodeRec r;
+        r.len = len[i];
+        r.pad = 0;
+        r.nc = 0;
+        r.il_stamp = STAMP_UNSET;
+        r.ol_stamp = STAMP_UNSET;
+        nodes[i] = r;
+    }
+}
+__global__ void clear_edges_kernel(EdgeSlot* e, uint32_t* edge_idx, uint64_t cap, int keys_too) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (keys_too) { e[i].key = KEY_EMPTY; edge_idx[i] = 0xFFFFFFFFu; }
+        e[i].count = 0;
+    }
+}
+__global__ void insert_edges_kernel(Tables T, const uint64_t* keys, uint64_t n_edges, unsigned long long* bad) {
+    for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < n_edges; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = keys[e];
+        const uint64_t from = key >> 32, to = key & 0xFFFFFFFFull;
+        if (from >= T.n_nodes || to >= T.n_nodes) { atomicAdd(bad, 1ull); continue; }
+        uint64_t i = from << T.edge_shift;
+        for (uint64_t probes = 0; probes < T.edge_cap; probes++) {
+            unsigned long long k = atomicCAS(&T.edges[i].key, KEY_EMPTY, (unsigned long long)key);
+            if (k == KEY_EMPTY) { T.edge_idx[i] = (uint32_t)e; break; }
+            if (k == key) { atomicAdd(bad, 1ull); break; }          // duplicate key: caller must de-duplicate
+            if (++i == T.edge_cap) i = 0;
+        }
+    }
+}
+__global__ void reset_nodes_kernel(NodeRec* nodes, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        nodes[i].nc = 0;
+        nodes[i].il_stamp = STAMP_UNSET;
+        nodes[i].ol_stamp = STAMP_UNSET;
+    }
+}
+__global__ void clear_side_kernel(SideSlot* s, uint64_t cap) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        SideSlot z;
+        z.key = KEY_EMPTY;
+        z.count = 0;
+        z.stamp = STAMP_UNSET;
+        z.pad = 0;
+        s[i] = z;
+    }
+}
+__global__ void export_nodes_kernel(Tables T, long long* sums, long long* stamps, uint64_t n_edges) {
+    const uint64_t N = T.n_nodes;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
+        const NodeRec r = T.nodes[i];
+        sums[i] = (long long)r.nc;
+        sums[N + i] = T.il_adj[i];
+        sums[2 * N + i] = T.ol_adj[i];
+        stamps[i] = (long long)r.il_stamp;
+        stamps[N + i] = (long long)r.ol_stamp;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        long long* tail = sums + 3 * N + n_edges;
+        tail[0] = (long long)T.sc[SC_REJ];
+        tail[1] = (long long)T.sc[SC_LINES];
+        tail[2] = 0;
+        tail[3] = 0;
+    }
+}
+__global__ void export_edges_kernel(Tables T, long long* rc) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < T.edge_cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t e = T.edge_idx[i];
+        if (e != 0xFFFFFFFFu) rc[e] = (long long)T.edges[i].count;
+    }
+}
+__global__ void compact_side_kernel(const SideSlot* s, uint64_t cap, unsigned long long* out, uint64_t rows,
+                                    unsigned long long* cursor) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const SideSlot v = s[i];
+        if (v.key == KEY_EMPTY) continue;
+        const unsigned long long j = atomicAdd(cursor, 1ull);
+        if (j < rows) {
+            out[3 * j] = v.key;
+            out[3 * j + 1] = v.count;
+            out[3 * j + 2] = v.stamp;
+        }
+    }
+}
+
+}  // namespace
+
+// ================================================================== host side
+
+struct pt_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+    bool own_stream;
+    cudaStream_t copy_stream;
+    cudaEvent_t ev_copied[2], ev_done[2], ev_t0, ev_t1;
+    bool have_graph;
+    Tables T;
+    uint64_t n_edges;
+    uint64_t novel_cap, sparse_cap;
+    unsigned long long* cursor;         // 2 compaction cursors
+    uint8_t* stage[2];
+    uint64_t stage_bytes;
+    int64_t next_ticket;
+    uint64_t launches;
+    uint32_t tile, over, list_cap, threads;
+    int ctas_per_sm;
+    char err[512];
+};
+
+static int fail_cuda(pt_ctx* c, cudaError_t e, const char* what) {
+    if (c) snprintf(c->err, sizeof c->err, "%s: %s", what, cudaGetErrorString(e));
+    return PT_ERR_CUDA;
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return fail_cuda(ctx, e_, #call);   \
+    } while (0)
+
+static int fail_msg(pt_ctx* c, int code, const char* msg) {
+    if (c) snprintf(c->err, sizeof c->err, "%s", msg);
+    return code;
+}
+
+static uint64_t pow2_at_least(uint64_t v) {
+    uint64_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    long x = strtol(v, NULL, 10);
+    return x > 0 ? (uint32_t)x : dflt;
+}
+static int grid_for(uint64_t n, int threads, int cap_blocks) {
+    uint64_t b = (n + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > (uint64_t)cap_blocks) b = cap_blocks;
+    return (int)b;
+}
+
+extern "C" {
+
+int pt_abi_version(void) { return PT_ABI_VERSION; }
+
+const char* pt_strerror(int code) {
+    switch (code) {
+        case 0: return "ok";
+        case PT_ERR_CUDA: return "CUDA runtime error";
+        case PT_ERR_ARG: return "bad argument";
+        case PT_ERR_STATE: return "call out of order";
+        case PT_ERR_NOMEM: return "out of memory";
+        case PT_ERR_NODEVICE: return "no sm_100 CUDA device";
+        case pt::PT_E_COLUMNS: return "GAF record has fewer than 12 columns (reference: IndexError)";
+        case pt::PT_E_MAPQ: return "MAPQ column is not an integer (reference: ValueError)";
+        case pt::PT_E_COORD: return "path length/start/end is not an integer (reference: ValueError)";
+        case pt::PT_E_NO_DV: return "record passes the filters but has no dv:f: tag (reference: ValueError)";
+        case pt::PT_E_EMPTY_PATH: return "path column holds no step (reference: AssertionError)";
+        case pt::PT_E_UNKNOWN_NODE: return "path step is not a node of the GFA (reference: KeyError)";
+        case pt::PT_E_CS_SHORT: return "cs string ends before the path does (reference: IndexError)";
+        case pt::PT_U_TILDE: return "unsupported: '~' op in cs string";
+        case pt::PT_U_NON_ASCII: return "unsupported: non-ASCII byte in GAF";
+        case pt::PT_U_BARE_CR: return "unsupported: lone carriage return in GAF";
+        case pt::PT_U_BIG_INT: return "unsupported: integer field too large";
+        case pt::PT_U_UNDERSCORE: return "unsupported: '_' inside an integer field";
+        case pt::PT_U_POSITION: return "unsupported: IL/OL position out of range";
+        case pt::PT_X_NOVEL_FULL: return "novel-link table full (raise PANTAS_NOVEL_CAP)";
+        case pt::PT_X_SPARSE_FULL: return "sparse IL/OL table full (raise PANTAS_SPARSE_CAP)";
+        case pt::PT_X_DEFER_FULL: return "long-record list full";
+        default: return "unknown code";
+    }
+}
+
+int pt_create(int device, pt_ctx** out) {
+    if (!out) return PT_ERR_ARG;
+    *out = NULL;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return PT_ERR_NODEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PT_ERR_NODEVICE;
+    if (prop.major != 10) return PT_ERR_NODEVICE;      // sm_100a cubin only; no fallback path exists
+    pt_ctx* ctx = (pt_ctx*)calloc(1, sizeof(pt_ctx));
+    if (!ctx) return PT_ERR_NOMEM;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess) { free(ctx); return PT_ERR_CUDA; }
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && e == cudaSuccess; k++) {
+        e = cudaEventCreateWithFlags(&ctx->ev_copied[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_t0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_t1);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->T.sc, SC_COUNT * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->cursor, 2 * sizeof(unsigned long long));
+    if (e != cudaSuccess) { free(ctx); return PT_ERR_CUDA; }
+    ctx->own_stream = true;
+    ctx->stage_bytes = (uint64_t)env_u32("PANTAS_STAGE_MB", 256) << 20;
+    ctx->tile = env_u32("PANTAS_TILE_KB", 64) << 10;
+    ctx->over = env_u32("PANTAS_OVER_KB", 4) << 10;
+    // byte-granular overrides (tests drive tiny tiles through the deferral path)
+    ctx->tile = (env_u32("PANTAS_TILE_BYTES", ctx->tile) + 15u) & ~15u;
+    ctx->over = (env_u32("PANTAS_OVER_BYTES", ctx->over) + 15u) & ~15u;
+    if (ctx->tile < 64) ctx->tile = 64;
+    if (ctx->over < 16) ctx->over = 16;
+    ctx->list_cap = env_u32("PANTAS_LIST_CAP", 1024);
+    ctx->threads = env_u32("PANTAS_THREADS", 256);
+    if (ctx->threads != 128 && ctx->threads != 256 && ctx->threads != 512) ctx->threads = 256;
+    *out = ctx;
+    return 0;
+}
+
+void pt_destroy(pt_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->T.nodes); cudaFree(ctx->T.il_adj); cudaFree(ctx->T.ol_adj); cudaFree(ctx->T.edges);
+    cudaFree(ctx->T.edge_idx); cudaFree(ctx->T.novel); cudaFree(ctx->T.sparse); cudaFree(ctx->T.sc);
+    cudaFree(ctx->T.deferred); cudaFree(ctx->cursor); cudaFree(ctx->stage[0]); cudaFree(ctx->stage[1]);
+    for (int k = 0; k < 2; k++) { cudaEventDestroy(ctx->ev_copied[k]); cudaEventDestroy(ctx->ev_done[k]); }
+    cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    free(ctx);
+}
+
+const char* pt_last_error(pt_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+int pt_set_stream(pt_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return PT_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return 0;
+}
+
+static int reset_counts_impl(pt_ctx* ctx) {
+    Tables& T = ctx->T;
+    const int cap = ctx->sm_count * 8;
+    reset_nodes_kernel<<<grid_for(T.n_nodes, 256, cap), 256, 0, ctx->stream>>>(T.nodes, T.n_nodes);
+    CK(cudaMemsetAsync(T.il_adj, 0, T.n_nodes * sizeof(long long), ctx->stream));
+    CK(cudaMemsetAsync(T.ol_adj, 0, T.n_nodes * sizeof(long long), ctx->stream));
+    clear_edges_kernel<<<grid_for(T.edge_cap, 256, cap), 256, 0, ctx->stream>>>(T.edges, T.edge_idx, T.edge_cap, 0);
+    clear_side_kernel<<<grid_for(T.novel_mask + 1, 256, cap), 256, 0, ctx->stream>>>(T.novel, T.novel_mask + 1);
+    clear_side_kernel<<<grid_for(T.sparse_mask + 1, 256, cap), 256, 0, ctx->stream>>>(T.sparse, T.sparse_mask + 1);
+    unsigned long long sc[SC_COUNT];
+    memset(sc, 0, sizeof sc);
+    sc[SC_ERR] = ~0ull;
+    CK(cudaMemcpyAsync(T.sc, sc, sizeof sc, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));       // sc[] is a stack buffer
+    CK(cudaGetLastError());
+    ctx->launches += 4;
+    return 0;
+}
+
+int pt_set_graph(pt_ctx* ctx, const uint32_t* node_len, uint64_t n_nodes, uint32_t min_id, const uint64_t* edge_keys,
+                 uint64_t n_edges, uint64_t novel_cap, uint64_t sparse_cap) {
+    if (!ctx || !node_len || n_nodes == 0 || (n_edges && !edge_keys)) return fail_msg(ctx, PT_ERR_ARG, "pt_set_graph: bad argument");
+    if (n_nodes >= 0xFFFFFFFFull || n_edges >= 0xFFFFFFFFull) return fail_msg(ctx, PT_ERR_ARG, "pt_set_graph: more than 2^32-2 nodes or links");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    Tables& T = ctx->T;
+    cudaFree(T.nodes); cudaFree(T.il_adj); cudaFree(T.ol_adj); cudaFree(T.edges); cudaFree(T.edge_idx);
+    cudaFree(T.novel); cudaFree(T.sparse);
+    T.nodes = NULL; T.il_adj = T.ol_adj = NULL; T.edges = NULL; T.edge_idx = NULL; T.novel = T.sparse = NULL;
+    ctx->have_graph = false;
+
+    T.n_nodes = n_nodes;
+    T.min_id = min_id;
+    // home slot of an edge = from_idx << shift: >= 2 slots per node and load factor <= 0.6
+    uint32_t shift = 1;
+    while (((n_nodes << shift) * 6) / 10 < n_edges) shift++;
+    T.edge_shift = shift;
+    T.edge_cap = n_nodes << shift;
+    if (!novel_cap) novel_cap = env_u32("PANTAS_NOVEL_CAP", 0);
+    if (!sparse_cap) sparse_cap = env_u32("PANTAS_SPARSE_CAP", 0);
+    if (!novel_cap) novel_cap = (n_edges / 2 > (1u << 20)) ? n_edges / 2 : (1u << 20);
+    if (!sparse_cap) sparse_cap = (n_nodes / 2 > (1u << 20)) ? n_nodes / 2 : (1u << 20);
+    ctx->novel_cap = pow2_at_least(novel_cap);
+    ctx->sparse_cap = pow2_at_least(sparse_cap);
+    T.novel_mask = ctx->novel_cap - 1;
+    T.sparse_mask = ctx->sparse_cap - 1;
+    ctx->n_edges = n_edges;
+
+    CK(cudaMalloc(&T.nodes, n_nodes * sizeof(NodeRec)));
+    CK(cudaMalloc(&T.il_adj, n_nodes * sizeof(long long)));
+    CK(cudaMalloc(&T.ol_adj, n_nodes * sizeof(long long)));
+    CK(cudaMalloc(&T.edges, T.edge_cap * sizeof(EdgeSlot)));
+    CK(cudaMalloc(&T.edge_idx, T.edge_cap * sizeof(uint32_t)));
+    CK(cudaMalloc(&T.novel, ctx->novel_cap * sizeof(SideSlot)));
+    CK(cudaMalloc(&T.sparse, ctx->sparse_cap * sizeof(SideSlot)));
+
+    uint32_t* d_len = NULL;
+    uint64_t* d_keys = NULL;
+    unsigned long long* d_bad = NULL;
+    CK(cudaMalloc(&d_len, n_nodes * sizeof(uint32_t)));
+    CK(cudaMalloc(&d_keys, (n_edges ? n_edges : 1) * sizeof(uint64_t)));
+    CK(cudaMalloc(&d_bad, sizeof(unsigned long long)));
+    CK(cudaMemcpyAsync(d_len, node_len, n_nodes * sizeof(uint32_t), cudaMemcpyDefault, ctx->stream));
+    if (n_edges) CK(cudaMemcpyAsync(d_keys, edge_keys, n_edges * sizeof(uint64_t), cudaMemcpyDefault, ctx->stream));
+    CK(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), ctx->stream));
+    const int cap = ctx->sm_count * 8;
+    init_nodes_kernel<<<grid_for(n_nodes, 256, cap), 256, 0, ctx->stream>>>(T.nodes, d_len, n_nodes);
+    clear_edges_kernel<<<grid_for(T.edge_cap, 256, cap), 256, 0, ctx->stream>>>(T.edges, T.edge_idx, T.edge_cap, 1);
+    if (n_edges) insert_edges_kernel<<<grid_for(n_edges, 256, cap), 256, 0, ctx->stream>>>(T, d_keys, n_edges, d_bad);
+    unsigned long long bad = 0;
+    CK(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    cudaFree(d_len); cudaFree(d_keys); cudaFree(d_bad);
+    ctx->launches += 3;
+    if (bad) return fail_msg(ctx, PT_ERR_ARG, "pt_set_graph: edge_keys hold duplicates or out-of-range node indices");
+    ctx->have_graph = true;
+    return reset_counts_impl(ctx);
+}
+
+int pt_reset_counts(pt_ctx* ctx) {
+    if (!ctx || !ctx->have_graph) return fail_msg(ctx, PT_ERR_STATE, "pt_reset_counts: no graph");
+    CK(cudaSetDevice(ctx->device));
+    return reset_counts_impl(ctx);
+}
+
+static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, uint64_t file_offset, int64_t thr) {
+    if (nbytes == 0) return 0;
+    if (((uintptr_t)gaf_dev & 15) != 0) return fail_msg(ctx, PT_ERR_ARG, "GAF chunk must be 16-byte aligned");
+    Tables& T = ctx->T;
+    // long-record list: records longer than the look-ahead, plus list overflow
+    const uint64_t want = nbytes / ctx->over + nbytes / (64ull * ctx->list_cap) + 4096;
+    if (want > T.deferred_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(T.deferred);
+        T.deferred = NULL;
+        T.deferred_cap = 0;
+        CK(cudaMalloc(&T.deferred, want * sizeof(unsigned long long)));
+        T.deferred_cap = want;
+    }
+    ChunkArgs A;
+    A.gaf = gaf_dev;
+    A.nbytes = nbytes;
+    A.file_off = (int64_t)file_offset;
+    A.thr = thr;
+    A.tile = ctx->tile;
+    A.over = ctx->over;
+    A.list_cap = ctx->list_cap;
+    const uint64_t n_tiles = (nbytes + ctx->tile - 1) / ctx->tile;
+    if (n_tiles > 0xFFFFFFF0ull) return fail_msg(ctx, PT_ERR_ARG, "chunk too large");
+    A.n_tiles = (uint32_t)n_tiles;
+    const size_t smem = ((16 + (size_t)ctx->tile + ctx->over + 127) & ~(size_t)127) + (size_t)ctx->list_cap * 4;
+    void (*kern)(ChunkArgs, Tables) = ctx->threads == 128   ? augment_tiles_kernel<128>
+                                      : ctx->threads == 512 ? augment_tiles_kernel<512>
+                                                            : augment_tiles_kernel<256>;
+    if (ctx->ctas_per_sm == 0) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (int)ctx->threads, smem));
+        if (occ < 1) return fail_msg(ctx, PT_ERR_ARG, "tile does not fit shared memory");
+        ctx->ctas_per_sm = occ;
+    }
+    uint64_t grid = (uint64_t)ctx->sm_count * ctx->ctas_per_sm;
+    if (grid > n_tiles) grid = n_tiles;
+    kern<<<(unsigned)grid, ctx->threads, smem, ctx->stream>>>(A, T);
+    augment_deferred_kernel<<<ctx->sm_count, 128, 0, ctx->stream>>>(A, T);
+    end_chunk_kernel<<<1, 1, 0, ctx->stream>>>(T);
+    CK(cudaGetLastError());
+    ctx->launches += 3;
+    return 0;
+}
+
+int pt_process_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, uint64_t file_offset, int64_t mapq_thr) {
+    if (!ctx || !ctx->have_graph) return fail_msg(ctx, PT_ERR_STATE, "pt_process_chunk: no graph");
+    if (nbytes && !gaf_dev) return fail_msg(ctx, PT_ERR_ARG, "pt_process_chunk: null chunk");
+    CK(cudaSetDevice(ctx->device));
+    return launch_chunk(ctx, gaf_dev, nbytes, file_offset, mapq_thr);
+}
+
+int pt_set_stage_bytes(pt_ctx* ctx, uint64_t bytes) {
+    if (!ctx || bytes < (1u << 16)) return PT_ERR_ARG;
+    if (ctx->stage[0]) return fail_msg(ctx, PT_ERR_STATE, "staging buffers already allocated");
+    ctx->stage_bytes = (bytes + 15) & ~15ull;
+    return 0;
+}
+uint64_t pt_stage_bytes(pt_ctx* ctx) { return ctx ? ctx->stage_bytes : 0; }
+
+int64_t pt_process_host(pt_ctx* ctx, const uint8_t* gaf_host, uint64_t nbytes, uint64_t file_offset, int64_t mapq_thr) {
+    if (!ctx || !ctx->have_graph) return fail_msg(ctx, PT_ERR_STATE, "pt_process_host: no graph");
+    if (nbytes > ctx->stage_bytes) return fail_msg(ctx, PT_ERR_ARG, "pt_process_host: chunk larger than pt_stage_bytes()");
+    if (nbytes && !gaf_host) return fail_msg(ctx, PT_ERR_ARG, "pt_process_host: null chunk");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->stage[0]) {
+        CK(cudaMalloc(&ctx->stage[0], ctx->stage_bytes + 16));
+        CK(cudaMalloc(&ctx->stage[1], ctx->stage_bytes + 16));
+    }
+    const int64_t ticket = ctx->next_ticket++;
+    const int k = (int)(ticket & 1);
+    if (ticket >= 2) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[k], 0));   // stage k is free again
+    if (nbytes) CK(cudaMemcpyAsync(ctx->stage[k], gaf_host, nbytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_copied[k], ctx->copy_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[k], 0));
+    int rc = launch_chunk(ctx, ctx->stage[k], nbytes, file_offset, mapq_thr);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev_done[k], ctx->stream));
+    return ticket;
+}
+
+int pt_wait_copy(pt_ctx* ctx, int64_t ticket) {
+    if (!ctx || ticket < 0 || ticket >= ctx->next_ticket) return PT_ERR_ARG;
+    if (ticket + 2 < ctx->next_ticket) return 0;          // its stage has been re-used: long done
+    CK(cudaEventSynchronize(ctx->ev_copied[ticket & 1]));
+    return 0;
+}
+
+int pt_sync(pt_ctx* ctx) {
+    if (!ctx) return PT_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int pt_error(pt_ctx* ctx, uint64_t* bad_offset, int* code) {
+    if (!ctx || !ctx->have_graph) return fail_msg(ctx, PT_ERR_STATE, "pt_error: no graph");
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long w = 0;
+    CK(cudaMemcpyAsync(&w, ctx->T.sc + SC_ERR, sizeof w, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (w == ~0ull) {
+        if (code) *code = 0;
+        if (bad_offset) *bad_offset = 0;
+    } else {
+        if (code) *code = (int)(w & 0xFF);
+        if (bad_offset) *bad_offset = w >> 8;
+    }
+    return 0;
+}
+
+int pt_finalize(pt_ctx* ctx, uint64_t* n_novel, uint64_t* n_sparse) {
+    if (!ctx || !ctx->have_graph) return fail_msg(ctx, PT_ERR_STATE, "pt_finalize: no graph");
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long sc[SC_COUNT];
+    CK(cudaMemcpyAsync(sc, ctx->T.sc, sizeof sc, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    if (n_novel) *n_novel = sc[SC_NOVEL_USED];
+    if (n_sparse) *n_sparse = sc[SC_SPARSE_USED];
+    return 0;
+}
+
+int pt_export_dense(pt_ctx* ctx, int64_t* sums_dev, uint64_t sums_len, int64_t* stamps_dev, uint64_t stamps_len) {
+    if (!ctx || !ctx->have_graph) return fail_msg(ctx, PT_ERR_STATE, "pt_export_dense: no graph");
+    const uint64_t N = ctx->T.n_nodes, E = ctx->n_edges;
+    if (!sums_dev || !stamps_dev || sums_len < 3 * N + E + 4 || stamps_len < 2 * N)
+        return fail_msg(ctx, PT_ERR_ARG, "pt_export_dense: buffers too small");
+    CK(cudaSetDevice(ctx->device));
+    const int cap = ctx->sm_count * 8;
+    if (E) CK(cudaMemsetAsync(sums_dev + 3 * N, 0, E * sizeof(int64_t), ctx->stream));
+    export_nodes_kernel<<<grid_for(N, 256, cap), 256, 0, ctx->stream>>>(ctx->T, (long long*)sums_dev, (long long*)stamps_dev, E);
+    export_edges_kernel<<<grid_for(ctx->T.edge_cap, 256, cap), 256, 0, ctx->stream>>>(ctx->T, (long long*)sums_dev + 3 * N);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+    return 0;
+}
+
+int pt_export_side(pt_ctx* ctx, uint64_t* novel_dev, uint64_t novel_rows, uint64_t* sparse_dev, uint64_t sparse_rows) {
+    if (!ctx || !ctx->have_graph) return fail_msg(ctx, PT_ERR_STATE, "pt_export_side: no graph");
+    CK(cudaSetDevice(ctx->device));
+    const int cap = ctx->sm_count * 8;
+    CK(cudaMemsetAsync(ctx->cursor, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (novel_rows && novel_dev)
+        compact_side_kernel<<<grid_for(ctx->novel_cap, 256, cap), 256, 0, ctx->stream>>>(
+            ctx->T.novel, ctx->novel_cap, (unsigned long long*)novel_dev, novel_rows, ctx->cursor);
+    if (sparse_rows && sparse_dev)
+        compact_side_kernel<<<grid_for(ctx->sparse_cap, 256, cap), 256, 0, ctx->stream>>>(
+            ctx->T.sparse, ctx->sparse_cap, (unsigned long long*)sparse_dev, sparse_rows, ctx->cursor + 1);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+    return 0;
+}
+
+int pt_timer_start(pt_ctx* ctx) {
+    if (!ctx) return PT_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev_t0, ctx->stream));
+    return 0;
+}
+int pt_timer_stop(pt_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return PT_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev_t1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev_t1));
+    CK(cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1));
+    return 0;
+}
+
+int pt_stats(pt_ctx* ctx, uint64_t* kernel_launches, uint64_t* deferred_lines, uint64_t* tiles) {
+    if (!ctx) return PT_ERR_ARG;
+    if (kernel_launches) *kernel_launches = ctx->launches;
+    if (ctx->have_graph && (deferred_lines || tiles)) {
+        CK(cudaSetDevice(ctx->device));
+        unsigned long long sc[SC_COUNT];
+        CK(cudaMemcpyAsync(sc, ctx->T.sc, sizeof sc, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (deferred_lines) *deferred_lines = sc[SC_DEFERRED_TOTAL];
+        if (tiles) *tiles = sc[SC_TILES];
+    } else {
+        if (deferred_lines) *deferred_lines = 0;
+        if (tiles) *tiles = 0;
+    }
+    return 0;
+}
+
+}  // extern "C"

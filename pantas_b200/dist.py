@@ -1,0 +1,53 @@
+"""Cross-rank reduction of augment results with torch.distributed.
+
+One process per GPU.  The data path has no collective; the only exchange is this
+one-shot reduction after the last chunk: ONE all_reduce(SUM) over the int64
+counter buffer [NC | IL0adj | OLadj | RC | rej, n_lines] and one all_reduce(MIN)
+over the first-touch stamps (NCCL over NVLink on the GPU box, gloo in the CPU
+tests), plus an all_gather of the two small side tables.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .counts import FlatResult, merge_side
+
+ERR_NONE = (1 << 63) - 1
+
+
+def reduce_error(err_word: int, device, group=None) -> int:
+    """min over ranks of (offset << 8 | code); ERR_NONE if no rank saw an error."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([err_word], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return int(t.item())
+
+
+def allreduce_results(sums, stamps, novel, sparse, n_nodes: int, n_edges: int, group=None) -> FlatResult:
+    """sums/stamps/novel/sparse: torch tensors (CUDA under NCCL, CPU under gloo).
+    Returns the job-wide FlatResult on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(stamps, op=dist.ReduceOp.MIN, group=group)
+
+    def gather_rows(rows):
+        rows = rows.reshape(-1, 3).contiguous()
+        n = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n, group=group)
+        sizes = [int(s.item()) for s in sizes]
+        m = max(max(sizes), 1)
+        pad = torch.zeros((m, 3), dtype=rows.dtype, device=rows.device)
+        pad[: rows.shape[0]] = rows
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad, group=group)
+        parts = [b[:s].cpu().numpy().view(np.uint64).reshape(-1, 3) for b, s in zip(bufs, sizes)]
+        return merge_side(parts)
+
+    return FlatResult(n_nodes, n_edges, sums.cpu().numpy(), stamps.cpu().numpy(),
+                      gather_rows(novel), gather_rows(sparse))

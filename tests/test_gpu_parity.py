@@ -1,0 +1,156 @@
+"""Parity of the CUDA path (through the C ABI) with the reference / oracle.  B200 only."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+import fuzzgen
+from conftest import GOLDEN, UNSUPPORTED_BY_DESIGN
+from oracle.oracle import run_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(**env):
+    from pantas_b200.engine import AugmentEngine
+
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return AugmentEngine(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def gpu_pipeline(tmp_path, gfa: str, gaf: str, thr=20, eng=None, via_host=False, chunks=1):
+    """-> ('ok', stdout, rej) | ('raise', code) | ('unsupported', code)"""
+    import torch
+
+    from pantas_b200.counts import Counts
+    from pantas_b200.errors import PantasDataError, UnsupportedInput
+    from pantas_b200.gfa import load_graph, write_augmented
+    from pantas_b200.shard import shard_bounds_bytes
+
+    gp = tmp_path / "g.gfa"
+    gp.write_bytes(gfa.encode())
+    try:
+        graph = load_graph(str(gp))
+    except PantasDataError:
+        return ("raise", 0)
+    eng = eng or _engine()
+    eng.set_graph(graph)
+    data = np.frombuffer(gaf.encode(), dtype=np.uint8)
+    bounds = shard_bounds_bytes(data, chunks) if data.size else [0, 0]
+    keep = []
+    for lo, hi in zip(bounds, bounds[1:]):
+        n = hi - lo
+        if via_host:
+            h = torch.zeros(n + 16, dtype=torch.uint8).pin_memory()
+            h[:n] = torch.from_numpy(data[lo:hi].copy())
+            keep.append(h)
+            t = eng.process_host(h.data_ptr(), n, lo, thr)
+            eng.wait_copy(t)
+        else:
+            d = torch.zeros(n + 16, dtype=torch.uint8, device="cuda")
+            d[:n] = torch.from_numpy(data[lo:hi].copy()).cuda()
+            keep.append(d)
+            eng.process_device(d, n, lo, thr)
+    try:
+        eng.check_data_error()
+    except PantasDataError as e:
+        return ("raise", e.code)
+    except UnsupportedInput as e:
+        return ("unsupported", e.code)
+    counts = Counts.from_flat(eng.export())
+    out = io.StringIO()
+    try:
+        write_augmented(str(gp), graph, counts, out)
+    except PantasDataError:
+        return ("raise", 0)
+    return ("ok", out.getvalue().encode(), counts.rej)
+
+
+def check_golden(case, res):
+    if case["name"] in UNSUPPORTED_BY_DESIGN:
+        assert res[0] == "unsupported", (case["name"], res)
+    elif case["returncode"] != 0:
+        assert res[0] == "raise", (case["name"], res)
+    else:
+        assert res[0] == "ok", (case["name"], res)
+        assert res[1] == case["stdout"], case["name"]
+        assert res[2] == case["rej"], case["name"]
+
+
+def test_library_is_native():
+    from pantas_b200 import _lib
+
+    lib = _lib.load_library()
+    assert lib.pt_abi_version() == 1
+
+
+def test_golden_cases_device_buffers(tmp_path):
+    eng = _engine()
+    for case in GOLDEN:
+        thr = 20 if case["thr"] is None else case["thr"]
+        check_golden(case, gpu_pipeline(tmp_path, case["gfa"], case["gaf"], thr, eng=eng))
+
+
+def test_golden_cases_host_buffers(tmp_path):
+    eng = _engine()
+    for case in GOLDEN:
+        thr = 20 if case["thr"] is None else case["thr"]
+        check_golden(case, gpu_pipeline(tmp_path, case["gfa"], case["gaf"], thr, eng=eng, via_host=True))
+
+
+@pytest.mark.parametrize("tile,over,listcap", [(64, 32, 1024), (256, 64, 2), (1024, 16, 1024), (4096, 4096, 8)])
+def test_golden_tiny_tiles(tile, over, listcap, tmp_path):
+    """Tile boundaries, look-ahead overflow (deferred records) and list overflow change nothing."""
+    eng = _engine(PANTAS_TILE_BYTES=tile, PANTAS_OVER_BYTES=over, PANTAS_LIST_CAP=listcap)
+    for case in GOLDEN:
+        if "\r" in case["gaf"]:
+            continue
+        thr = 20 if case["thr"] is None else case["thr"]
+        check_golden(case, gpu_pipeline(tmp_path, case["gfa"], case["gaf"], thr, eng=eng))
+
+
+@pytest.mark.parametrize("threads", [128, 512])
+def test_golden_other_block_sizes(threads, tmp_path):
+    eng = _engine(PANTAS_THREADS=threads, PANTAS_TILE_KB=32)
+    for case in GOLDEN[:80]:
+        thr = 20 if case["thr"] is None else case["thr"]
+        check_golden(case, gpu_pipeline(tmp_path, case["gfa"], case["gaf"], thr, eng=eng))
+
+
+@pytest.mark.parametrize("seed", range(9000, 9030))
+def test_fuzz_vs_oracle(seed, tmp_path):
+    gfa, gaf = fuzzgen.make_case(seed, n_nodes=10 + seed % 40, n_reads=400, weird=(seed % 2 == 0),
+                                 crlf=(seed % 6 == 0), trailing_newline=(seed % 4 != 0))
+    orc = run_oracle(gaf.encode(), gfa.encode())
+    assert orc.rc == 0
+    eng = _engine(PANTAS_TILE_BYTES=[65536, 2048, 512][seed % 3], PANTAS_OVER_BYTES=[4096, 256, 64][seed % 3])
+    res = gpu_pipeline(tmp_path, gfa, gaf, eng=eng, chunks=1 + seed % 3, via_host=(seed % 5 == 0))
+    assert res[0] == "ok", res
+    assert res[1] == orc.out
+    assert res[2] == orc.rej
+
+
+def test_rerun_after_reset_is_identical(tmp_path):
+    gfa, gaf = fuzzgen.make_case(4242, n_nodes=30, n_reads=500)
+    eng = _engine()
+    a = gpu_pipeline(tmp_path, gfa, gaf, eng=eng)
+    eng.reset()
+    b = gpu_pipeline(tmp_path, gfa, gaf, eng=eng)
+    assert a == b and a[0] == "ok"
+
+
+def test_no_graph_is_an_error():
+    from pantas_b200.errors import NativeLibraryError
+
+    eng = _engine()
+    with pytest.raises(NativeLibraryError):
+        eng.reset()
