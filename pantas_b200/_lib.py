@@ -36,6 +36,8 @@ SIGNATURES = {
     "pt_export_side": (ctypes.c_int, [c_ctx, vp, u64, vp, u64]),
     "pt_timer_start": (ctypes.c_int, [c_ctx]),
     "pt_timer_stop": (ctypes.c_int, [c_ctx, ctypes.POINTER(ctypes.c_float)]),
+    "pt_profile_enable": (ctypes.c_int, [c_ctx, ctypes.c_int]),
+    "pt_kernel_time": (ctypes.c_int, [c_ctx, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(u64)]),
     "pt_stats": (ctypes.c_int, [c_ctx, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(u64)]),
 }
 

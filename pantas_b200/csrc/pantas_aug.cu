@@ -463,6 +463,9 @@ struct pt_ctx {
     uint64_t launches;
     uint32_t tile, over, list_cap, threads;
     int ctas_per_sm;
+    bool profile;
+    cudaEvent_t* prof_ev;        // pairs
+    uint32_t prof_n, prof_cap;
     char err[512];
 };
 
@@ -582,6 +585,8 @@ void pt_destroy(pt_ctx* ctx) {
     cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_stream);
+    for (uint32_t k = 0; k < ctx->prof_cap; k++) cudaEventDestroy(ctx->prof_ev[k]);
+    free(ctx->prof_ev);
     free(ctx);
 }
 
@@ -721,7 +726,22 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
     }
     uint64_t grid = (uint64_t)ctx->sm_count * ctx->ctas_per_sm;
     if (grid > n_tiles) grid = n_tiles;
+    if (ctx->profile) {
+        if (ctx->prof_n + 2 > ctx->prof_cap) {
+            uint32_t nc = ctx->prof_cap ? ctx->prof_cap * 2 : 64;
+            cudaEvent_t* ne = (cudaEvent_t*)realloc(ctx->prof_ev, nc * sizeof(cudaEvent_t));
+            if (!ne) return fail_msg(ctx, PT_ERR_NOMEM, "profile events");
+            ctx->prof_ev = ne;
+            for (uint32_t k = ctx->prof_cap; k < nc; k++) CK(cudaEventCreate(&ctx->prof_ev[k]));
+            ctx->prof_cap = nc;
+        }
+        CK(cudaEventRecord(ctx->prof_ev[ctx->prof_n], ctx->stream));
+    }
     kern<<<(unsigned)grid, ctx->threads, smem, ctx->stream>>>(A, T);
+    if (ctx->profile) {
+        CK(cudaEventRecord(ctx->prof_ev[ctx->prof_n + 1], ctx->stream));
+        ctx->prof_n += 2;
+    }
     augment_deferred_kernel<<<ctx->sm_count, 128, 0, ctx->stream>>>(A, T);
     end_chunk_kernel<<<1, 1, 0, ctx->stream>>>(T);
     CK(cudaGetLastError());
@@ -851,6 +871,28 @@ int pt_timer_stop(pt_ctx* ctx, float* ms) {
     CK(cudaEventRecord(ctx->ev_t1, ctx->stream));
     CK(cudaEventSynchronize(ctx->ev_t1));
     CK(cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1));
+    return 0;
+}
+
+int pt_profile_enable(pt_ctx* ctx, int on) {
+    if (!ctx) return PT_ERR_ARG;
+    ctx->profile = on != 0;
+    return 0;
+}
+
+int pt_kernel_time(pt_ctx* ctx, float* ms_total, uint64_t* launches) {
+    if (!ctx) return PT_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float tot = 0;
+    for (uint32_t k = 0; k + 1 < ctx->prof_n; k += 2) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->prof_ev[k], ctx->prof_ev[k + 1]));
+        tot += ms;
+    }
+    if (ms_total) *ms_total = tot;
+    if (launches) *launches = ctx->prof_n / 2;
+    ctx->prof_n = 0;
     return 0;
 }
 

@@ -136,6 +136,15 @@ class AugmentEngine:
         self._check(self.lib.pt_timer_stop(self._ctx, ctypes.byref(ms)))
         return float(ms.value)
 
+    def profile(self, on: bool = True):
+        self._check(self.lib.pt_profile_enable(self._ctx, 1 if on else 0))
+
+    def kernel_time(self):
+        """(summed ms of augment_tiles_kernel, launches) since the last call."""
+        ms, n = ctypes.c_float(), ctypes.c_uint64()
+        self._check(self.lib.pt_kernel_time(self._ctx, ctypes.byref(ms), ctypes.byref(n)))
+        return float(ms.value), int(n.value)
+
     def stats(self) -> dict:
         a, b, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
         self._check(self.lib.pt_stats(self._ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
