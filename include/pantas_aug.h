@@ -121,9 +121,9 @@ int pt_export_side(pt_ctx* ctx, uint64_t* novel_dev, uint64_t novel_rows, uint64
 int pt_timer_start(pt_ctx* ctx);
 int pt_timer_stop(pt_ctx* ctx, float* ms);     /* synchronises on the stop event */
 
-/* Per-kernel timing of the dominant kernel (augment_tiles_kernel): when enabled,
- * every chunk records a CUDA event pair around that kernel alone on the
- * context's stream.  pt_kernel_time() synchronises and returns the summed
+/* Timing of the augment pass alone (augment_tiles_kernel + the second-pass
+ * kernel for records with a non-trivial cs string): when enabled, every chunk
+ * records a CUDA event pair around those launches on the context's stream.  pt_kernel_time() synchronises and returns the summed
  * duration and the number of launches since the last call (then clears them). */
 int pt_profile_enable(pt_ctx* ctx, int on);
 int pt_kernel_time(pt_ctx* ctx, float* ms_total, uint64_t* launches);

@@ -38,4 +38,6 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build_library(force=True, verbose=True))
+    import sys
+
+    print(build_library(force=True, verbose="-v" in sys.argv))

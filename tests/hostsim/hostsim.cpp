@@ -31,17 +31,21 @@ struct HostSink {
     int64_t rej = 0;
     uint64_t err = UINT64_MAX;                      // (offset << 8) | code, min wins
 
-    bool lookup(uint64_t id, uint32_t& idx, uint32_t& len) {
+    struct Stamps { uint64_t il, ol; };
+    struct EdgePf { int unused; };
+    bool id_to_idx(uint64_t id, uint32_t& idx) {
         if (id < min_id) return false;
         uint64_t d = id - min_id;
         if (d >= n_nodes) return false;
-        if (node_len[d] == 0xFFFFFFFFu) return false;
         idx = (uint32_t)d;
-        len = node_len[d];
         return true;
     }
+    uint32_t load_len(uint32_t idx) { return node_len[idx]; }
+    Stamps load_stamps(uint32_t idx) { return Stamps{il_stamp[idx], ol_stamp[idx]}; }
+    void edge_pf_init(EdgePf& pf) { pf.unused = 0; }
+    void prefetch_edge(EdgePf&, uint32_t) {}
     void count_node(uint32_t idx) { nc[idx]++; }
-    void dense(uint32_t idx, int64_t il, int64_t ol, uint64_t stamp) {
+    void dense(uint32_t idx, int64_t il, int64_t ol, uint64_t stamp, const Stamps&) {
         il_adj[idx] += il - 1;
         ol_adj[idx] += ol - 1;
         if (il > 0) il_stamp[idx] = std::min(il_stamp[idx], stamp);
@@ -58,7 +62,7 @@ struct HostSink {
         uint64_t key = ((uint64_t)idx << 32) | ((uint64_t)dir << 31) | (uint64_t)(pos + bias);
         sparse_ev(key, stamp, sparse_tab);
     }
-    void edge(uint32_t a, uint32_t b, uint64_t stamp) {
+    void edge(uint32_t a, uint32_t b, uint64_t stamp, const EdgePf&) {
         uint64_t key = ((uint64_t)a << 32) | b;
         auto it = known.find(key);
         if (it != known.end()) rc[it->second]++;
@@ -103,6 +107,11 @@ int hostsim_run(const uint8_t* gaf, uint64_t nbytes, uint64_t file_off, int64_t 
     sink.ol_stamp.assign(n_nodes, (uint64_t)INT64_MAX);
     for (uint64_t e = 0; e < n_edges; e++) sink.known.emplace(edge_keys[e], e);
 
+    // the device buffers are readable up to the next multiple of 16 past the data; give the
+    // host copy the same slack (SWAR loads touch whole aligned words)
+    std::vector<uint8_t> padded(nbytes + 64, (uint8_t)'\n');
+    if (nbytes) memcpy(padded.data(), gaf, nbytes);
+    gaf = padded.data();
     uint64_t n_lines = 0, n_deferred = 0;
     // cooperative-scan equivalents: non-ASCII, bare CR
     for (uint64_t i = 0; i < nbytes; i++) {
