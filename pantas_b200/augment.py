@@ -130,6 +130,13 @@ def main(argv, out=None, err=None) -> int:
 
         from .dist import ERR_NONE, allreduce_results, reduce_error
 
+        # stdout carries the GFA and nothing else: NCCL prints its version banner on fd 1,
+        # so park the real stdout and point fd 1 at stderr until the writer runs
+        if out is sys.stdout:
+            sys.stdout.flush()
+            saved_fd = os.dup(1)
+            os.dup2(2, 1)
+            out = os.fdopen(saved_fd, "w")
         torch.cuda.set_device(local_rank)
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -157,6 +164,7 @@ def main(argv, out=None, err=None) -> int:
     print(f"Rejected alignments: {counts.rej}", file=err)  # REF:375
     print("Annotating GFA", file=err)                      # REF:376
     write_augmented(gfa_file, graph, counts, out)
+    out.flush()
     return 0
 
 
