@@ -195,6 +195,33 @@ PT_HD int parse_py_int(const uint8_t* s, int a, int b, int64_t& out) {
     return 1;
 }
 
+// float(text) > 0.1 for the regex match dv:f:(\d+(\.\d+)?) starting at s[d0] (a digit), where the
+// bytes [d0, b) are all there is (b = end of the token).  Same exact decimal rule as front_line().
+PT_HD bool dv_token_greater(const uint8_t* s, int d0, int b) {
+    int t = d0;
+    bool int_nonzero = false;
+    while (t < b && is_digit(s[t])) { int_nonzero |= (s[t] != '0'); t++; }
+    if (int_nonzero) return true;
+    if (!(t + 1 < b && s[t] == '.' && is_digit(s[t + 1]))) return false;
+    t++;
+    const uint32_t f0 = s[t];
+    if (f0 == '0') return false;
+    if (f0 >= '2') return true;
+    int k = 0, cmp = 0;
+    while (t < b && is_digit(s[t])) {
+        if (cmp == 0) {
+            const uint32_t fd = s[t] - '0', md = dv_midpoint_digit(k);
+            cmp = fd > md ? 1 : (fd < md ? -1 : 0);
+        }
+        k++;
+        t++;
+    }
+    if (cmp == 0)
+        for (; k < 57; k++)
+            if (dv_midpoint_digit(k) != 0) { cmp = -1; break; }
+    return cmp > 0;
+}
+
 // ---- front half ----------------------------------------------------------------
 
 // Returns LINE_DEFER (nothing emitted) when the record runs past `lim` and lim

@@ -110,7 +110,7 @@ def test_golden_cases_host_buffers(tmp_path):
 @pytest.mark.parametrize("tile,over,listcap", [(64, 32, 1024), (256, 64, 2), (1024, 16, 1024), (4096, 4096, 8)])
 def test_golden_tiny_tiles(tile, over, listcap, tmp_path):
     """Tile boundaries, look-ahead overflow (deferred records) and list overflow change nothing."""
-    eng = _engine(PANTAS_TILE_BYTES=tile, PANTAS_OVER_BYTES=over, PANTAS_LIST_CAP=listcap)
+    eng = _engine(PANTAS_KERNEL=1, PANTAS_TILE_BYTES=tile, PANTAS_OVER_BYTES=over, PANTAS_LIST_CAP=listcap)
     for case in GOLDEN:
         if "\r" in case["gaf"]:
             continue
@@ -118,9 +118,19 @@ def test_golden_tiny_tiles(tile, over, listcap, tmp_path):
         check_golden(case, gpu_pipeline(tmp_path, case["gfa"], case["gaf"], thr, eng=eng))
 
 
+@pytest.mark.parametrize("fast_t", [1024, 4096, 8192])
+def test_golden_fast_path_geometries(fast_t, tmp_path):
+    """The warp-autonomous fast path gives the same bytes for every mini-tile size (records that
+    cross a mini-tile's look-ahead or fail a fast-path precondition take the slow path)."""
+    eng = _engine(PANTAS_KERNEL=2, PANTAS_FAST_T=fast_t)
+    for case in GOLDEN:
+        thr = 20 if case["thr"] is None else case["thr"]
+        check_golden(case, gpu_pipeline(tmp_path, case["gfa"], case["gaf"], thr, eng=eng))
+
+
 @pytest.mark.parametrize("threads", [128, 512])
 def test_golden_other_block_sizes(threads, tmp_path):
-    eng = _engine(PANTAS_THREADS=threads, PANTAS_TILE_KB=32)
+    eng = _engine(PANTAS_KERNEL=1, PANTAS_THREADS=threads, PANTAS_TILE_KB=32)
     for case in GOLDEN[:80]:
         thr = 20 if case["thr"] is None else case["thr"]
         check_golden(case, gpu_pipeline(tmp_path, case["gfa"], case["gaf"], thr, eng=eng))
@@ -132,11 +142,49 @@ def test_fuzz_vs_oracle(seed, tmp_path):
                                  crlf=(seed % 6 == 0), trailing_newline=(seed % 4 != 0))
     orc = run_oracle(gaf.encode(), gfa.encode())
     assert orc.rc == 0
-    eng = _engine(PANTAS_TILE_BYTES=[65536, 2048, 512][seed % 3], PANTAS_OVER_BYTES=[4096, 256, 64][seed % 3])
+    eng = _engine(PANTAS_KERNEL=[2, 2, 2, 1][seed % 4], PANTAS_FAST_T=[8192, 1024, 4096][seed % 3],
+                  PANTAS_TILE_BYTES=[65536, 2048, 512][seed % 3], PANTAS_OVER_BYTES=[4096, 256, 64][seed % 3])
     res = gpu_pipeline(tmp_path, gfa, gaf, eng=eng, chunks=1 + seed % 3, via_host=(seed % 5 == 0))
     assert res[0] == "ok", res
     assert res[1] == orc.out
     assert res[2] == orc.rej
+
+
+@pytest.mark.parametrize("preset,pairs,fast_t,kernel", [("tiny", 20000, 8192, 2), ("dm-chr4", 100000, 8192, 2),
+                                                        ("dm-chr4", 50000, 4096, 2), ("tiny", 20000, 1024, 2),
+                                                        ("gene-panel", 50000, 8192, 2), ("tiny", 20000, 8192, 1)])
+def test_synthetic_workload_matches_oracle(preset, pairs, fast_t, kernel, tmp_path):
+    """The bench workload's generator (vg-mpmap-shaped records, mostly fast-path) at a size the CPU oracle
+    finishes in seconds: the augmented GFA is byte-identical."""
+    import torch
+
+    from pantas_b200.counts import Counts
+    from pantas_b200.gfa import load_graph, write_augmented
+    from pantas_b200.synth import SynthGraph
+
+    sg = SynthGraph(preset, seed=77)
+    gp = tmp_path / "g.gfa"
+    sg.write_gfa(str(gp))
+    gaf, n_lines = sg.gaf(pairs, first_pair=0, threads=4)
+    want = run_oracle(gaf, gp.read_bytes())
+    assert want.rc == 0, want.err
+    graph = load_graph(str(gp))
+    eng = _engine(PANTAS_KERNEL=kernel, PANTAS_FAST_T=fast_t)
+    eng.set_graph(graph)
+    n = int(gaf.shape[0])
+    d = torch.zeros(n + 32, dtype=torch.uint8, device="cuda")
+    d[:n] = torch.from_numpy(gaf).cuda()
+    eng.process_device(d, n, 0, 20)
+    eng.check_data_error()
+    counts = Counts.from_flat(eng.export())
+    assert counts.n_lines == n_lines == want.n_lines
+    assert counts.rej == want.rej
+    out = io.StringIO()
+    write_augmented(str(gp), graph, counts, out)
+    assert out.getvalue().encode() == want.out
+    st = eng.stats()
+    if kernel == 2 and fast_t >= 4096:
+        assert st["deferred_lines"] < 0.15 * n_lines, st      # the fast path really is the path taken
 
 
 def test_rerun_after_reset_is_identical(tmp_path):
