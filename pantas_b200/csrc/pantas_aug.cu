@@ -428,7 +428,7 @@ int pt_create(int device, pt_ctx** out) {
         ctx->threads != 512)
         ctx->threads = 256;
     ctx->kernel_ver = env_u32("PANTAS_KERNEL", 2);
-    ctx->fast_geo = env_u32("PANTAS_FAST_T", 8192);
+    ctx->fast_geo = env_u32("PANTAS_FAST_T", 24576);
     *out = ctx;
     return 0;
 }
@@ -624,14 +624,17 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
     uint32_t f_tiles = 0, f_grid = 0;
     uint32_t f_threads = 0;
     if (ctx->kernel_ver == 2) {
-        typedef fastp::Geo<8192, 768, 10> G8;
-        typedef fastp::Geo<4096, 512, 10> G4;
-        typedef fastp::Geo<1024, 256, 8> G1;     // tests: many mini-tile boundaries, records longer than the look-ahead
-        uint32_t ft, fw;
-        if (ctx->fast_geo == 1024) { fkern = fastp::augment_fast_kernel<G1>; fsmem = (size_t)G1::WARP_BYTES * G1::WARPS; ft = G1::T; fw = G1::WARPS; }
-        else if (ctx->fast_geo == 4096) { fkern = fastp::augment_fast_kernel<G4>; fsmem = (size_t)G4::WARP_BYTES * G4::WARPS; ft = G4::T; fw = G4::WARPS; }
-        else { fkern = fastp::augment_fast_kernel<G8>; fsmem = (size_t)G8::WARP_BYTES * G8::WARPS; ft = G8::T; fw = G8::WARPS; }
-        f_threads = fw * 32;
+        typedef fastp::Geo<24576, 1024, 256> GA;
+        typedef fastp::Geo<32768, 1024, 512> GB;
+        typedef fastp::Geo<16384, 1024, 256> GC;
+        typedef fastp::Geo<1024, 256, 64> GT;    // tests: many tile boundaries, records longer than the look-ahead
+        uint32_t ft;
+#define PT_PICK(Gx) { fkern = fastp::augment_fast_kernel<Gx>; fsmem = (size_t)Gx::SMEM_BYTES; ft = Gx::TILE; f_threads = Gx::THREADS; }
+        if (ctx->fast_geo == 1024) PT_PICK(GT)
+        else if (ctx->fast_geo == 32768) PT_PICK(GB)
+        else if (ctx->fast_geo == 16384) PT_PICK(GC)
+        else PT_PICK(GA)
+#undef PT_PICK
         if (ctx->fast_ctas_per_sm == 0) {
             CK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
             int occ = 0;
@@ -642,8 +645,7 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
         const uint64_t nt = (nbytes + ft - 1) / ft;
         f_tiles = (uint32_t)nt;
         uint64_t g = (uint64_t)ctx->sm_count * ctx->fast_ctas_per_sm;
-        const uint64_t need = (nt + fw - 1) / fw;
-        if (g > need) g = need;
+        if (g > nt) g = nt;
         f_grid = (uint32_t)g;
     }
     if (ctx->profile) {

@@ -118,7 +118,7 @@ def test_golden_tiny_tiles(tile, over, listcap, tmp_path):
         check_golden(case, gpu_pipeline(tmp_path, case["gfa"], case["gaf"], thr, eng=eng))
 
 
-@pytest.mark.parametrize("fast_t", [1024, 4096, 8192])
+@pytest.mark.parametrize("fast_t", [1024, 16384, 24576, 32768])
 def test_golden_fast_path_geometries(fast_t, tmp_path):
     """The warp-autonomous fast path gives the same bytes for every mini-tile size (records that
     cross a mini-tile's look-ahead or fail a fast-path precondition take the slow path)."""
@@ -142,7 +142,7 @@ def test_fuzz_vs_oracle(seed, tmp_path):
                                  crlf=(seed % 6 == 0), trailing_newline=(seed % 4 != 0))
     orc = run_oracle(gaf.encode(), gfa.encode())
     assert orc.rc == 0
-    eng = _engine(PANTAS_KERNEL=[2, 2, 2, 1][seed % 4], PANTAS_FAST_T=[8192, 1024, 4096][seed % 3],
+    eng = _engine(PANTAS_KERNEL=[2, 2, 2, 1][seed % 4], PANTAS_FAST_T=[24576, 1024, 32768][seed % 3],
                   PANTAS_TILE_BYTES=[65536, 2048, 512][seed % 3], PANTAS_OVER_BYTES=[4096, 256, 64][seed % 3])
     res = gpu_pipeline(tmp_path, gfa, gaf, eng=eng, chunks=1 + seed % 3, via_host=(seed % 5 == 0))
     assert res[0] == "ok", res
@@ -150,9 +150,9 @@ def test_fuzz_vs_oracle(seed, tmp_path):
     assert res[2] == orc.rej
 
 
-@pytest.mark.parametrize("preset,pairs,fast_t,kernel", [("tiny", 20000, 8192, 2), ("dm-chr4", 100000, 8192, 2),
-                                                        ("dm-chr4", 50000, 4096, 2), ("tiny", 20000, 1024, 2),
-                                                        ("gene-panel", 50000, 8192, 2), ("tiny", 20000, 8192, 1)])
+@pytest.mark.parametrize("preset,pairs,fast_t,kernel", [("tiny", 20000, 24576, 2), ("dm-chr4", 100000, 24576, 2),
+                                                        ("dm-chr4", 50000, 32768, 2), ("tiny", 20000, 1024, 2),
+                                                        ("gene-panel", 50000, 16384, 2), ("tiny", 20000, 24576, 1)])
 def test_synthetic_workload_matches_oracle(preset, pairs, fast_t, kernel, tmp_path):
     """The bench workload's generator (vg-mpmap-shaped records, mostly fast-path) at a size the CPU oracle
     finishes in seconds: the augmented GFA is byte-identical."""
