@@ -127,10 +127,18 @@ int pt_timer_stop(pt_ctx* ctx, float* ms);     /* synchronises on the stop event
  * duration and the number of launches since the last call (then clears them). */
 int pt_profile_enable(pt_ctx* ctx, int on);
 int pt_kernel_time(pt_ctx* ctx, float* ms_total, uint64_t* launches);
+/* Same, split into the fast-path kernel and the exact per-record kernel (+ the chunk epilogue). */
+int pt_kernel_time_split(pt_ctx* ctx, float* ms_fast, float* ms_slow, uint64_t* launches);
 
 /* Counters for reports: kernel launches since create, records that took the
  * long-line path, tiles processed. */
 int pt_stats(pt_ctx* ctx, uint64_t* kernel_launches, uint64_t* deferred_lines, uint64_t* tiles);
+
+/* Why records were handed from the fast path to the exact per-record path since the last reset
+ * (diagnostics): out[0..n) = long record / look-ahead, columns not 12 single tabs, integer syntax,
+ * tag order or content, cs class, path column, step list full, walk (duplicate / unknown id, node
+ * without bases, cs too short), record list full, round-1a tile kernel.  Synchronises. */
+int pt_debug_counters(pt_ctx* ctx, uint64_t* out, int n);
 
 #ifdef __cplusplus
 }

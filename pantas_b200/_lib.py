@@ -38,6 +38,8 @@ SIGNATURES = {
     "pt_timer_stop": (ctypes.c_int, [c_ctx, ctypes.POINTER(ctypes.c_float)]),
     "pt_profile_enable": (ctypes.c_int, [c_ctx, ctypes.c_int]),
     "pt_kernel_time": (ctypes.c_int, [c_ctx, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(u64)]),
+    "pt_kernel_time_split": (ctypes.c_int, [c_ctx, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(u64)]),
+    "pt_debug_counters": (ctypes.c_int, [c_ctx, ctypes.POINTER(u64), ctypes.c_int]),
     "pt_stats": (ctypes.c_int, [c_ctx, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(u64)]),
 }
 

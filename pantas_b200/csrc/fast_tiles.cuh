@@ -80,7 +80,9 @@ struct Geo {
     static constexpr int OFF_SIDX = OFF_STEP + 4 * STEP_CAP;
     static constexpr int OFF_LINES = OFF_SIDX + 4 * STEP_CAP;
     static constexpr int OFF_REC = (OFF_LINES + 2 * LINE_CAP + 7) & ~7;
-    static constexpr int SMEM_BYTES = (OFF_REC + (int)sizeof(LineRecF) * LINE_CAP + 127) & ~127;
+    static constexpr int FAR_CAP = (STEP_CAP / 6 + 31) & ~31;           // links that are not inline: typically 1-2 per record
+    static constexpr int OFF_FAR = (OFF_REC + (int)sizeof(LineRecF) * LINE_CAP + 15) & ~15;
+    static constexpr int SMEM_BYTES = (OFF_FAR + 12 * FAR_CAP + 127) & ~127;
     static constexpr int FIT = (227 * 1024) / (SMEM_BYTES + 1024);                    // CTAs per SM by shared memory
     static constexpr int REG = 1024 / THREADS < 1 ? 1 : 1024 / THREADS;               // ... leaving >= 64 registers per thread
     static constexpr int MIN_CTAS = FIT < 1 ? 1 : (FIT < REG ? FIT : REG);
@@ -116,6 +118,19 @@ __device__ __forceinline__ bool token_is_inert(const uint8_t* s, uint32_t a, uin
         prev = c;
     }
     return true;
+}
+
+// a tag the aligner always writes first: "AS:i:<int>" -- inert when nothing after the prefix is a ':'
+__device__ __forceinline__ bool no_colon(const uint8_t* s, uint32_t a, uint32_t b) {
+    if (b - a > 48u) return false;
+    bool ok = true;
+    for (uint32_t q = a; q < b; q++) ok &= s[q] != ':';
+    return ok;
+}
+__device__ __forceinline__ bool tag_is_inert(const uint8_t* s, uint32_t a, uint32_t b) {
+    if (b - a >= 6u && s[a] == 'A' && s[a + 1] == 'S' && s[a + 2] == ':' && s[a + 3] == 'i' && s[a + 4] == ':')
+        return no_colon(s, a + 5u, b);
+    return token_is_inert(s, a, b);
 }
 
 // four ASCII digits, most significant in the lowest byte, already xor'ed with '0'
@@ -190,7 +205,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
     constexpr uint32_t THREADS = G::THREADS;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t s_nlines, s_nsteps;
+    __shared__ uint32_t s_nlines, s_nsteps, s_nfar;
 
     const uint32_t tid = threadIdx.x;
     uint8_t* const buf = smem;
@@ -202,11 +217,13 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
     uint32_t* const sidx = reinterpret_cast<uint32_t*>(smem + G::OFF_SIDX);
     uint16_t* const lines = reinterpret_cast<uint16_t*>(smem + G::OFF_LINES);
     LineRecF* const recs = reinterpret_cast<LineRecF*>(smem + G::OFF_REC);
+    uint32_t* const far = reinterpret_cast<uint32_t*>(smem + G::OFF_FAR);     // {from, to, separator position} x FAR_CAP
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
         s_nlines = 0;
         s_nsteps = 0;
+        s_nfar = 0;
     }
     __syncthreads();
 
@@ -240,57 +257,63 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         parity ^= 1;
 
         // ================= scan: whitespace / separator masks, record starts =================
-        for (uint32_t v = tid; v < nvec4; v += THREADS) {
-            uint32_t wm = 0, sm = 0;
-            if (v < nvec) {
-                const uint4 q4 = *reinterpret_cast<const uint4*>(buf + 16u * v);
-                const uint32_t w0 = flag_ws(q4.x), w1 = flag_ws(q4.y), w2 = flag_ws(q4.z), w3 = flag_ws(q4.w);
-                wm = mask16(w0, w1, w2, w3);
-                sm = mask16(flag_sep(q4.x), flag_sep(q4.y), flag_sep(q4.z), flag_sep(q4.w));
+        // one thread per 64 bytes (four LDS.128): one 64-bit word of each mask per thread and iteration
+        unsigned long long* const wm64w = reinterpret_cast<unsigned long long*>(smem + G::OFF_WM);
+        unsigned long long* const sm64w = reinterpret_cast<unsigned long long*>(smem + G::OFF_SM);
+        for (uint32_t g = tid; g < nwords; g += THREADS) {
+            unsigned long long wm = 0, sm = 0;
+            uint32_t oth = 0, hib = 0;
+            uint4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) q[u] = *reinterpret_cast<const uint4*>(buf + 64u * g + 16u * u);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t w0 = flag_ws(q[u].x), w1 = flag_ws(q[u].y), w2 = flag_ws(q[u].z), w3 = flag_ws(q[u].w);
+                wm |= (unsigned long long)mask16(w0, w1, w2, w3) << (16 * u);
+                sm |= (unsigned long long)mask16(flag_sep(q[u].x), flag_sep(q[u].y), flag_sep(q[u].z), flag_sep(q[u].w)) << (16 * u);
                 // whitespace that is not a tab: '\n' (record start), '\r' (lone: error); the rest only matters to the walkers
-                const uint32_t o0 = w0 & ~flag_tab(q4.x), o1 = w1 & ~flag_tab(q4.y), o2 = w2 & ~flag_tab(q4.z), o3 = w3 & ~flag_tab(q4.w);
-                const uint32_t room = lim - 16u * v;                        // > 0
-                const uint32_t keep = room < 16u ? (1u << room) - 1u : 0xFFFFu;
-                wm &= keep;
-                sm &= keep;
-                if (v == 0) {                                               // bytes before the tile
-                    wm = 0;
-                    sm = 0;
-                    if (tile == 0 && owned > 0u) {                          // the chunk starts at a record start
-                        const uint32_t j = atomicAdd(&s_nlines, 1u);
-                        if (j < (uint32_t)G::LINE_CAP) lines[j] = 16;
-                    }
-                }
-                if ((o0 | o1 | o2 | o3) != 0u) {
-                    uint32_t om = mask16(o0, o1, o2, o3) & keep;
-                    if (v == 0) om &= tile ? 0x8000u : 0u;                  // only: is the byte before the tile a newline?
-                    while (om) {
-                        const uint32_t p = 16u * v + (uint32_t)(__ffs((int)om) - 1);
-                        om &= om - 1u;
-                        const uint32_t c = buf[p];
-                        if (c == '\n') {
-                            if (p + 1u < own_end) {
-                                const uint32_t j = atomicAdd(&s_nlines, 1u);
-                                if (j < (uint32_t)G::LINE_CAP) lines[j] = (uint16_t)(p + 1u);
-                            }
-                        } else if (c == '\r' && p >= 16u && p < own_end) {
-                            const uint64_t abs_pos = t0 + p - 16u;
-                            if (abs_pos + 1 < A.nbytes && buf[p + 1] != '\n')
-                                report_error(T, pt::PT_U_BARE_CR, base_off + (int64_t)p);
+                oth |= (w0 & ~flag_tab(q[u].x)) | (w1 & ~flag_tab(q[u].y)) | (w2 & ~flag_tab(q[u].z)) | (w3 & ~flag_tab(q[u].w));
+                hib |= q[u].x | q[u].y | q[u].z | q[u].w;
+            }
+            const uint32_t room = lim > 64u * g ? lim - 64u * g : 0u;       // loaded bytes in this group
+            unsigned long long keep = room < 64u ? ~(~0ull << room) : ~0ull;
+            if (g == 0) keep &= ~0xFFFFull;                                 // positions 0..15 are before the tile
+            wm &= keep;
+            sm &= keep;
+            wm64w[g] = wm;
+            sm64w[g] = sm;
+            if (g == 0 && tile == 0 && owned > 0u) {                        // the chunk starts at a record start
+                const uint32_t j = atomicAdd(&s_nlines, 1u);
+                if (j < (uint32_t)G::LINE_CAP) lines[j] = 16;
+            }
+            if (oth != 0u) {
+                unsigned long long om = 0;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    om |= (unsigned long long)mask16(flag_ws(q[u].x) & ~flag_tab(q[u].x), flag_ws(q[u].y) & ~flag_tab(q[u].y),
+                                                     flag_ws(q[u].z) & ~flag_tab(q[u].z), flag_ws(q[u].w) & ~flag_tab(q[u].w)) << (16 * u);
+                if (g == 0 && tile != 0) keep |= 0x8000ull;                 // is the byte before the tile a newline?
+                om &= keep;
+                while (om) {
+                    const uint32_t p = 64u * g + (uint32_t)(__ffsll((long long)om) - 1);
+                    om &= om - 1ull;
+                    const uint32_t c = buf[p];
+                    if (c == '\n') {
+                        if (p + 1u < own_end) {
+                            const uint32_t j = atomicAdd(&s_nlines, 1u);
+                            if (j < (uint32_t)G::LINE_CAP) lines[j] = (uint16_t)(p + 1u);
                         }
-                    }
-                }
-                const uint32_t hib = (q4.x | q4.y | q4.z | q4.w) & 0x80808080u;
-                if (hib != 0u && v != 0u) {                                 // non-ASCII byte: not modelled
-                    const uint32_t hm = mask16(q4.x & 0x80808080u, q4.y & 0x80808080u, q4.z & 0x80808080u, q4.w & 0x80808080u) & keep;
-                    if (hm) {
-                        const uint32_t p = 16u * v + (uint32_t)(__ffs((int)hm) - 1);
-                        if (p < own_end) report_error(T, pt::PT_U_NON_ASCII, base_off + (int64_t)p);
+                    } else if (c == '\r' && p >= 16u && p < own_end) {
+                        const uint64_t abs_pos = t0 + p - 16u;
+                        if (abs_pos + 1 < A.nbytes && buf[p + 1] != '\n')
+                            report_error(T, pt::PT_U_BARE_CR, base_off + (int64_t)p);
                     }
                 }
             }
-            wm16[v] = (uint16_t)wm;
-            sm16[v] = (uint16_t)sm;
+            if ((hib & 0x80808080u) != 0u) {                                // non-ASCII byte: not modelled
+                for (uint32_t p = max(64u * g, 16u); p < min(64u * g + 64u, min(lim, own_end)); p++)
+                    if (buf[p] >= 0x80u) { report_error(T, pt::PT_U_NON_ASCII, base_off + (int64_t)p); break; }
+            }
         }
         __syncthreads();                                                    // ---- masks + record list complete
         const uint32_t n_lines_all = s_nlines;
@@ -300,7 +323,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             // more records than the list holds (pathological input): all of them take the slow path
             for (uint32_t p = 15u + tid; p + 1u < own_end; p += THREADS) {
                 const bool nl = p == 15u ? (tile == 0 || buf[p] == '\n') : buf[p] == '\n';
-                if (nl) defer_line(T, t0 + p + 1u - 16u, A.file_off);
+                if (nl) defer_line(T, t0 + p + 1u - 16u, A.file_off, WHY_LINES_FULL);
             }
             __syncthreads();
             if (tid == 0) {
@@ -316,6 +339,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         // ================= records: one thread per record =================
         for (uint32_t l = tid; l < n_lines; l += THREADS) {
             bool slow = false, done = false;
+            int why = WHY_LONG;
             const uint32_t ls = lines[l];
             uint32_t ns = 0, a5 = 0, b5 = 0;
             int32_t mapq = 0, plen = 0, start = 0, pend = 0, n_tot = 0;
@@ -334,13 +358,20 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                     if (!next_ws(wm64, nwords, wi, wmk, e[j])) slow = true;          // record runs past the look-ahead
                     else if (j <= 12) {
                         gaps_ok &= e[j] - e[j - 1] >= 2u;                            // no empty column
-                        tabs &= buf[e[j]] == '\t' ? 0xFFFFFFFFu : 0u;
+                        if (j < 12) tabs &= buf[e[j]] == '\t' ? 0xFFFFFFFFu : 0u;
                     }
                 }
             }
-            slow = slow || !gaps_ok || tabs == 0u;
+            // 11 single tabs, then a tab (tags follow) or the end of a 12-column record
+            bool no_tags = false;
+            if (!slow) {
+                const uint32_t c12 = buf[e[12]];
+                no_tags = c12 == '\n';
+                if (!gaps_ok || tabs == 0u || (c12 != '\t' && !no_tags)) { slow = true; why = WHY_COLUMNS; }
+            }
             if (!slow) {
                 slow = !small_uint(buf, e[11] + 1u, e[12], mapq);
+                why = WHY_INTS;
                 if (!slow) {
                     if ((int64_t)mapq < A.thr) { sink.reject(); done = true; }                       // REF:143-146
                     else if (e[6] - e[5] == 2u && buf[e[5] + 1u] == '*') done = true;                 // REF:147-148
@@ -351,7 +382,9 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                        !small_uint(buf, e[8] + 1u, e[9], pend);
             // ---- tags: [inert]* cs [inert]* dv in any order, within the first few tags
             uint32_t cs_a = 0, cs_b = 0, dv_a = 0, dv_b = 0;
+            if (!slow && !done && no_tags) { slow = true; why = WHY_TAGS; }       // no dv tag: ValueError (REF:179), slow path reports
             if (!slow && !done) {
+                why = WHY_TAGS;
                 uint32_t a = e[12] + 1u, b = e[13];
                 for (int j = 13;; j++) {
                     if (!cs_b && b - a >= 3u && buf[a] == 'c' && buf[a + 1] == 's' && buf[a + 2] == ':') {
@@ -359,10 +392,10 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                         cs_b = b;
                     } else if (!dv_b && b - a >= 6u && buf[a] == 'd' && buf[a + 1] == 'v' && buf[a + 2] == ':' &&
                                buf[a + 3] == 'f' && buf[a + 4] == ':' && pt::is_digit(buf[a + 5]) &&
-                               token_is_inert(buf, a + 5u, b)) {
+                               no_colon(buf, a + 5u, b)) {
                         dv_a = a + 5u;
                         dv_b = b;
-                    } else if (!token_is_inert(buf, a, b)) {
+                    } else if (!tag_is_inert(buf, a, b)) {
                         slow = true;
                         break;
                     }
@@ -373,10 +406,26 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                     else if (!next_ws(wm64, nwords, wi, wmk, b)) { slow = true; break; }
                 }
             }
+            // ---- dv filter (REF:172-180).  The reference parses cs first, but that has no side effects and cannot
+            //      raise, so a record that dv filters out needs no cs class
+            if (!slow && !done) {
+                const uint32_t f = buf[dv_a], g = dv_a + 1u < dv_b ? buf[dv_a + 1u] : 0u, h = dv_a + 2u < dv_b ? buf[dv_a + 2u] : 0u;
+                if (f == '0' && g == '.' && h == '0') {
+                    // 0.0xxx: never greater
+                } else if (pt::dv_token_greater(buf, (int)dv_a, (int)dv_b)) {
+                    done = true;
+                }
+            }
             // ---- cs string: "cs:Z:" then ':'<digits> and '*'<2 letters> ops only (REF:10-37)
             if (!slow && !done) {
+                why = WHY_CS;
                 if (cs_b - cs_a < 7u || buf[cs_a + 3] != 'Z' || buf[cs_a + 4] != ':') slow = true;
                 uint32_t q = cs_a + 5u;
+                uint64_t one;
+                if (!slow && buf[q] == ':' && cs_b - q - 1u <= 7u && step_id(buf, q + 1u, cs_b - q - 1u, one) && one != 0u) {
+                    n_tot = (int32_t)one;                                    // cs:Z::<n> -- a perfect match
+                    q = cs_b;
+                }
                 while (!slow && q < cs_b) {
                     const uint32_t c = buf[q];
                     if (c == ':') {
@@ -401,18 +450,10 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 }
                 if (n_tot <= 0 || n_tot > MAX_NTOT) slow = true;
             }
-            // ---- dv filter (REF:172-180), after cs like the reference (cs has no side effects)
-            if (!slow && !done) {
-                const uint32_t f = buf[dv_a], g = dv_a + 1u < dv_b ? buf[dv_a + 1u] : 0u, h = dv_a + 2u < dv_b ? buf[dv_a + 2u] : 0u;
-                if (f == '0' && g == '.' && h == '0') {
-                    // 0.0xxx: never greater
-                } else if (pt::dv_token_greater(buf, (int)dv_a, (int)dv_b)) {
-                    done = true;
-                }
-            }
             // ---- path column (REF:185-197): it must start with a separator; count the steps
             uint32_t off = 0;
             if (!slow && !done) {
+                why = WHY_PATH;
                 a5 = e[5] + 1u;
                 b5 = e[6];
                 for (uint32_t w = a5 >> 6; w <= ((b5 - 1u) >> 6); w++) ns += (uint32_t)__popcll(sep_word(sm64, w, a5, b5));
@@ -422,6 +463,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                     off = atomicAdd(&s_nsteps, ns);                               // any order: a record only needs a contiguous range
                     if (off + ns > (uint32_t)G::STEP_CAP) {                       // list full: slow path
                         slow = true;
+                        why = WHY_STEPS_FULL;
                         for (uint32_t i = off; i < (uint32_t)G::STEP_CAP; i++) steps[i] = SE_INVALID;
                     }
                 }
@@ -429,6 +471,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             LineRecF& R = recs[l];
             R.ls = (uint16_t)ls;
             R.status = slow ? ST_DEFER : (done ? ST_DONE : ST_FAST);
+            R.nstar = (uint8_t)why;                                        // reason, read by `walk` when status is ST_DEFER
             R.nsteps = 0;
             if (!slow && !done) {
                 R.start = start;
@@ -477,6 +520,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         __syncthreads();                                                    // ---- node indices complete; the bytes are dead
         if (tid == 0) {
             s_nsteps = 0;
+            s_nfar = 0;
             const uint32_t nxt = tile + gridDim.x;
             if (nxt < A.n_tiles) issue_load(nxt);                           // overlaps walk + count
         }
@@ -488,7 +532,9 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             if (st == ST_FAST) {
                 const uint32_t s0 = R.s0, ns = R.nsteps, n_tot = (uint32_t)R.n_tot, nstar = R.nstar;
                 const int32_t start = R.start, end_rel1 = R.end_rel1;
-                const uint32_t x0 = R.star[0], x1 = R.star[1], x2 = R.star[2], x3 = R.star[3];
+                uint32_t x[MAX_STARS];
+#pragma unroll
+                for (int j = 0; j < MAX_STARS; j++) x[j] = R.star[j];
                 uint32_t pos = 0, prev = NONE32;
                 bool bad = false;
 #pragma unroll 4
@@ -504,10 +550,10 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                     const uint32_t Lc = L <= 0 ? 0u : (L > (int64_t)L_CLAMP ? L_CLAMP : (uint32_t)L);
                     const uint32_t endp = min(pos + Lc, n_tot);
                     uint32_t stars_in = 0;
-                    stars_in += (nstar > 0u && x0 >= pos && x0 < endp) ? 1u : 0u;
-                    stars_in += (nstar > 1u && x1 >= pos && x1 < endp) ? 1u : 0u;
-                    stars_in += (nstar > 2u && x2 >= pos && x2 < endp) ? 1u : 0u;
-                    stars_in += (nstar > 3u && x3 >= pos && x3 < endp) ? 1u : 0u;
+                    if (nstar != 0u) {
+#pragma unroll
+                        for (int j = 0; j < MAX_STARS; j++) stars_in += ((uint32_t)j < nstar && x[j] >= pos && x[j] < endp) ? 1u : 0u;
+                    }
                     if (stars_in < endp - pos) steps[s0 + k] |= SE_COUNTS;  // the slice holds a ':' piece (REF:63-94)
                     pos += Lc;
                     prev = idx;
@@ -517,7 +563,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                     for (uint32_t k = 0; k < ns; k++) steps[s0 + k] = SE_INVALID;
                 }
             }
-            if (st == ST_DEFER) defer_line(T, t0 + R.ls - 16u, A.file_off);
+            if (st == ST_DEFER) defer_line(T, t0 + R.ls - 16u, A.file_off, R.status == ST_DEFER ? (int)R.nstar : (int)WHY_WALK);
         }
         __syncthreads();                                                    // ---- nothing counted so far; hand-overs done
 
@@ -559,9 +605,17 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                     }
                     sink.bump(idx, eslot);                                              // REF:263-269, 357-363
                     if (have_edge && eslot < 0) {
-                        // stamped like the reference's insertion: when the later of the two steps is reached
-                        const uint64_t es = rev ? stamp : (uint64_t)(base_off + (int64_t)(steps[s + 1u] & SE_POS_MASK) + 1) << 2;
-                        sink.edge_far(idx, other, es);
+                        // not inline: hash-table work, collected and done below with every lane busy.  Stamped like
+                        // the reference's insertion: when the later of the two steps is reached
+                        const uint32_t ep = rev ? (se & SE_POS_MASK) : (steps[s + 1u] & SE_POS_MASK);
+                        const uint32_t j = atomicAdd(&s_nfar, 1u);
+                        if (j < (uint32_t)G::FAR_CAP) {
+                            far[3u * j] = idx;
+                            far[3u * j + 1u] = other;
+                            far[3u * j + 2u] = ep;
+                        } else {
+                            sink.edge_far(idx, other, (uint64_t)(base_off + (int64_t)ep + 1) << 2);
+                        }
                     }
                     DevSink::Stamps st;
                     st.il = hot_[u].il;
@@ -569,6 +623,12 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                     sink.dense(idx, il_cond ? n_count : 0, ol_cond ? n_count : 0, stamp | 1u, st);   // REF:298-351
                 }
             }
+        }
+        __syncthreads();                                                    // ---- far-link list complete
+        {
+            const uint32_t n_far = min(s_nfar, (uint32_t)G::FAR_CAP);
+            for (uint32_t j = tid; j < n_far; j += THREADS)
+                sink.edge_far(far[3u * j], far[3u * j + 1u], (uint64_t)(base_off + (int64_t)far[3u * j + 2u] + 1) << 2);
         }
         // no barrier here: the next tile's scan writes only the masks and the record list, which
         // nobody reads any more, and its first barrier orders everything else

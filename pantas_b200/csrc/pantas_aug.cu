@@ -73,7 +73,11 @@ struct ChunkArgs {
     uint32_t n_tiles;
 };
 
-__device__ __forceinline__ void defer_line(const Tables& T, uint64_t chunk_pos, int64_t file_off) {
+// why a record is handed to the slow path (pt_debug_counters)
+enum { WHY_LONG = 0, WHY_COLUMNS, WHY_INTS, WHY_TAGS, WHY_CS, WHY_PATH, WHY_STEPS_FULL, WHY_WALK, WHY_LINES_FULL, WHY_V1 };
+
+__device__ __forceinline__ void defer_line(const Tables& T, uint64_t chunk_pos, int64_t file_off, int why = WHY_V1) {
+    atomicAdd(&T.sc[SC_WHY + why], 1ull);
     const unsigned long long j = atomicAdd(&T.sc[SC_NDEFER], 1ull);
     if (j < T.deferred_cap) T.deferred[j] = (uint32_t)chunk_pos;
     else report_error(T, pt::PT_X_DEFER_FULL, file_off + (int64_t)chunk_pos);
@@ -627,12 +631,18 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
         typedef fastp::Geo<24576, 1024, 256> GA;
         typedef fastp::Geo<32768, 1024, 512> GB;
         typedef fastp::Geo<16384, 1024, 256> GC;
+        typedef fastp::Geo<12288, 1024, 128> GD;
+        typedef fastp::Geo<16384, 1024, 128> GE;
+        typedef fastp::Geo<32768, 1024, 256> GF;
         typedef fastp::Geo<1024, 256, 64> GT;    // tests: many tile boundaries, records longer than the look-ahead
         uint32_t ft;
 #define PT_PICK(Gx) { fkern = fastp::augment_fast_kernel<Gx>; fsmem = (size_t)Gx::SMEM_BYTES; ft = Gx::TILE; f_threads = Gx::THREADS; }
         if (ctx->fast_geo == 1024) PT_PICK(GT)
         else if (ctx->fast_geo == 32768) PT_PICK(GB)
         else if (ctx->fast_geo == 16384) PT_PICK(GC)
+        else if (ctx->fast_geo == 12288) PT_PICK(GD)
+        else if (ctx->fast_geo == 16385) PT_PICK(GE)
+        else if (ctx->fast_geo == 32769) PT_PICK(GF)
         else PT_PICK(GA)
 #undef PT_PICK
         if (ctx->fast_ctas_per_sm == 0) {
@@ -649,8 +659,8 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
         f_grid = (uint32_t)g;
     }
     if (ctx->profile) {
-        if (ctx->prof_n + 2 > ctx->prof_cap) {
-            uint32_t nc = ctx->prof_cap ? ctx->prof_cap * 2 : 64;
+        if (ctx->prof_n + 3 > ctx->prof_cap) {
+            uint32_t nc = ctx->prof_cap ? ctx->prof_cap * 2 : 96;
             cudaEvent_t* ne = (cudaEvent_t*)realloc(ctx->prof_ev, nc * sizeof(cudaEvent_t));
             if (!ne) return fail_msg(ctx, PT_ERR_NOMEM, "profile events");
             ctx->prof_ev = ne;
@@ -666,11 +676,12 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
     } else {
         kern<<<(unsigned)grid, ctx->threads, smem, ctx->stream>>>(A, T);
     }
+    if (ctx->profile) CK(cudaEventRecord(ctx->prof_ev[ctx->prof_n + 1], ctx->stream));
     augment_deferred_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(A, T);
     end_chunk_kernel<<<1, 1, 0, ctx->stream>>>(T);
-    if (ctx->profile) {      // the pair tiles + second pass is "the augment pass" over this chunk
-        CK(cudaEventRecord(ctx->prof_ev[ctx->prof_n + 1], ctx->stream));
-        ctx->prof_n += 2;
+    if (ctx->profile) {      // fast path + exact per-record path = "the augment pass" over this chunk
+        CK(cudaEventRecord(ctx->prof_ev[ctx->prof_n + 2], ctx->stream));
+        ctx->prof_n += 3;
     }
     CK(cudaGetLastError());
     ctx->launches += 3;
@@ -809,19 +820,41 @@ int pt_profile_enable(pt_ctx* ctx, int on) {
     return 0;
 }
 
-int pt_kernel_time(pt_ctx* ctx, float* ms_total, uint64_t* launches) {
+int pt_kernel_time_split(pt_ctx* ctx, float* ms_fast, float* ms_slow, uint64_t* launches) {
     if (!ctx) return PT_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    float tot = 0;
-    for (uint32_t k = 0; k + 1 < ctx->prof_n; k += 2) {
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, ctx->prof_ev[k], ctx->prof_ev[k + 1]));
-        tot += ms;
+    float tf = 0, ts = 0;
+    for (uint32_t k = 0; k + 2 < ctx->prof_n; k += 3) {
+        float a = 0, b = 0;
+        CK(cudaEventElapsedTime(&a, ctx->prof_ev[k], ctx->prof_ev[k + 1]));
+        CK(cudaEventElapsedTime(&b, ctx->prof_ev[k + 1], ctx->prof_ev[k + 2]));
+        tf += a;
+        ts += b;
     }
-    if (ms_total) *ms_total = tot;
-    if (launches) *launches = ctx->prof_n / 2;
+    if (ms_fast) *ms_fast = tf;
+    if (ms_slow) *ms_slow = ts;
+    if (launches) *launches = ctx->prof_n / 3;
     ctx->prof_n = 0;
+    return 0;
+}
+
+int pt_kernel_time(pt_ctx* ctx, float* ms_total, uint64_t* launches) {
+    float a = 0, b = 0;
+    const int rc = pt_kernel_time_split(ctx, &a, &b, launches);
+    if (rc) return rc;
+    if (ms_total) *ms_total = a + b;
+    return 0;
+}
+
+int pt_debug_counters(pt_ctx* ctx, uint64_t* out, int n) {
+    if (!ctx || !out || n < 0) return PT_ERR_ARG;
+    if (!ctx->have_graph) return fail_msg(ctx, PT_ERR_STATE, "pt_debug_counters: no graph");
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long sc[SC_COUNT];
+    CK(cudaMemcpyAsync(sc, ctx->T.sc, sizeof sc, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < n; k++) out[k] = k < 16 ? sc[SC_WHY + k] : 0;
     return 0;
 }
 

@@ -56,7 +56,8 @@ struct __align__(32) SideSlot {
 };
 
 // device scalars (unsigned long long each)
-enum { SC_REJ = 0, SC_LINES, SC_ERR, SC_NOVEL_USED, SC_SPARSE_USED, SC_DEFERRED_TOTAL, SC_TILES, SC_TILE_NEXT, SC_NDEFER, SC_COUNT = 16 };
+enum { SC_REJ = 0, SC_LINES, SC_ERR, SC_NOVEL_USED, SC_SPARSE_USED, SC_DEFERRED_TOTAL, SC_TILES, SC_TILE_NEXT, SC_NDEFER,
+       SC_WHY = 16 /* 16 hand-over reasons */, SC_COUNT = 32 };
 
 struct Tables {
     NodeRec* nodes;
@@ -167,7 +168,7 @@ struct DevSink {
     }
     // NC[idx] += 1 and, if slot >= 0, RC of that inline link += 1: one RED.ADD.64
     __device__ __forceinline__ void bump(uint32_t idx, int slot) {
-        unsigned long long* c = slot == 1 ? &T.nodes[idx].c1 : &T.nodes[idx].c0;
+        unsigned long long* c = &T.nodes[idx].c0 + (slot > 0 ? 1 : 0);       // c1 follows c0
         atomicAdd(c, slot >= 0 ? 0x100000001ull : 1ull);
     }
     // RC of a link that is not inline: known link -> ovf table, otherwise novel (REF:426-427)

@@ -145,6 +145,20 @@ class AugmentEngine:
         self._check(self.lib.pt_kernel_time(self._ctx, ctypes.byref(ms), ctypes.byref(n)))
         return float(ms.value), int(n.value)
 
+    WHY = ("long", "columns", "ints", "tags", "cs", "path", "steps_full", "walk", "lines_full", "v1")
+
+    def handover_reasons(self) -> dict:
+        """Why records left the fast path (diagnostics)."""
+        out = (ctypes.c_uint64 * 16)()
+        self._check(self.lib.pt_debug_counters(self._ctx, out, 16))
+        return {k: int(out[i]) for i, k in enumerate(self.WHY)}
+
+    def kernel_time_split(self):
+        """(ms fast-path kernel, ms per-record kernel, launches) since the last call."""
+        a, b, n = ctypes.c_float(), ctypes.c_float(), ctypes.c_uint64()
+        self._check(self.lib.pt_kernel_time_split(self._ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)))
+        return float(a.value), float(b.value), int(n.value)
+
     def stats(self) -> dict:
         a, b, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
         self._check(self.lib.pt_stats(self._ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))

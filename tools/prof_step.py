@@ -28,6 +28,7 @@ buf, n_lines = sg.gaf(a.pairs, first_pair=0)
 n = int(buf.shape[0])
 eng = AugmentEngine(0)
 eng.set_graph(sg.graph())
+eng.profile(True)
 dev = torch.zeros(n + 32, dtype=torch.uint8, device="cuda")
 dev[:n] = torch.from_numpy(buf).cuda()
 torch.cuda.synchronize()
@@ -39,5 +40,7 @@ for i in range(a.steps):
     e1.record()
     e1.synchronize()
     print(f"pass {i}: {e0.elapsed_time(e1):.3f} ms, {n / e0.elapsed_time(e1) / 1e6:.1f} GB/s, {n_lines} records, {n} bytes")
+f, sl, nn = eng.kernel_time_split()
+print(f"fast kernel {f / nn:.3f} ms, per-record kernel {sl / nn:.3f} ms (avg of {nn})")
 eng.check_data_error()
-print(eng.stats())
+print(eng.stats(), eng.handover_reasons())
