@@ -4,65 +4,71 @@
 // Reference loop body: /root/reference/scripts/alignments_augmentation_from_gaf.py:142-363 (REF:n).
 //
 // A persistent CTA takes tiles of the GAF chunk (TILE bytes + OV bytes of look-ahead, one 1-D TMA
-// bulk copy, UBLKCP) and runs six data-parallel phases over the tile in shared memory:
+// bulk copy, UBLKCP) and runs data-parallel phases over the tile in shared memory:
 //
-//   scan     one thread per 16 bytes (LDS.128), branch-free SWAR: a 16-bit whitespace mask and a
-//            16-bit path-separator ('>' '<') mask per vector; record starts ('\n') go to a list;
+//   scan     one thread per 64 bytes (4 x LDS.128), branch-free SWAR: a 64-bit whitespace mask and a
+//            64-bit path-separator ('>' '<') mask per group; record starts ('\n') go to a list;
 //            lone '\r' and non-ASCII bytes are (fatal) errors.
-//   records  one thread per record: walks the whitespace mask 64 bytes at a time to get the 12
-//            column boundaries and the tag boundaries, then MAPQ / '*' / dv filters
-//            (REF:143-148,172-180), the three coordinates (REF:151-153) and the cs string
-//            (REF:154-160), classified as
-//              SIMPLE  cs:Z::<n>                        (a perfect match)
-//              STAR    only ':' and '*' ops, <= 4 '*'   (substitutions only)
-//            Everything else -- any other cs op, any whitespace other than single tabs in the
-//            first 12 columns, tags that could confuse the reference's regexes, integers that
-//            are not plain digits, ... -- is handed to the exact thread-per-record path
-//            (line_core.cuh via augment_deferred_kernel).  The thread then walks the separator
-//            mask of its path column and appends one entry per path step to the tile's step list.
+//   records  TWO threads per record, both walking the whitespace mask from the record start:
+//              B  the 12 column boundaries (single tabs, no empty column), MAPQ and '*' filters
+//                 (REF:143-148), the three coordinates (REF:151-153), then the separator mask of
+//                 the path column -> one entry per path step (+ a sentinel) in the tile's step list;
+//              A  the tags: first cs token, first dv:f: token (REF:154-160,172-180), the dv filter,
+//                 and the cs string parsed into the tile's op pool (REF:10-50, incl. cigar_clipping).
+//            Anything unusual -- other whitespace in the columns, integers that are not plain
+//            digits, tags that could confuse the reference's regexes, '~' or zero-length or oddly
+//            spelled cs ops -- hands the record to the exact per-record path (line_core.cuh via
+//            augment_deferred_kernel).
 //   ids      one thread per path step: SWAR decimal parse of the id out of shared memory, node
 //            index, L2 prefetch of the node record.  After this phase the bytes are dead and the
-//            next tile's TMA copy is issued: it overlaps the table traffic of the last two phases.
-//   walk     one thread per record: node lengths -> position of every node in the cs string
-//            (REF:205-255 reduces to a prefix sum for the two classes), the one-counting-op test of
-//            compact_align (REF:63-94), and every condition under which the slow path must redo
-//            the record (duplicate / unknown ids, first or last node without bases REF:215-218,
-//            cs shorter than the path REF:227).  Nothing has been counted yet, so the hand-over
-//            is clean.
-//   count    one thread per path step: NC / IL / OL / RC events (REF:263-363): one RED.ADD.64 on
-//            the node's sector (tables.cuh), RED.MIN for first-touch stamps only when earlier.
-//
-// For the two classes every node with L > 0 survives clear_align (REF:97-107) and its compacted
-// slice has exactly one counting op iff the slice holds a ':' piece.
+//            next tile's TMA copy is issued: it overlaps the table traffic of the remaining phases.
+//   walk     one thread per path step.  The reference's merge walk (REF:205-255) gives node k the
+//            ops that overlap [A_k, A_k + L_k) in cs coordinates, where A is the prefix sum of the
+//            node lengths L (first / last node shortened, REF:215-218): a block-wide prefix sum,
+//            then every step finds its op pieces independently and folds clear_align /
+//            compact_align (REF:63-107) over them: dropped or not, number of counting ops,
+//            deletion-derived IL/OL keys.  Collapsible duplicate ids (REF:188), unknown ids and a
+//            cs string shorter than the path hand the record over.  Nothing has been counted yet,
+//            so the hand-over is clean.
+//   count    one thread per surviving step: NC / IL / OL / RC events (REF:263-363): one RED.ADD.64
+//            on the node's sector (tables.cuh), RED.MIN for first-touch stamps only when earlier.
+//            Links that are not inline and deletion-derived keys are collected in two short lists
+//            and done by all threads at the end of the tile (hash-table work, all lanes busy).
 #pragma once
 
 namespace fastp {
 
 constexpr uint32_t NONE32 = 0xffffffffu;
-constexpr int MAX_STARS = 4;
 constexpr int MAX_STEPS = 250;                // longer paths take the slow path
+constexpr int MAX_OPS = 48;                   // more cs ops: slow path
 constexpr uint32_t L_CLAMP = 1u << 23;        // step lengths are clamped here (> any cs length the fast path takes)
 constexpr int32_t MAX_NTOT = 1 << 22;
 
-enum : uint8_t { ST_FAST = 0, ST_DEFER = 1, ST_DONE = 2 };
+enum : uint8_t { ST_FAST = 0, ST_DONE = 1, ST_DEFER = 2 };      // per role; a record's status is the maximum
+enum : uint32_t { OP_MATCH = 0, OP_SUB = 1, OP_DEL = 2, OP_INS = 3, OP_EQ = 4 };   // ':' '*' '-' '+' '='  (op = kind | len << 3)
 
 struct __align__(4) LineRecF {
-    int32_t start;        // int(tokens[7])
-    int32_t end_rel1;     // int(tokens[6]) - int(tokens[8]) - 1
-    int32_t n_tot;        // sum of the cs op lengths
-    uint16_t s0;          // first entry of the record in the step list
-    uint16_t nsteps;
-    uint16_t ls;          // buffer position of the record's first byte
-    uint16_t b5;          // buffer position of the end of the path column
-    uint16_t star[MAX_STARS];   // cs coordinate of every '*' op
-    uint8_t nstar;
-    uint8_t status;       // ST_*
+    int32_t start;        // int(tokens[7])                                    (role B)
+    int32_t end_rel1;     // int(tokens[6]) - int(tokens[8]) - 1               (role B)
+    int32_t start_add;    // cigar_clipping: start_pos += len of a leading '+' (role A, REF:46-47)
+    uint32_t n_tot;       // sum of the cs op lengths                          (role A)
+    uint32_t base;        // step-length prefix at the record's first step     (walk)
+    uint16_t s0;          // first entry of the record in the step list        (role B)
+    uint16_t nsteps;      //                                                   (role B)
+    uint16_t ls;          // buffer position of the record's first byte        (role B)
+    uint16_t op_off;      // first op of the record in the op pool             (role A)
+    uint8_t nops;         //                                                   (role A)
+    uint8_t stA, stB;     // ST_* per role; walk raises stB
+    uint8_t whyA, whyB;   // WHY_* when the role says ST_DEFER
+    uint8_t pad[3];
 };
 
-// step list entry: bits 0..15 buffer position of the separator, then flags
-constexpr uint32_t SE_POS_MASK = 0xFFFFu;
-constexpr uint32_t SE_FIRST = 1u << 16, SE_LAST = 1u << 17, SE_REV = 1u << 18, SE_COUNTS = 1u << 19;
-constexpr int SE_SLOT_SHIFT = 20;             // bits 20..31 record slot
+// step list entry
+constexpr uint32_t SE_POS_MASK = 0xFFFFu;     // bits 0..15  buffer position of the separator (sentinel: end of the path column)
+constexpr int SE_SLOT_SHIFT = 16;             // bits 16..24 record slot
+constexpr uint32_t SE_SLOT_MASK = 0x1FFu;
+constexpr uint32_t SE_FIRST = 1u << 25, SE_LAST = 1u << 26, SE_REV = 1u << 27, SE_SENT = 1u << 28, SE_DROPPED = 1u << 29;
+constexpr int SE_NCNT_SHIFT = 30;             // bits 30..31 counting ops of the compacted slice (0..3)
 constexpr uint32_t SE_INVALID = 0xFFFFFFFFu;
 
 template <int TILE_, int OV_, int THREADS_>
@@ -72,23 +78,30 @@ struct Geo {
     static constexpr int THREADS = THREADS_;
     static constexpr int BUF = 16 + TILE + OV + 16;               // [pre 16][tile][look-ahead][pad 16]
     static constexpr int NV = ((16 + TILE + OV) / 16 + 3) & ~3;   // 16-byte vectors, padded to whole 64-bit mask words
-    static constexpr int STEP_CAP = ((TILE + OV) / 12 + 63) & ~63;   // typical: 14 steps per 300 bytes
     static constexpr int LINE_CAP = ((TILE + 111) / 112 + 7) & ~7;   // typical: one record per 300 bytes
+    static constexpr int STEP_CAP = (((TILE + OV) / 12 + LINE_CAP) + 63) & ~63;   // typical: 14 steps per 300 bytes, + sentinels
+    static constexpr int OPS_CAP = (LINE_CAP * 4 + 63) & ~63;
+    static constexpr int FAR_CAP = (STEP_CAP / 8 + 31) & ~31;     // links that are not inline: typically 1-2 per record
+    static constexpr int DEL_CAP = (LINE_CAP / 2 + 31) & ~31;     // steps with deletion-derived keys
+    static constexpr int MASK_BYTES = 4 * NV;                     // whitespace + separator masks; dead after `records`:
+    static constexpr int LIST_BYTES = 12 * FAR_CAP + 12 * DEL_CAP;    // ... the two end-of-tile lists reuse the space
     static constexpr int OFF_WM = (BUF + 127) & ~127;
     static constexpr int OFF_SM = OFF_WM + 2 * NV;
-    static constexpr int OFF_STEP = OFF_SM + 2 * NV;
+    static constexpr int OFF_FAR = OFF_WM;
+    static constexpr int OFF_DEL = OFF_WM + 12 * FAR_CAP;
+    static constexpr int OFF_STEP = (OFF_WM + (MASK_BYTES > LIST_BYTES ? MASK_BYTES : LIST_BYTES) + 15) & ~15;
     static constexpr int OFF_SIDX = OFF_STEP + 4 * STEP_CAP;
-    static constexpr int OFF_LINES = OFF_SIDX + 4 * STEP_CAP;
+    static constexpr int OFF_SINFO = OFF_SIDX + 4 * STEP_CAP;
+    static constexpr int OFF_OPS = OFF_SINFO + 4 * (STEP_CAP + 4);
+    static constexpr int OFF_LINES = OFF_OPS + 4 * OPS_CAP;
     static constexpr int OFF_REC = (OFF_LINES + 2 * LINE_CAP + 7) & ~7;
-    static constexpr int FAR_CAP = (STEP_CAP / 6 + 31) & ~31;           // links that are not inline: typically 1-2 per record
-    static constexpr int OFF_FAR = (OFF_REC + (int)sizeof(LineRecF) * LINE_CAP + 15) & ~15;
-    static constexpr int SMEM_BYTES = (OFF_FAR + 12 * FAR_CAP + 127) & ~127;
+    static constexpr int SMEM_BYTES = (OFF_REC + (int)sizeof(LineRecF) * LINE_CAP + 127) & ~127;
     static constexpr int FIT = (227 * 1024) / (SMEM_BYTES + 1024);                    // CTAs per SM by shared memory
     static constexpr int REG = 1024 / THREADS < 1 ? 1 : 1024 / THREADS;               // ... leaving >= 64 registers per thread
     static constexpr int MIN_CTAS = FIT < 1 ? 1 : (FIT < REG ? FIT : REG);
     static_assert(BUF <= 65536, "step entries hold 16-bit positions");
-    static_assert(LINE_CAP < 4095, "step entries hold 12-bit record slots");
-    static_assert(STEP_CAP < 65536, "records hold 16-bit step list offsets");
+    static_assert(LINE_CAP <= 512, "step entries hold 9-bit record slots");
+    static_assert(STEP_CAP < 65536 && OPS_CAP < 65536, "records hold 16-bit list offsets");
 };
 
 // 0x80 flags at bits 7/15/23/31 -> 4-bit mask in the top nibble (no carries: the partial products
@@ -119,14 +132,13 @@ __device__ __forceinline__ bool token_is_inert(const uint8_t* s, uint32_t a, uin
     }
     return true;
 }
-
-// a tag the aligner always writes first: "AS:i:<int>" -- inert when nothing after the prefix is a ':'
 __device__ __forceinline__ bool no_colon(const uint8_t* s, uint32_t a, uint32_t b) {
     if (b - a > 48u) return false;
     bool ok = true;
     for (uint32_t q = a; q < b; q++) ok &= s[q] != ':';
     return ok;
 }
+// a tag the aligner always writes first: "AS:i:<int>" -- inert when nothing after the prefix is a ':'
 __device__ __forceinline__ bool tag_is_inert(const uint8_t* s, uint32_t a, uint32_t b) {
     if (b - a >= 6u && s[a] == 'A' && s[a + 1] == 'S' && s[a + 2] == ':' && s[a + 3] == 'i' && s[a + 4] == ':')
         return no_colon(s, a + 5u, b);
@@ -200,30 +212,40 @@ __device__ __forceinline__ unsigned long long sep_word(const unsigned long long*
     return m;
 }
 
+__device__ __forceinline__ bool is_lower(uint32_t c) { return c - 'a' <= 25u; }
+
+// status of a record = the worse of its two roles
+__device__ __forceinline__ uint32_t rec_status(const LineRecF& R) { return max((uint32_t)R.stA, (uint32_t)R.stB); }
+
 template <class G>
 __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(ChunkArgs A, Tables T) {
     constexpr uint32_t THREADS = G::THREADS;
+    constexpr uint32_t NWARPS = THREADS / 32;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t s_nlines, s_nsteps, s_nfar;
+    __shared__ uint32_t s_nlines, s_nsteps, s_nops, s_nfar, s_ndel;
+    __shared__ uint32_t s_wsum[NWARPS];
 
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint8_t* const buf = smem;
-    uint16_t* const wm16 = reinterpret_cast<uint16_t*>(smem + G::OFF_WM);
-    uint16_t* const sm16 = reinterpret_cast<uint16_t*>(smem + G::OFF_SM);
-    const unsigned long long* const wm64 = reinterpret_cast<const unsigned long long*>(smem + G::OFF_WM);
-    const unsigned long long* const sm64 = reinterpret_cast<const unsigned long long*>(smem + G::OFF_SM);
+    unsigned long long* const wm64 = reinterpret_cast<unsigned long long*>(smem + G::OFF_WM);
+    unsigned long long* const sm64 = reinterpret_cast<unsigned long long*>(smem + G::OFF_SM);
+    uint32_t* const far = reinterpret_cast<uint32_t*>(smem + G::OFF_FAR);      // {from, to, separator position} (reuses the masks)
+    uint32_t* const dels = reinterpret_cast<uint32_t*>(smem + G::OFF_DEL);     // {step, first del, last del}     (reuses the masks)
     uint32_t* const steps = reinterpret_cast<uint32_t*>(smem + G::OFF_STEP);
     uint32_t* const sidx = reinterpret_cast<uint32_t*>(smem + G::OFF_SIDX);
+    uint32_t* const sinfo = reinterpret_cast<uint32_t*>(smem + G::OFF_SINFO);  // step-length prefix
+    uint32_t* const ops = reinterpret_cast<uint32_t*>(smem + G::OFF_OPS);
     uint16_t* const lines = reinterpret_cast<uint16_t*>(smem + G::OFF_LINES);
     LineRecF* const recs = reinterpret_cast<LineRecF*>(smem + G::OFF_REC);
-    uint32_t* const far = reinterpret_cast<uint32_t*>(smem + G::OFF_FAR);     // {from, to, separator position} x FAR_CAP
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
         s_nlines = 0;
         s_nsteps = 0;
+        s_nops = 0;
         s_nfar = 0;
+        s_ndel = 0;
     }
     __syncthreads();
 
@@ -252,14 +274,11 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         const uint32_t lim = 16u + (uint32_t)(min(hi, A.nbytes) - t0);     // data ends here in the buffer
         const int64_t base_off = A.file_off + (int64_t)t0 - 16;            // file offset of buf[0]
         const uint32_t own_end = 16u + owned;                               // records starting before this are ours
-        const uint32_t nvec = (lim + 15u) >> 4, nvec4 = (nvec + 3u) & ~3u, nwords = nvec4 >> 2;
+        const uint32_t nvec = (lim + 15u) >> 4, nwords = (nvec + 3u) >> 2;
         mbar_wait(&mbar, parity);
         parity ^= 1;
 
         // ================= scan: whitespace / separator masks, record starts =================
-        // one thread per 64 bytes (four LDS.128): one 64-bit word of each mask per thread and iteration
-        unsigned long long* const wm64w = reinterpret_cast<unsigned long long*>(smem + G::OFF_WM);
-        unsigned long long* const sm64w = reinterpret_cast<unsigned long long*>(smem + G::OFF_SM);
         for (uint32_t g = tid; g < nwords; g += THREADS) {
             unsigned long long wm = 0, sm = 0;
             uint32_t oth = 0, hib = 0;
@@ -280,8 +299,8 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             if (g == 0) keep &= ~0xFFFFull;                                 // positions 0..15 are before the tile
             wm &= keep;
             sm &= keep;
-            wm64w[g] = wm;
-            sm64w[g] = sm;
+            wm64[g] = wm;
+            sm64[g] = sm;
             if (g == 0 && tile == 0 && owned > 0u) {                        // the chunk starts at a record start
                 const uint32_t j = atomicAdd(&s_nlines, 1u);
                 if (j < (uint32_t)G::LINE_CAP) lines[j] = 16;
@@ -336,178 +355,238 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         }
         const uint32_t n_lines = n_lines_all;
 
-        // ================= records: one thread per record =================
-        for (uint32_t l = tid; l < n_lines; l += THREADS) {
-            bool slow = false, done = false;
-            int why = WHY_LONG;
+        // ================= records: two threads per record =================
+        for (uint32_t item = tid; item < 2u * n_lines; item += THREADS) {
+            const bool roleA = item >= n_lines;
+            const uint32_t l = roleA ? item - n_lines : item;
+            LineRecF& R = recs[l];
             const uint32_t ls = lines[l];
-            uint32_t ns = 0, a5 = 0, b5 = 0;
-            int32_t mapq = 0, plen = 0, start = 0, pend = 0, n_tot = 0;
-            uint32_t nstar = 0;
-            uint16_t star[MAX_STARS] = {0, 0, 0, 0};
             uint32_t wi = ls >> 6;
             unsigned long long wmk = wm64[wi] & (~0ull << (ls & 63u));
-            uint32_t e[15];
-            e[0] = ls - 1u;
-            bool gaps_ok = true;
-            uint32_t tabs = 0xFFFFFFFFu;                      // AND of (byte == '\t') over the first 12 boundaries
+            uint32_t st = ST_FAST;
+            int why = WHY_LONG;
+            if (!roleA) {
+                // ---------------- role B: columns, filters, coordinates, path steps
+                uint32_t e[13];
+                e[0] = ls - 1u;
+                bool ran_off = false, gaps_ok = true;
+                uint32_t tabs = 0xFFFFFFFFu;                  // AND of (byte == '\t') over the first 11 boundaries
 #pragma unroll
-            for (int j = 1; j <= 14; j++) {
-                e[j] = 0;
-                if (!slow) {
-                    if (!next_ws(wm64, nwords, wi, wmk, e[j])) slow = true;          // record runs past the look-ahead
-                    else if (j <= 12) {
-                        gaps_ok &= e[j] - e[j - 1] >= 2u;                            // no empty column
-                        if (j < 12) tabs &= buf[e[j]] == '\t' ? 0xFFFFFFFFu : 0u;
+                for (int j = 1; j <= 12; j++) {
+                    e[j] = 0;
+                    if (!ran_off) {
+                        if (!next_ws(wm64, nwords, wi, wmk, e[j])) ran_off = true;   // record runs past the look-ahead
+                        else {
+                            gaps_ok &= e[j] - e[j - 1] >= 2u;                        // no empty column
+                            if (j < 12) tabs &= buf[e[j]] == '\t' ? 0xFFFFFFFFu : 0u;
+                        }
                     }
                 }
-            }
-            // 11 single tabs, then a tab (tags follow) or the end of a 12-column record
-            bool no_tags = false;
-            if (!slow) {
-                const uint32_t c12 = buf[e[12]];
-                no_tags = c12 == '\n';
-                if (!gaps_ok || tabs == 0u || (c12 != '\t' && !no_tags)) { slow = true; why = WHY_COLUMNS; }
-            }
-            if (!slow) {
-                slow = !small_uint(buf, e[11] + 1u, e[12], mapq);
-                why = WHY_INTS;
+                bool slow = ran_off, done = false, no_tags = false;
+                int32_t mapq = 0, plen = 0, start = 0, pend = 0;
                 if (!slow) {
-                    if ((int64_t)mapq < A.thr) { sink.reject(); done = true; }                       // REF:143-146
-                    else if (e[6] - e[5] == 2u && buf[e[5] + 1u] == '*') done = true;                 // REF:147-148
+                    // 11 single tabs, then a tab (tags follow) or the end of a 12-column record
+                    const uint32_t c12 = buf[e[12]];
+                    no_tags = c12 == '\n';
+                    if (!gaps_ok || tabs == 0u || (c12 != '\t' && !no_tags)) { slow = true; why = WHY_COLUMNS; }
                 }
-            }
-            if (!slow && !done)
-                slow = !small_uint(buf, e[6] + 1u, e[7], plen) || !small_uint(buf, e[7] + 1u, e[8], start) ||
-                       !small_uint(buf, e[8] + 1u, e[9], pend);
-            // ---- tags: [inert]* cs [inert]* dv in any order, within the first few tags
-            uint32_t cs_a = 0, cs_b = 0, dv_a = 0, dv_b = 0;
-            if (!slow && !done && no_tags) { slow = true; why = WHY_TAGS; }       // no dv tag: ValueError (REF:179), slow path reports
-            if (!slow && !done) {
-                why = WHY_TAGS;
-                uint32_t a = e[12] + 1u, b = e[13];
-                for (int j = 13;; j++) {
-                    if (!cs_b && b - a >= 3u && buf[a] == 'c' && buf[a + 1] == 's' && buf[a + 2] == ':') {
-                        cs_a = a;
-                        cs_b = b;
-                    } else if (!dv_b && b - a >= 6u && buf[a] == 'd' && buf[a + 1] == 'v' && buf[a + 2] == ':' &&
-                               buf[a + 3] == 'f' && buf[a + 4] == ':' && pt::is_digit(buf[a + 5]) &&
-                               no_colon(buf, a + 5u, b)) {
-                        dv_a = a + 5u;
-                        dv_b = b;
-                    } else if (!tag_is_inert(buf, a, b)) {
+                if (!slow) {
+                    why = WHY_INTS;
+                    slow = !small_uint(buf, e[11] + 1u, e[12], mapq);
+                    if (!slow) {
+                        if ((int64_t)mapq < A.thr) { sink.reject(); done = true; }                   // REF:143-146
+                        else if (e[6] - e[5] == 2u && buf[e[5] + 1u] == '*') done = true;             // REF:147-148
+                    }
+                }
+                if (!slow && !done)
+                    slow = !small_uint(buf, e[6] + 1u, e[7], plen) || !small_uint(buf, e[7] + 1u, e[8], start) ||
+                           !small_uint(buf, e[8] + 1u, e[9], pend);
+                if (!slow && !done && no_tags) { slow = true; why = WHY_TAGS; }   // no dv tag: ValueError (REF:179), slow path reports
+                // ---- path column (REF:185-197): it must start with a separator; count the steps
+                uint32_t ns = 0, off = 0, a5 = 0, b5 = 0;
+                if (!slow && !done) {
+                    why = WHY_PATH;
+                    a5 = e[5] + 1u;
+                    b5 = e[6];
+                    for (uint32_t w = a5 >> 6; w <= ((b5 - 1u) >> 6); w++) ns += (uint32_t)__popcll(sep_word(sm64, w, a5, b5));
+                    if (ns == 0u || ns > (uint32_t)MAX_STEPS || !((sm64[a5 >> 6] >> (a5 & 63u)) & 1ull)) {
                         slow = true;
-                        break;
-                    }
-                    if (cs_b && dv_b) break;
-                    if (buf[b] == '\n' || j >= 18) { slow = true; break; }          // end of the record: a tag is missing
-                    a = b + 1u;
-                    if (j == 13) b = e[14];
-                    else if (!next_ws(wm64, nwords, wi, wmk, b)) { slow = true; break; }
-                }
-            }
-            // ---- dv filter (REF:172-180).  The reference parses cs first, but that has no side effects and cannot
-            //      raise, so a record that dv filters out needs no cs class
-            if (!slow && !done) {
-                const uint32_t f = buf[dv_a], g = dv_a + 1u < dv_b ? buf[dv_a + 1u] : 0u, h = dv_a + 2u < dv_b ? buf[dv_a + 2u] : 0u;
-                if (f == '0' && g == '.' && h == '0') {
-                    // 0.0xxx: never greater
-                } else if (pt::dv_token_greater(buf, (int)dv_a, (int)dv_b)) {
-                    done = true;
-                }
-            }
-            // ---- cs string: "cs:Z:" then ':'<digits> and '*'<2 letters> ops only (REF:10-37)
-            if (!slow && !done) {
-                why = WHY_CS;
-                if (cs_b - cs_a < 7u || buf[cs_a + 3] != 'Z' || buf[cs_a + 4] != ':') slow = true;
-                uint32_t q = cs_a + 5u;
-                uint64_t one;
-                if (!slow && buf[q] == ':' && cs_b - q - 1u <= 7u && step_id(buf, q + 1u, cs_b - q - 1u, one) && one != 0u) {
-                    n_tot = (int32_t)one;                                    // cs:Z::<n> -- a perfect match
-                    q = cs_b;
-                }
-                while (!slow && q < cs_b) {
-                    const uint32_t c = buf[q];
-                    if (c == ':') {
-                        uint32_t v = 0, nd = 0;
-                        q++;
-                        while (q < cs_b && pt::is_digit(buf[q])) { v = v * 10u + (buf[q] - '0'); q++; nd++; }
-                        if (nd == 0u || nd > 7u || v == 0u) slow = true;
-                        n_tot += (int32_t)v;
-                    } else if (c == '*') {
-                        if (q + 3u > cs_b || nstar >= (uint32_t)MAX_STARS || n_tot > 0xFFFF) { slow = true; break; }
-                        const uint32_t x = buf[q + 1], y = buf[q + 2];
-                        if ((x | 0x20u) - 'a' > 25u || (y | 0x20u) - 'a' > 25u) { slow = true; break; }
-#pragma unroll
-                        for (int k = 0; k < MAX_STARS; k++)
-                            if ((uint32_t)k == nstar) star[k] = (uint16_t)n_tot;
-                        nstar++;
-                        n_tot += 1;
-                        q += 3u;
                     } else {
-                        slow = true;
+                        off = atomicAdd(&s_nsteps, ns + 1u);                      // any order: a record only needs a contiguous range
+                        if (off + ns + 1u > (uint32_t)G::STEP_CAP) {              // list full: slow path
+                            slow = true;
+                            why = WHY_STEPS_FULL;
+                            for (uint32_t i = off; i < (uint32_t)G::STEP_CAP; i++) steps[i] = SE_INVALID;
+                        }
                     }
                 }
-                if (n_tot <= 0 || n_tot > MAX_NTOT) slow = true;
-            }
-            // ---- path column (REF:185-197): it must start with a separator; count the steps
-            uint32_t off = 0;
-            if (!slow && !done) {
-                why = WHY_PATH;
-                a5 = e[5] + 1u;
-                b5 = e[6];
-                for (uint32_t w = a5 >> 6; w <= ((b5 - 1u) >> 6); w++) ns += (uint32_t)__popcll(sep_word(sm64, w, a5, b5));
-                if (ns == 0u || ns > (uint32_t)MAX_STEPS || !((sm64[a5 >> 6] >> (a5 & 63u)) & 1ull)) {
-                    slow = true;
-                } else {
-                    off = atomicAdd(&s_nsteps, ns);                               // any order: a record only needs a contiguous range
-                    if (off + ns > (uint32_t)G::STEP_CAP) {                       // list full: slow path
-                        slow = true;
-                        why = WHY_STEPS_FULL;
-                        for (uint32_t i = off; i < (uint32_t)G::STEP_CAP; i++) steps[i] = SE_INVALID;
+                st = slow ? ST_DEFER : (done ? ST_DONE : ST_FAST);
+                R.ls = (uint16_t)ls;
+                R.stB = (uint8_t)st;
+                R.whyB = (uint8_t)why;
+                R.nsteps = 0;
+                R.s0 = 0;
+                if (st == ST_FAST) {
+                    R.start = start;
+                    R.end_rel1 = plen - pend - 1;
+                    R.s0 = (uint16_t)off;
+                    R.nsteps = (uint16_t)ns;
+                    // ---- one entry per path step, then the sentinel (end of the column)
+                    const uint32_t common = (l << SE_SLOT_SHIFT) | (buf[a5] == '<' ? SE_REV : 0u);
+                    uint32_t i = off;
+                    for (uint32_t w = a5 >> 6; w <= ((b5 - 1u) >> 6); w++) {
+                        unsigned long long m = sep_word(sm64, w, a5, b5);
+                        while (m) {
+                            const uint32_t q = 64u * w + (uint32_t)(__ffsll((long long)m) - 1);
+                            m &= m - 1ull;
+                            steps[i] = q | common | (i == off ? SE_FIRST : 0u) | (i + 1u == off + ns ? SE_LAST : 0u);
+                            i++;
+                        }
+                    }
+                    steps[off + ns] = b5 | (l << SE_SLOT_SHIFT) | SE_SENT;
+                }
+            } else {
+                // ---------------- role A: tags -> dv filter, cs ops
+                uint32_t e11 = 0, e12 = 0, pos = 0;
+                bool ran_off = false;
+#pragma unroll 1
+                for (int j = 1; j <= 12 && !ran_off; j++) {
+                    if (!next_ws(wm64, nwords, wi, wmk, pos)) ran_off = true;
+                    e11 = e12;
+                    e12 = pos;
+                }
+                // role B decides about everything up to column 12; here: is there anything left to do?
+                int32_t mapq = 0;
+                bool idle = ran_off || buf[e12] != '\t' || !small_uint(buf, e11 + 1u, e12, mapq) || (int64_t)mapq < A.thr;
+                bool slow = false, done = false;
+                uint32_t cs_a = 0, cs_b = 0, dv_a = 0, dv_b = 0;
+                if (!idle) {
+                    // ---- tags: [inert]* cs [inert]* dv in any order, within the first few tags
+                    why = WHY_TAGS;
+                    uint32_t a = e12 + 1u, b = 0;
+                    if (!next_ws(wm64, nwords, wi, wmk, b)) slow = true;
+                    for (int j = 13; !slow; j++) {
+                        if (!cs_b && b - a >= 3u && buf[a] == 'c' && buf[a + 1] == 's' && buf[a + 2] == ':') {
+                            cs_a = a;
+                            cs_b = b;
+                        } else if (!dv_b && b - a >= 6u && buf[a] == 'd' && buf[a + 1] == 'v' && buf[a + 2] == ':' &&
+                                   buf[a + 3] == 'f' && buf[a + 4] == ':' && pt::is_digit(buf[a + 5]) &&
+                                   no_colon(buf, a + 5u, b)) {
+                            dv_a = a + 5u;
+                            dv_b = b;
+                        } else if (!tag_is_inert(buf, a, b)) {
+                            slow = true;
+                            break;
+                        }
+                        if (cs_b && dv_b) break;
+                        if (buf[b] == '\n' || j >= 18) { slow = true; break; }      // end of the record: a tag is missing
+                        a = b + 1u;
+                        if (!next_ws(wm64, nwords, wi, wmk, b)) { slow = true; break; }
+                    }
+                    // ---- dv filter (REF:172-180).  The reference parses cs first, but that has no side effects and
+                    //      cannot raise, so a record that dv filters out needs no cs class
+                    if (!slow) {
+                        const uint32_t f = buf[dv_a], g = dv_a + 1u < dv_b ? buf[dv_a + 1u] : 0u, h = dv_a + 2u < dv_b ? buf[dv_a + 2u] : 0u;
+                        if (f == '0' && g == '.' && h == '0') {
+                            // 0.0xxx: never greater
+                        } else if (pt::dv_token_greater(buf, (int)dv_a, (int)dv_b)) {
+                            done = true;
+                        }
+                    }
+                    // ---- cs string (REF:10-37): "cs:Z:" then ops spelled the way an aligner spells them:
+                    //      ':'<digits>  '*'<2 letters>  '-'<letters>  '+'<letters>  '='<LETTERS>, every length >= 1
+                    if (!slow && !done) {
+                        why = WHY_CS;
+                        uint32_t n_tot = 0, nops = 0, op_off = 0;
+                        int32_t start_add = 0;
+                        if (cs_b - cs_a < 7u || buf[cs_a + 3] != 'Z' || buf[cs_a + 4] != ':') slow = true;
+                        uint32_t q = cs_a + 5u;
+                        uint64_t one;
+                        if (!slow && buf[q] == ':' && cs_b - q - 1u <= 7u && step_id(buf, q + 1u, cs_b - q - 1u, one) && one != 0u) {
+                            // cs:Z::<n> -- a perfect match
+                            op_off = atomicAdd(&s_nops, 1u);
+                            if (op_off < (uint32_t)G::OPS_CAP) ops[op_off] = OP_MATCH | ((uint32_t)one << 3);
+                            else slow = true;
+                            nops = 1;
+                            n_tot = (uint32_t)one;
+                        } else if (!slow) {
+                            // every op takes at least two bytes: room for (bytes / 2) ops is enough
+                            const uint32_t room = min((cs_b - q) >> 1, (uint32_t)MAX_OPS);
+                            op_off = atomicAdd(&s_nops, room);
+                            if (op_off + room > (uint32_t)G::OPS_CAP) slow = true;
+                            while (!slow && q < cs_b) {
+                                const uint32_t c = buf[q++];
+                                uint32_t kind, len = 0;
+                                if (c == ':') {
+                                    kind = OP_MATCH;
+                                    uint32_t nd = 0;
+                                    while (q < cs_b && pt::is_digit(buf[q])) { len = len * 10u + (buf[q] - '0'); q++; nd++; }
+                                    if (nd == 0u || nd > 7u) slow = true;
+                                } else if (c == '*') {
+                                    kind = OP_SUB;
+                                    if (q + 2u > cs_b || !is_lower(buf[q]) || !is_lower(buf[q + 1])) slow = true;
+                                    q += 2u;
+                                    len = 1;
+                                } else if (c == '-' || c == '+') {
+                                    kind = c == '-' ? OP_DEL : OP_INS;
+                                    while (q < cs_b && is_lower(buf[q])) { q++; len++; }
+                                } else if (c == '=') {
+                                    kind = OP_EQ;
+                                    while (q < cs_b && buf[q] - 'A' <= 24u) { q++; len++; }      // 'A'..'Y': "cs:Z:" cannot hide in here
+                                } else {
+                                    slow = true;
+                                    kind = 0;
+                                }
+                                // the text must end where the next op starts
+                                if (q < cs_b) {
+                                    const uint32_t d = buf[q];
+                                    if (d != ':' && d != '*' && d != '-' && d != '+' && d != '=') slow = true;
+                                }
+                                if (len == 0u || len > (uint32_t)MAX_NTOT || nops >= room) slow = true;
+                                if (!slow) {
+                                    ops[op_off + nops] = kind | (len << 3);
+                                    nops++;
+                                    n_tot += len;
+                                    if (n_tot > (uint32_t)MAX_NTOT) slow = true;
+                                }
+                            }
+                            if (nops == 0u) slow = true;
+                            // cigar_clipping (REF:40-50): only when there are exactly two ops
+                            if (!slow && nops == 2u) {
+                                const uint32_t o0 = ops[op_off], o1 = ops[op_off + 1u];
+                                if ((o0 & 7u) == OP_INS && (o1 & 7u) == OP_MATCH) {
+                                    start_add = (int32_t)(o0 >> 3);
+                                    ops[op_off] = o1;
+                                    nops = 1;
+                                    n_tot = o1 >> 3;
+                                } else if ((o0 & 7u) == OP_MATCH && (o1 & 7u) == OP_INS) {
+                                    nops = 1;
+                                    n_tot = o0 >> 3;
+                                }
+                            }
+                        }
+                        R.n_tot = n_tot;
+                        R.op_off = (uint16_t)op_off;
+                        R.nops = (uint8_t)nops;
+                        R.start_add = start_add;
                     }
                 }
-            }
-            LineRecF& R = recs[l];
-            R.ls = (uint16_t)ls;
-            R.status = slow ? ST_DEFER : (done ? ST_DONE : ST_FAST);
-            R.nstar = (uint8_t)why;                                        // reason, read by `walk` when status is ST_DEFER
-            R.nsteps = 0;
-            if (!slow && !done) {
-                R.start = start;
-                R.end_rel1 = plen - pend - 1;
-                R.n_tot = n_tot;
-                R.s0 = (uint16_t)off;
-                R.nsteps = (uint16_t)ns;
-                R.b5 = (uint16_t)b5;
-#pragma unroll
-                for (int k = 0; k < MAX_STARS; k++) R.star[k] = star[k];
-                R.nstar = (uint8_t)nstar;
-                // ---- one entry per path step
-                const uint32_t common = (l << SE_SLOT_SHIFT) | (buf[a5] == '<' ? SE_REV : 0u);
-                uint32_t i = off;
-                for (uint32_t w = a5 >> 6; w <= ((b5 - 1u) >> 6); w++) {
-                    unsigned long long m = sep_word(sm64, w, a5, b5);
-                    while (m) {
-                        const uint32_t q = 64u * w + (uint32_t)(__ffsll((long long)m) - 1);
-                        m &= m - 1ull;
-                        steps[i] = q | common | (i == off ? SE_FIRST : 0u) | (i + 1u == off + ns ? SE_LAST : 0u);
-                        i++;
-                    }
-                }
+                st = slow ? ST_DEFER : (done ? ST_DONE : ST_FAST);
+                R.stA = (uint8_t)st;
+                R.whyA = (uint8_t)why;
             }
         }
-        __syncthreads();                                                    // ---- records + step list complete
-        const uint32_t n_steps = min(s_nsteps, (uint32_t)G::STEP_CAP);
+        __syncthreads();                                                    // ---- records, ops, step list complete
+        const uint32_t n_ent = min(s_nsteps, (uint32_t)G::STEP_CAP);       // step entries incl. sentinels
         if (tid == 0) s_nlines = 0;                                         // everyone has read it
 
         // ================= ids: one thread per path step: id -> node index =================
-        for (uint32_t s = tid; s < n_steps; s += THREADS) {
+        for (uint32_t s = tid; s < n_ent; s += THREADS) {
             const uint32_t se = steps[s];
             uint32_t idx = NONE32;
-            if (se != SE_INVALID) {
+            if (se != SE_INVALID && !(se & SE_SENT)) {
                 const uint32_t p = se & SE_POS_MASK;
-                const uint32_t end = (se & SE_LAST) ? (uint32_t)recs[se >> SE_SLOT_SHIFT].b5 : (steps[s + 1u] & SE_POS_MASK);
+                const uint32_t end = steps[s + 1u] & SE_POS_MASK;           // next separator, or the sentinel
                 uint64_t id;
                 uint32_t ix;
                 if (buf[p] == ((se & SE_REV) ? '<' : '>') && step_id(buf, p + 1u, end - p - 1u, id) && sink.id_to_idx(id, ix)) {
@@ -517,71 +596,180 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             }
             sidx[s] = idx;                                                  // NONE32: KeyError in the reference, `walk` hands the record over
         }
-        __syncthreads();                                                    // ---- node indices complete; the bytes are dead
+        __syncthreads();                                                    // ---- node indices complete; the bytes and the masks are dead
         if (tid == 0) {
             s_nsteps = 0;
+            s_nops = 0;
             s_nfar = 0;
+            s_ndel = 0;
             const uint32_t nxt = tile + gridDim.x;
             if (nxt < A.n_tiles) issue_load(nxt);                           // overlaps walk + count
         }
 
-        // ================= walk: one thread per record: cs coordinates, slow-path conditions =================
-        for (uint32_t l = tid; l < n_lines; l += THREADS) {
-            LineRecF& R = recs[l];
-            uint32_t st = R.status;
-            if (st == ST_FAST) {
-                const uint32_t s0 = R.s0, ns = R.nsteps, n_tot = (uint32_t)R.n_tot, nstar = R.nstar;
-                const int32_t start = R.start, end_rel1 = R.end_rel1;
-                uint32_t x[MAX_STARS];
-#pragma unroll
-                for (int j = 0; j < MAX_STARS; j++) x[j] = R.star[j];
-                uint32_t pos = 0, prev = NONE32;
-                bool bad = false;
-#pragma unroll 4
-                for (uint32_t k = 0; k < ns; k++) {
-                    const uint32_t idx = sidx[s0 + k];
-                    const uint32_t len = sink.load_len(idx == NONE32 ? 0u : idx);
-                    // unknown id (KeyError REF:214), collapsible duplicate (REF:188), cs used up (IndexError REF:227)
-                    bad |= idx == NONE32 || idx == prev || len == pt::NODE_LEN_ABSENT || pos >= n_tot;
-                    int64_t L = (int64_t)len;
-                    if (k == 0u) L -= start;                                // REF:215-216
-                    if (k + 1u == ns) L -= end_rel1;                        // REF:217-218
-                    bad |= L <= 0;                                          // a node without bases drops out of the walk: slow path
-                    const uint32_t Lc = L <= 0 ? 0u : (L > (int64_t)L_CLAMP ? L_CLAMP : (uint32_t)L);
-                    const uint32_t endp = min(pos + Lc, n_tot);
-                    uint32_t stars_in = 0;
-                    if (nstar != 0u) {
-#pragma unroll
-                        for (int j = 0; j < MAX_STARS; j++) stars_in += ((uint32_t)j < nstar && x[j] >= pos && x[j] < endp) ? 1u : 0u;
+        // ================= walk 1: step lengths and their block-wide prefix sum =================
+        const uint32_t per = (n_ent + THREADS - 1u) / THREADS;              // consecutive entries per thread
+        const uint32_t sa = min(tid * per, n_ent), sb = min(sa + per, n_ent);
+        {
+            uint32_t local = 0;
+            for (uint32_t s = sa; s < sb; s++) {
+                const uint32_t se = steps[s];
+                uint32_t Lc = 0;
+                if (se != SE_INVALID && !(se & SE_SENT)) {
+                    LineRecF& R = recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK];
+                    if (rec_status(R) == ST_FAST) {
+                        const uint32_t idx = sidx[s];
+                        const uint32_t len = sink.load_len(idx == NONE32 ? 0u : idx);
+                        // unknown id: KeyError (REF:214); collapsible duplicate (REF:188): the slow path redoes the record
+                        if (idx == NONE32 || len == pt::NODE_LEN_ABSENT || (!(se & SE_FIRST) && idx == sidx[s - 1u])) {
+                            R.stB = ST_DEFER;
+                            R.whyB = WHY_WALK;
+                        } else {
+                            int64_t L = (int64_t)len;
+                            if (se & SE_FIRST) L -= (int64_t)R.start + R.start_add;           // REF:215-216
+                            if (se & SE_LAST) L -= R.end_rel1;                                // REF:217-218
+                            Lc = L <= 0 ? 0u : (L > (int64_t)L_CLAMP ? L_CLAMP : (uint32_t)L);
+                        }
                     }
-                    if (stars_in < endp - pos) steps[s0 + k] |= SE_COUNTS;  // the slice holds a ':' piece (REF:63-94)
-                    pos += Lc;
-                    prev = idx;
                 }
-                if (bad) {
-                    st = ST_DEFER;
-                    for (uint32_t k = 0; k < ns; k++) steps[s0 + k] = SE_INVALID;
+                sinfo[s] = local;
+                local += Lc;
+            }
+            uint32_t incl = local;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += y;
+            }
+            if (lane == 31u) s_wsum[warp] = incl;
+            __syncthreads();
+            uint32_t basev = incl - local;
+            for (uint32_t w = 0; w < warp; w++) basev += s_wsum[w];
+            for (uint32_t s = sa; s < sb; s++) {
+                const uint32_t g = sinfo[s] + basev;
+                sinfo[s] = g;
+                const uint32_t se = steps[s];
+                if (se != SE_INVALID && (se & SE_FIRST)) recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK].base = g;
+            }
+        }
+        __syncthreads();                                                    // ---- prefix sums, record bases, duplicate / unknown ids known
+
+        // ================= walk 2: every step folds the cs ops that overlap its node =================
+        for (uint32_t s = tid; s < n_ent; s += THREADS) {
+            const uint32_t se = steps[s];
+            if (se == SE_INVALID || (se & SE_SENT)) continue;
+            LineRecF& R = recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK];
+            if (rec_status(R) != ST_FAST) continue;
+            const uint32_t Ak = sinfo[s] - R.base;                          // cs coordinate where this node starts
+            const uint32_t Lk = sinfo[s + 1u] - sinfo[s];                   // the sentinel closes the last step
+            if (Lk == 0u) {                                                 // no bases left for this node: it is not in `align`
+                steps[s] = se | SE_DROPPED;
+                continue;
+            }
+            const uint32_t n_tot = R.n_tot;
+            if (Ak >= n_tot) {                                              // cs used up before the path ends: IndexError (REF:227)
+                R.stB = ST_DEFER;
+                R.whyB = WHY_WALK;
+                continue;
+            }
+            const uint32_t Bk = min(Ak + Lk, n_tot);
+            const uint32_t* op = ops + R.op_off;
+            const uint32_t nops = R.nops;
+            // pieces of the node = ops overlapping [Ak, Bk), clipped; compact_align as a running fold (REF:63-94)
+            uint32_t j = 0, o_start = 0, o_end = op[0] >> 3;
+            while (o_end <= Ak) {                                           // ends before the node starts (j < nops: Ak < n_tot)
+                j++;
+                o_start = o_end;
+                o_end += op[j] >> 3;
+            }
+            uint32_t nP = 0, nQ = 0, p0 = 0, qlast_op = 0, qlast_len = 0, first_op = 0, first_len = 0, n_count = 0;
+            for (;;) {
+                const uint32_t kind = op[j] & 7u;
+                const uint32_t take = min(o_end, Bk) - max(o_start, Ak);
+                bool push = false;
+                uint32_t push_len = take;
+                if (nP == 0u) { p0 = kind; push = kind != OP_SUB; }
+                else if (nQ == 0u) { push = true; push_len = take + 1u; }
+                else if (kind == qlast_op || kind == OP_SUB) qlast_len += take;
+                else push = true;
+                if (push) {
+                    if (nQ == 1u) { first_op = qlast_op; first_len = qlast_len; }
+                    qlast_op = kind;
+                    qlast_len = push_len;
+                    nQ++;
+                    if (kind != OP_DEL && kind != OP_SUB) n_count++;
+                }
+                nP++;
+                if (o_end >= Bk || j + 1u >= nops) break;
+                j++;
+                o_start = o_end;
+                o_end += op[j] >> 3;
+            }
+            if (nQ == 1u) { first_op = qlast_op; first_len = qlast_len; }
+            if (nP == 1u && (p0 == OP_DEL || p0 == OP_INS)) {               // clear_align drops the node (REF:101-102)
+                steps[s] = se | SE_DROPPED;
+                continue;
+            }
+            if (n_count > 3u) {                                             // more counting ops than the entry holds: slow path
+                R.stB = ST_DEFER;
+                R.whyB = WHY_WALK;
+                continue;
+            }
+            steps[s] = se | (n_count << SE_NCNT_SHIFT);
+            const bool first_del = nQ > 0u && first_op == OP_DEL, last_del = nQ > 0u && qlast_op == OP_DEL;
+            if (first_del || last_del) {                                    // deletion-derived IL/OL keys (REF:281-297,317-333)
+                const uint32_t k = atomicAdd(&s_ndel, 1u);
+                if (k < (uint32_t)G::DEL_CAP) {
+                    dels[3u * k] = s;
+                    dels[3u * k + 1u] = first_len | (first_del ? 0x80000000u : 0u);
+                    dels[3u * k + 2u] = qlast_len | (last_del ? 0x80000000u : 0u);
+                } else {
+                    R.stB = ST_DEFER;                                       // list full: slow path (nothing counted yet)
+                    R.whyB = WHY_WALK;
                 }
             }
-            if (st == ST_DEFER) defer_line(T, t0 + R.ls - 16u, A.file_off, R.status == ST_DEFER ? (int)R.nstar : (int)WHY_WALK);
         }
-        __syncthreads();                                                    // ---- nothing counted so far; hand-overs done
+        __syncthreads();                                                    // ---- every hand-over decision is made; nothing counted so far
+        for (uint32_t l = tid; l < n_lines; l += THREADS) {
+            const LineRecF& R = recs[l];
+            if (rec_status(R) == ST_DEFER) defer_line(T, t0 + R.ls - 16u, A.file_off, R.stB == ST_DEFER ? R.whyB : R.whyA);
+        }
 
-        // ================= count: one thread per path step =================
+        // surviving neighbours of step s inside its record (dropped nodes are skipped)
+        auto prev_survivor = [&](uint32_t s) -> uint32_t {                  // NONE32: s is the first survivor
+            uint32_t t = s;
+            while (!(steps[t] & SE_FIRST)) {
+                t--;
+                if (!(steps[t] & SE_DROPPED)) return t;
+            }
+            return NONE32;
+        };
+        auto next_survivor = [&](uint32_t s) -> uint32_t {                  // NONE32: s is the last survivor
+            uint32_t t = s;
+            while (!(steps[t] & SE_LAST)) {
+                t++;
+                if (!(steps[t] & SE_DROPPED)) return t;
+            }
+            return NONE32;
+        };
+
+        // ================= count: one thread per surviving step =================
         // UB steps per thread and iteration: their node-record loads (one 16-byte LDG each, L2 hits
         // thanks to the prefetch) are all in flight before the first one is used.
         {
             constexpr int UB = 2;
-            for (uint32_t s00 = 0; s00 < n_steps; s00 += THREADS * UB) {
+            for (uint32_t s00 = 0; s00 < n_ent; s00 += THREADS * UB) {
                 uint32_t se_[UB], idx_[UB];
                 DevSink::Hot hot_[UB];
 #pragma unroll
                 for (int u = 0; u < UB; u++) {
                     const uint32_t s = s00 + THREADS * u + tid;
-                    se_[u] = s < n_steps ? steps[s] : SE_INVALID;
+                    uint32_t se = s < n_ent ? steps[s] : SE_INVALID;
+                    if (se != SE_INVALID && ((se & (SE_SENT | SE_DROPPED)) || rec_status(recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK]) != ST_FAST))
+                        se = SE_INVALID;
+                    se_[u] = se;
                     idx_[u] = 0;
                     hot_[u].len = 0; hot_[u].il = 0; hot_[u].ol = 0; hot_[u].d01 = 0;
-                    if (se_[u] != SE_INVALID) {
+                    if (se != SE_INVALID) {
                         idx_[u] = sidx[s];
                         hot_[u] = sink.load_hot(idx_[u]);
                     }
@@ -591,23 +779,25 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                     const uint32_t s = s00 + THREADS * u + tid;
                     const uint32_t se = se_[u], idx = idx_[u];
                     if (se == SE_INVALID) continue;
-                    const bool first = (se & SE_FIRST) != 0u, last = (se & SE_LAST) != 0u, rev = (se & SE_REV) != 0u;
-                    const int64_t n_count = (se & SE_COUNTS) ? 1 : 0;
+                    const bool rev = (se & SE_REV) != 0u;
+                    const uint32_t ps = prev_survivor(s), nx = next_survivor(s);
+                    const bool first = ps == NONE32, last = nx == NONE32;   // among the surviving nodes (REF:276-353: i == 0, i == last)
+                    const int64_t n_count = (int64_t)(se >> SE_NCNT_SHIFT);
                     const bool il_cond = rev ? !last : !first, ol_cond = rev ? !first : !last;
                     const uint64_t stamp = (uint64_t)(base_off + (int64_t)(se & SE_POS_MASK) + 1) << 2;
-                    // this thread owns the link that LEAVES its node: (k -> k+1) forward, (k -> k-1) reverse
+                    // this thread owns the link that LEAVES its node: to the next survivor forward, to the previous one reverse
                     const bool have_edge = rev ? !first : !last;
                     int eslot = -1;
                     uint32_t other = 0;
                     if (have_edge) {
-                        other = rev ? sidx[s - 1u] : sidx[s + 1u];
+                        other = sidx[rev ? ps : nx];
                         eslot = DevSink::inline_slot(hot_[u].d01, idx, other);
                     }
                     sink.bump(idx, eslot);                                              // REF:263-269, 357-363
                     if (have_edge && eslot < 0) {
                         // not inline: hash-table work, collected and done below with every lane busy.  Stamped like
                         // the reference's insertion: when the later of the two steps is reached
-                        const uint32_t ep = rev ? (se & SE_POS_MASK) : (steps[s + 1u] & SE_POS_MASK);
+                        const uint32_t ep = rev ? (se & SE_POS_MASK) : (steps[nx] & SE_POS_MASK);
                         const uint32_t j = atomicAdd(&s_nfar, 1u);
                         if (j < (uint32_t)G::FAR_CAP) {
                             far[3u * j] = idx;
@@ -629,16 +819,38 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             const uint32_t n_far = min(s_nfar, (uint32_t)G::FAR_CAP);
             for (uint32_t j = tid; j < n_far; j += THREADS)
                 sink.edge_far(far[3u * j], far[3u * j + 1u], (uint64_t)(base_off + (int64_t)far[3u * j + 2u] + 1) << 2);
+            // deletion-derived keys: position of the deletion inside the node, IL or OL by orientation
+            const uint32_t n_del = min(s_ndel, (uint32_t)G::DEL_CAP);
+            for (uint32_t j = tid; j < n_del; j += THREADS) {
+                const uint32_t s = dels[3u * j], f = dels[3u * j + 1u], g = dels[3u * j + 2u];
+                const uint32_t se = steps[s];
+                if (rec_status(recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK]) != ST_FAST) continue;
+                const uint32_t idx = sidx[s];
+                const int64_t len = (int64_t)sink.load_len(idx);
+                const bool rev = (se & SE_REV) != 0u;
+                const bool not_first = prev_survivor(s) != NONE32, not_last = next_survivor(s) != NONE32;
+                const bool first_del = (f >> 31) != 0u, last_del = (g >> 31) != 0u;
+                const int64_t first_len = f & 0x7FFFFFFFu, last_len = g & 0x7FFFFFFFu;     // >= 1: no op is empty here
+                const uint64_t stamp = (uint64_t)(base_off + (int64_t)(se & SE_POS_MASK) + 1) << 2;
+                if (!rev) {
+                    if (first_del && not_first) sink.sparse(idx, 0, first_len, stamp | 0u);               // REF:282-289
+                    if (last_del && not_last) sink.sparse(idx, 1, len - last_len - 1, stamp | 2u);         // REF:290-297
+                } else {
+                    if (first_del && not_first) sink.sparse(idx, 1, len - 1 - first_len, stamp | 0u);      // REF:318-325
+                    if (last_del && not_last) sink.sparse(idx, 0, last_len, stamp | 2u);                   // REF:326-333
+                }
+            }
         }
-        // no barrier here: the next tile's scan writes only the masks and the record list, which
-        // nobody reads any more, and its first barrier orders everything else
+        // no barrier here: the next tile's scan writes the masks (= the two lists, nobody reads them any more
+        // once its first barrier is passed ... which every thread reaches only after finishing the loops above)
+        __syncthreads();
     }
 
     // rejected-record count: warp reduce, one RED per warp
     uint32_t r = sink.rej;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-    if ((tid & 31u) == 0u && r) atomicAdd(&T.sc[SC_REJ], (unsigned long long)r);
+    if (lane == 0u && r) atomicAdd(&T.sc[SC_REJ], (unsigned long long)r);
     if (tid == 0) {
         if (my_lines) atomicAdd(&T.sc[SC_LINES], my_lines);
         if (my_tiles) atomicAdd(&T.sc[SC_TILES], my_tiles);
