@@ -221,7 +221,7 @@ template <class G>
 __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(ChunkArgs A, Tables T) {
     constexpr uint32_t THREADS = G::THREADS;
     constexpr uint32_t NWARPS = THREADS / 32;
-    extern __shared__ __align__(128) uint8_t smem[];
+    PT_DYNAMIC_SMEM(smem);
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t s_nlines, s_nsteps, s_nops, s_nfar, s_ndel;
     __shared__ uint32_t s_wsum[NWARPS];
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         const uint64_t lo = tile ? t0 - 16 : 0;
         const uint64_t hi = min(t0 + G::TILE + G::OV, nbytes16);
         const uint32_t bytes = (uint32_t)(hi - lo);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        fence_async_smem();
         mbar_expect_tx(&mbar, bytes);
         tma_load_1d(buf + (tile ? 0u : 16u), A.gaf + lo, bytes, &mbar);
     };

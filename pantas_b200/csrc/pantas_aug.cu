@@ -27,63 +27,7 @@
 
 namespace {
 
-#include "tables.cuh"
-
-// ---------------------------------------------------------------- TMA helpers
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-// 1-D bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// ---------------------------------------------------------------- main kernel
-
-struct ChunkArgs {
-    const uint8_t* gaf;
-    uint64_t nbytes;
-    int64_t file_off;
-    int64_t thr;
-    uint32_t tile;       // bytes per tile, multiple of 16
-    uint32_t over;       // look-ahead bytes after the tile, multiple of 16
-    uint32_t list_cap;   // line-start slots in shared memory
-    uint32_t n_tiles;
-};
-
-// why a record is handed to the slow path (pt_debug_counters)
-enum { WHY_LONG = 0, WHY_COLUMNS, WHY_INTS, WHY_TAGS, WHY_CS, WHY_PATH, WHY_STEPS_FULL, WHY_WALK, WHY_LINES_FULL, WHY_V1 };
-
-__device__ __forceinline__ void defer_line(const Tables& T, uint64_t chunk_pos, int64_t file_off, int why = WHY_V1) {
-    atomicAdd(&T.sc[SC_WHY + why], 1ull);
-    const unsigned long long j = atomicAdd(&T.sc[SC_NDEFER], 1ull);
-    if (j < T.deferred_cap) T.deferred[j] = (uint32_t)chunk_pos;
-    else report_error(T, pt::PT_X_DEFER_FULL, file_off + (int64_t)chunk_pos);
-}
-
-#include "fast_tiles.cuh"
+#include "aug_kernels.cuh"
 
 constexpr int N_BUCKETS = 32;       // walk order: perfect-match records by path length, then the rest
 
@@ -243,35 +187,6 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) augment_tiles_kernel(ChunkA
         if (my_lines) atomicAdd(&T.sc[SC_LINES], my_lines);
         if (my_tiles) atomicAdd(&T.sc[SC_TILES], my_tiles);
     }
-}
-
-// Records that did not fit a tile's look-ahead window: same logic, bytes from global memory.
-__global__ void __launch_bounds__(128) augment_deferred_kernel(ChunkArgs A, Tables T) {
-    DevSink sink(T);
-    const unsigned long long n = min(T.sc[SC_NDEFER], (unsigned long long)T.deferred_cap);
-    for (unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; j < n;
-         j += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint64_t a = T.deferred[j];
-        const uint64_t a16 = a & ~15ull;                     // word loads need an aligned base
-        pt::LineCtx cx;
-        cx.s = A.gaf + a16;
-        const uint64_t rest = A.nbytes - a16;
-        cx.lim = rest > 0x7ffffff0ull ? 0x7ffffff0 : (int)rest;
-        cx.lim_final = true;
-        cx.base_off = A.file_off + (int64_t)a16;
-        pt::process_line(cx, (int)(a - a16), A.thr, sink);
-    }
-    uint32_t r = sink.rej;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-    if ((threadIdx.x & 31) == 0 && r) atomicAdd(&T.sc[SC_REJ], (unsigned long long)r);
-}
-
-// After both kernels of a chunk: fold the per-chunk scalars.
-__global__ void end_chunk_kernel(Tables T) {
-    T.sc[SC_DEFERRED_TOTAL] += min(T.sc[SC_NDEFER], (unsigned long long)T.deferred_cap);
-    T.sc[SC_NDEFER] = 0;
-    T.sc[SC_TILE_NEXT] = 0;
 }
 
 }  // namespace

@@ -137,7 +137,11 @@ struct DevSink {
         return true;
     }
     __device__ __forceinline__ void prefetch_node(uint32_t idx) {
+#ifndef PT_EMU
         asm volatile("prefetch.global.L2 [%0];" ::"l"(&T.nodes[idx]));
+#else
+        (void)idx;
+#endif
     }
     // L2 (always current): first-touch stamps only ever decrease, len / d01 never change
     __device__ __forceinline__ Hot load_hot(uint32_t idx) {

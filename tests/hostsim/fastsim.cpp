@@ -1,0 +1,153 @@
+// tests/hostsim/fastsim.cpp -- TEST HARNESS, NOT PRODUCT CODE.
+//
+// Runs the REAL device code of the augment pass (pantas_b200/csrc/aug_kernels.cuh: table build, the
+// fast path of fast_tiles.cuh, the exact per-record kernel, epoch fold, export) on the CPU through the
+// fibre emulator of cuda_emu.h, following the launch sequence of pantas_aug.cu (pt_set_graph,
+// pt_reset_counts, pt_process_chunk, pt_export_dense / pt_export_side).  The build container has no
+// GPU: this is how CPU-only tests fuzz the fast path against the oracle.  Nothing under pantas_b200/
+// loads this.
+#include "cuda_emu.h"
+
+#include <algorithm>
+
+#include "../../pantas_b200/csrc/line_core.cuh"
+
+namespace {
+#include "../../pantas_b200/csrc/aug_kernels.cuh"
+
+uint64_t pow2_at_least(uint64_t v) {
+    uint64_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+template <class T> T* zalloc(uint64_t n) { return (T*)calloc(n ? n : 1, sizeof(T)); }
+
+template <class G>
+void run_fast(unsigned grid, ChunkArgs A, const Tables& T) {
+    A.n_tiles = (uint32_t)((A.nbytes + G::TILE - 1) / G::TILE);
+    if (grid > A.n_tiles) grid = A.n_tiles;
+    emu::launch(grid, G::THREADS, G::SMEM_BYTES, [&] { fastp::augment_fast_kernel<G>(A, T); });
+}
+
+}  // namespace
+
+extern "C" {
+
+struct fastsim_result {
+    int64_t* sums;
+    int64_t* stamps;
+    uint64_t* novel;
+    uint64_t n_novel;
+    uint64_t* sparse;
+    uint64_t n_sparse;
+    uint64_t err_offset;
+    int err_code;
+    uint64_t n_deferred;
+    uint64_t why[16];
+};
+
+// geo: 0 = tiny test tiles (1 KiB), 1 = 4 KiB tiles, 2 = the production geometry
+int fastsim_run(const uint8_t* gaf, uint64_t nbytes, uint64_t file_off, int64_t thr, const uint32_t* node_len,
+                uint64_t n_nodes, uint32_t min_id, const uint64_t* edge_keys, uint64_t n_edges, int geo, uint32_t grid,
+                fastsim_result* out) {
+    const uint64_t N = n_nodes, E = n_edges;
+    Tables T;
+    memset(&T, 0, sizeof T);
+    T.n_nodes = N;
+    T.min_id = min_id;
+    const uint64_t novel_cap = 1u << 12, sparse_cap = 1u << 12;
+    T.novel_mask = novel_cap - 1;
+    T.sparse_mask = sparse_cap - 1;
+    T.nodes = zalloc<NodeRec>(N);
+    T.il_adj32 = zalloc<int32_t>(N);
+    T.ol_adj32 = zalloc<int32_t>(N);
+    T.inl_edge = zalloc<uint32_t>(2 * N);
+    T.nc64 = zalloc<long long>(N);
+    T.il_adj64 = zalloc<long long>(N);
+    T.ol_adj64 = zalloc<long long>(N);
+    T.il_st64 = zalloc<unsigned long long>(N);
+    T.ol_st64 = zalloc<unsigned long long>(N);
+    T.rc64 = zalloc<long long>(E);
+    T.novel = zalloc<SideSlot>(novel_cap);
+    T.sparse = zalloc<SideSlot>(sparse_cap);
+    T.sc = zalloc<unsigned long long>(SC_COUNT);
+    T.deferred_cap = nbytes / 2 + 4096;
+    T.deferred = zalloc<uint32_t>(T.deferred_cap);
+    unsigned long long stats[2] = {0, 0};
+    const unsigned KG = 2, KB = 64;
+
+    // ---- pt_set_graph
+    emu::launch(KG, KB, 0, [&] { init_nodes_kernel(T, node_len); });
+    if (E) emu::launch(KG, KB, 0, [&] { inline_edges_kernel(T, edge_keys, E, stats); });
+    const uint64_t ovf_cap = pow2_at_least(stats[1] * 2 + 16);
+    T.ovf_mask = ovf_cap - 1;
+    T.ovf = zalloc<OvfSlot>(ovf_cap);
+    T.ovf_edge = zalloc<uint32_t>(ovf_cap);
+    emu::launch(KG, KB, 0, [&] { clear_ovf_kernel(T.ovf, T.ovf_edge, ovf_cap, 1); });
+    if (E) emu::launch(KG, KB, 0, [&] { ovf_edges_kernel(T, edge_keys, E, stats); });
+    // ---- pt_reset_counts
+    emu::launch(KG, KB, 0, [&] { reset_nodes_kernel(T); });
+    emu::launch(KG, KB, 0, [&] { clear_side_kernel(T.novel, novel_cap); });
+    emu::launch(KG, KB, 0, [&] { clear_side_kernel(T.sparse, sparse_cap); });
+    T.sc[SC_ERR] = ~0ull;
+    T.epoch_base = (int64_t)file_off;
+
+    // ---- pt_process_chunk: the chunk must be 16-byte aligned and readable up to the next multiple of 16
+    uint8_t* raw = (uint8_t*)malloc(nbytes + 96);
+    uint8_t* dev = (uint8_t*)(((uintptr_t)raw + 15) & ~(uintptr_t)15);
+    memset(dev, 0xEE, nbytes + 64);          // garbage after the data, like a reused staging buffer
+    if (nbytes) memcpy(dev, gaf, nbytes);
+    ChunkArgs A;
+    memset(&A, 0, sizeof A);
+    A.gaf = dev;
+    A.nbytes = nbytes;
+    A.file_off = (int64_t)file_off;
+    A.thr = thr;
+    if (nbytes) {
+        typedef fastp::Geo<1024, 256, 64> G0;
+        typedef fastp::Geo<4096, 512, 128> G1;
+        typedef fastp::Geo<16384, 1024, 256> G2;
+        if (geo == 0) run_fast<G0>(grid, A, T);
+        else if (geo == 1) run_fast<G1>(grid, A, T);
+        else run_fast<G2>(grid, A, T);
+        emu::launch(2, 128, 0, [&] { augment_deferred_kernel(A, T); });
+        emu::launch(1, 1, 0, [&] { end_chunk_kernel(T); });
+    }
+    // ---- pt_export_dense / pt_export_side
+    emu::launch(KG, KB, 0, [&] { fold_epoch_kernel(T); });
+    out->sums = (int64_t*)calloc(3 * N + E + 4, sizeof(int64_t));
+    out->stamps = (int64_t*)calloc(2 * N + 1, sizeof(int64_t));
+    emu::launch(KG, KB, 0, [&] { export_nodes_kernel(T, (long long*)out->sums, (long long*)out->stamps, E); });
+    emu::launch(KG, KB, 0, [&] { export_ovf_kernel(T, (long long*)out->sums + 3 * N); });
+    unsigned long long cursor[2] = {0, 0};
+    out->novel = (uint64_t*)calloc(3 * novel_cap + 1, sizeof(uint64_t));
+    out->sparse = (uint64_t*)calloc(3 * sparse_cap + 1, sizeof(uint64_t));
+    emu::launch(KG, KB, 0, [&] { compact_side_kernel(T.novel, novel_cap, (unsigned long long*)out->novel, novel_cap, &cursor[0]); });
+    emu::launch(KG, KB, 0, [&] { compact_side_kernel(T.sparse, sparse_cap, (unsigned long long*)out->sparse, sparse_cap, &cursor[1]); });
+    out->n_novel = cursor[0];
+    out->n_sparse = cursor[1];
+    out->n_deferred = T.sc[SC_DEFERRED_TOTAL];
+    for (int k = 0; k < 16; k++) out->why[k] = T.sc[SC_WHY + k];
+    if (T.sc[SC_ERR] != ~0ull) {
+        out->err_offset = T.sc[SC_ERR] >> 8;
+        out->err_code = (int)(T.sc[SC_ERR] & 0xff);
+    } else {
+        out->err_offset = 0;
+        out->err_code = 0;
+    }
+    free(raw);
+    free(T.nodes); free(T.il_adj32); free(T.ol_adj32); free(T.inl_edge); free(T.nc64); free(T.il_adj64); free(T.ol_adj64);
+    free(T.il_st64); free(T.ol_st64); free(T.rc64); free(T.novel); free(T.sparse); free(T.sc); free(T.deferred); free(T.ovf);
+    free(T.ovf_edge);
+    return 0;
+}
+
+void fastsim_free(fastsim_result* r) {
+    free(r->sums);
+    free(r->stamps);
+    free(r->novel);
+    free(r->sparse);
+    memset(r, 0, sizeof *r);
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+"""The fast path (pantas_b200/csrc/fast_tiles.cuh) and the kernels around it, run thread by thread on
+the CPU by tests/hostsim/cuda_emu.h (test harness) and compared with the reference's golden outputs and
+the oracle.  Same code as the sm_100a build; the GPU parity tests (-m gpu) cover the real thing.
+"""
+import io
+
+import pytest
+
+import fuzzgen
+from conftest import GOLDEN, UNSUPPORTED_BY_DESIGN
+from hostsim_util import run_fastsim
+from oracle.oracle import run_oracle
+from pantas_b200.counts import Counts, merge_flat
+from pantas_b200.errors import PantasDataError
+from pantas_b200.gfa import load_graph, write_augmented
+from pantas_b200.shard import shard_bounds_bytes
+
+
+def pipeline(tmp_path, gfa: str, gaf: str, thr=20, geo=0, grid=2, shards=1, stats=None):
+    gp = tmp_path / "g.gfa"
+    gp.write_bytes(gfa.encode())
+    try:
+        graph = load_graph(str(gp))
+    except PantasDataError:
+        return ("raise", 0)
+    data = gaf.encode()
+    bounds = shard_bounds_bytes(data, shards)
+    parts, worst = [], None
+    for r in range(shards):
+        lo, hi = bounds[r], bounds[r + 1]
+        flat, code, off, ndef, why = run_fastsim(graph, data[lo:hi], thr, file_off=lo, geo=geo, grid=grid)
+        if stats is not None:
+            stats["deferred"] = stats.get("deferred", 0) + ndef
+            stats["lines"] = stats.get("lines", 0) + int(flat.sums[-3])
+        if code and (worst is None or (off, code) < worst):
+            worst = (off, code)
+        parts.append(flat)
+    if worst:
+        return ("raise" if worst[1] < 20 else "unsupported", worst[1])
+    counts = Counts.from_flat(merge_flat(parts))
+    out = io.StringIO()
+    try:
+        write_augmented(str(gp), graph, counts, out)
+    except PantasDataError:
+        return ("raise", 0)
+    return ("ok", out.getvalue().encode(), counts.rej)
+
+
+@pytest.mark.parametrize("geo", [0, 1])
+def test_golden(geo, tmp_path):
+    for case in GOLDEN:
+        thr = 20 if case["thr"] is None else case["thr"]
+        res = pipeline(tmp_path, case["gfa"], case["gaf"], thr, geo=geo)
+        if case["name"] in UNSUPPORTED_BY_DESIGN:
+            assert res[0] == "unsupported", (case["name"], res)
+        elif case["returncode"] != 0:
+            assert res[0] == "raise", (case["name"], res)
+        else:
+            assert res[0] == "ok", (case["name"], res)
+            assert res[1] == case["stdout"], case["name"]
+            assert res[2] == case["rej"], case["name"]
+
+
+@pytest.mark.parametrize("seed", range(7300, 7340))
+def test_fuzz_vs_oracle(seed, tmp_path):
+    gfa, gaf = fuzzgen.make_case(seed, n_nodes=8 + seed % 20, n_reads=60 + 40 * (seed % 3), weird=(seed % 2 == 0),
+                                 crlf=(seed % 6 == 0), trailing_newline=(seed % 4 != 0))
+    orc = run_oracle(gaf.encode(), gfa.encode())
+    res = pipeline(tmp_path, gfa, gaf, geo=seed % 2, grid=1 + seed % 3, shards=1 + seed % 3)
+    assert orc.rc == 0
+    assert res[0] == "ok", res
+    assert res[1] == orc.out
+    assert res[2] == orc.rej
+
+
+@pytest.mark.parametrize("seed", range(7400, 7430))
+def test_fuzz_risky_vs_oracle(seed, tmp_path):
+    gfa, gaf = fuzzgen.make_risky_case(seed)
+    orc = run_oracle(gaf.encode(), gfa.encode())
+    res = pipeline(tmp_path, gfa, gaf, geo=seed % 2)
+    if orc.rc == 0:
+        assert res[0] == "ok" and res[1] == orc.out and res[2] == orc.rej
+    else:
+        assert res[0] == "raise", (res, orc.err)
+
+
+def test_synthetic_reads_stay_on_the_fast_path(tmp_path):
+    """Generator output (bench input): bit-exact, and (almost) nothing is handed to the per-record kernel."""
+    from pantas_b200.synth import SynthGraph
+
+    sg = SynthGraph("tiny", seed=11)
+    gp = tmp_path / "g.gfa"
+    sg.write_gfa(str(gp))
+    buf, n = sg.gaf(300, first_pair=0)
+    gaf = bytes(buf)
+    orc = run_oracle(gaf, gp.read_bytes())
+    assert orc.rc == 0
+    for geo in (1, 2):
+        st = {}
+        res = pipeline(tmp_path, gp.read_text(), gaf.decode(), geo=geo, grid=3, stats=st)
+        assert res[0] == "ok" and res[1] == orc.out and res[2] == orc.rej
+        assert st["lines"] == n
+        assert st["deferred"] <= n // 50, st
