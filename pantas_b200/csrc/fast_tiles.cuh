@@ -1,20 +1,30 @@
-// fast_tiles.cuh -- the fast path of the augment kernel (included by pantas_aug.cu inside its
-// anonymous namespace, after tables.cuh, the TMA helpers, ChunkArgs and defer_line()).
+// fast_tiles.cuh -- the fast path of the augment kernel (included by aug_kernels.cuh after tables.cuh,
+// the TMA helpers, ChunkArgs and defer_line()).
 //
 // Reference loop body: /root/reference/scripts/alignments_augmentation_from_gaf.py:142-363 (REF:n).
 //
 // A persistent CTA takes tiles of the GAF chunk (TILE bytes + OV bytes of look-ahead, one 1-D TMA
-// bulk copy, UBLKCP) and runs data-parallel phases over the tile in shared memory:
+// bulk copy, UBLKCP) and runs data-parallel phases over the tile in shared memory.  Nothing in the
+// first half walks a record serially: every phase is "one thread per <small thing>", and where a
+// thing sits inside its record comes from prefix counts, not from a per-record loop.
 //
-//   scan     one thread per 64 bytes (4 x LDS.128), branch-free SWAR: a 64-bit whitespace mask and a
-//            64-bit path-separator ('>' '<') mask per group; record starts ('\n') go to a list;
-//            lone '\r' and non-ASCII bytes are (fatal) errors.
-//   records  TWO threads per record, both walking the whitespace mask from the record start:
-//              B  the 12 column boundaries (single tabs, no empty column), MAPQ and '*' filters
-//                 (REF:143-148), the three coordinates (REF:151-153), then the separator mask of
-//                 the path column -> one entry per path step (+ a sentinel) in the tile's step list;
-//              A  the tags: first cs token, first dv:f: token (REF:154-160,172-180), the dv filter,
-//                 and the cs string parsed into the tile's op pool (REF:10-50, incl. cigar_clipping).
+//   scan     one thread per 16-byte vector (LDS.128, conflict free), branch-free SWAR: 16-bit pieces of
+//            three masks -- whitespace (<= 0x20), newline, path separator ('>' '<').  Lone '\r' and
+//            non-ASCII bytes are (fatal) errors; any whitespace other than tab / newline raises a
+//            tile flag that switches on the per-column tab check below.
+//   prefix   per 64-byte mask word: exclusive counts of whitespace, separators and record starts
+//            before the word, and the start of the record that is open there (block-wide scan).
+//   columns  one thread per mask word walks its whitespace bits: bit -> (record, column number) from
+//            the prefix counts -> the column-boundary table ecol[record][column]; newlines open the
+//            next record (lines[], ncol[]).
+//   fields   small independent items, one thread each:
+//              A   tags of a record: first cs token, first dv:f: token (REF:154-160,172-180), the dv
+//                  filter, the cs string parsed into the tile's op pool (REF:10-50, cigar_clipping)
+//              T0  column shape, MAPQ and '*' filters (REF:143-148), path column shape, the record's
+//                  sentinel in the step list
+//              T1  the three coordinates (REF:151-153)
+//              S   one thread per mask word walks its separator bits: bit -> step-list slot
+//                  (separator ordinal + record number), entry = position | record | first/last/rev
 //            Anything unusual -- other whitespace in the columns, integers that are not plain
 //            digits, tags that could confuse the reference's regexes, '~' or zero-length or oddly
 //            spelled cs ops -- hands the record to the exact per-record path (line_core.cuh via
@@ -44,24 +54,23 @@ constexpr int MAX_OPS = 48;                   // more cs ops: slow path
 constexpr uint32_t L_CLAMP = 1u << 23;        // step lengths are clamped here (> any cs length the fast path takes)
 constexpr int32_t MAX_NTOT = 1 << 22;
 
-enum : uint8_t { ST_FAST = 0, ST_DONE = 1, ST_DEFER = 2 };      // per role; a record's status is the maximum
+enum : uint8_t { ST_FAST = 0, ST_DONE = 1, ST_DEFER = 2 };      // per role
 enum : uint32_t { OP_MATCH = 0, OP_SUB = 1, OP_DEL = 2, OP_INS = 3, OP_EQ = 4 };   // ':' '*' '-' '+' '='  (op = kind | len << 3)
 
-struct __align__(4) LineRecF {
-    int32_t start;        // int(tokens[7])                                    (role B)
-    int32_t end_rel1;     // int(tokens[6]) - int(tokens[8]) - 1               (role B)
+struct __align__(8) LineRecF {
+    int32_t start;        // int(tokens[7])                                    (role T1)
+    int32_t end_rel1;     // int(tokens[6]) - int(tokens[8]) - 1               (role T1)
     int32_t start_add;    // cigar_clipping: start_pos += len of a leading '+' (role A, REF:46-47)
     uint32_t n_tot;       // sum of the cs op lengths                          (role A)
     uint32_t base;        // step-length prefix at the record's first step     (walk)
-    uint16_t s0;          // first entry of the record in the step list        (role B)
-    uint16_t nsteps;      //                                                   (role B)
-    uint16_t ls;          // buffer position of the record's first byte        (role B)
+    uint16_t ls;          // buffer position of the record's first byte        (role T0)
     uint16_t op_off;      // first op of the record in the op pool             (role A)
     uint8_t nops;         //                                                   (role A)
-    uint8_t stA, stB;     // ST_* per role; walk raises stB
-    uint8_t whyA, whyB;   // WHY_* when the role says ST_DEFER
-    uint8_t pad[3];
+    uint8_t stA, stB, stC;   // ST_* per role; walk raises stB
+    uint8_t whyA, whyB;   // WHY_* when the role says ST_DEFER (T1: always WHY_INTS)
+    uint8_t pad[2];
 };
+static_assert(sizeof(LineRecF) == 32, "record layout");
 
 // step list entry
 constexpr uint32_t SE_POS_MASK = 0xFFFFu;     // bits 0..15  buffer position of the separator (sentinel: end of the path column)
@@ -71,35 +80,47 @@ constexpr uint32_t SE_FIRST = 1u << 25, SE_LAST = 1u << 26, SE_REV = 1u << 27, S
 constexpr int SE_NCNT_SHIFT = 30;             // bits 30..31 counting ops of the compacted slice (0..3)
 constexpr uint32_t SE_INVALID = 0xFFFFFFFFu;
 
+// per mask word: counts before the word, packed
+constexpr unsigned long long PRE_SUMS = 0xFFFFFFFFFFFFull;    // bits 0..15 whitespace, 16..31 separators, 32..47 record starts
+constexpr int PRE_LS_SHIFT = 48;                              // bits 48..63 first byte of the record open at the word (0: none)
+
 template <int TILE_, int OV_, int THREADS_>
 struct Geo {
     static constexpr int TILE = TILE_;
     static constexpr int OV = OV_;
     static constexpr int THREADS = THREADS_;
+    static constexpr int NCOLS = 20;                              // column boundaries kept per record: 12 columns + 6 tags
     static constexpr int BUF = 16 + TILE + OV + 16;               // [pre 16][tile][look-ahead][pad 16]
     static constexpr int NV = ((16 + TILE + OV) / 16 + 3) & ~3;   // 16-byte vectors, padded to whole 64-bit mask words
-    static constexpr int LINE_CAP = ((TILE + 111) / 112 + 7) & ~7;   // typical: one record per 300 bytes
+    static constexpr int NW = NV / 4;                             // 64-bit mask words
+    static constexpr int LINE_CAP = ((TILE + OV + 111) / 112 + 7) & ~7;   // typical: one record per 300 bytes
     static constexpr int STEP_CAP = (((TILE + OV) / 12 + LINE_CAP) + 63) & ~63;   // typical: 14 steps per 300 bytes, + sentinels
     static constexpr int OPS_CAP = (LINE_CAP * 4 + 63) & ~63;
     static constexpr int FAR_CAP = (STEP_CAP / 8 + 31) & ~31;     // links that are not inline: typically 1-2 per record
     static constexpr int DEL_CAP = (LINE_CAP / 2 + 31) & ~31;     // steps with deletion-derived keys
-    static constexpr int MASK_BYTES = 4 * NV;                     // whitespace + separator masks; dead after `records`:
-    static constexpr int LIST_BYTES = 12 * FAR_CAP + 12 * DEL_CAP;    // ... the two end-of-tile lists reuse the space
+    // region X, first life (scan .. fields): three masks, the per-word prefix, column boundaries, record starts
     static constexpr int OFF_WM = (BUF + 127) & ~127;
-    static constexpr int OFF_SM = OFF_WM + 2 * NV;
-    static constexpr int OFF_FAR = OFF_WM;
-    static constexpr int OFF_DEL = OFF_WM + 12 * FAR_CAP;
-    static constexpr int OFF_STEP = (OFF_WM + (MASK_BYTES > LIST_BYTES ? MASK_BYTES : LIST_BYTES) + 15) & ~15;
+    static constexpr int OFF_NL = OFF_WM + 8 * NW;
+    static constexpr int OFF_SM = OFF_NL + 8 * NW;
+    static constexpr int OFF_PRE = OFF_SM + 8 * NW;
+    static constexpr int OFF_ECOL = OFF_PRE + 8 * (NW + 1);        // + one word of totals (a position may be the end of the data)
+    static constexpr int OFF_LINES = OFF_ECOL + 2 * NCOLS * LINE_CAP;
+    static constexpr int OFF_NCOL = OFF_LINES + 2 * LINE_CAP;
+    static constexpr int X_END1 = OFF_NCOL + LINE_CAP;
+    // region X, second life (walk .. count): step-length prefix and the two end-of-tile lists
+    static constexpr int OFF_SINFO = OFF_WM;
+    static constexpr int OFF_FAR = OFF_SINFO + 4 * (STEP_CAP + 4);
+    static constexpr int OFF_DEL = OFF_FAR + 12 * FAR_CAP;
+    static constexpr int X_END2 = OFF_DEL + 12 * DEL_CAP;
+    static constexpr int OFF_STEP = ((X_END1 > X_END2 ? X_END1 : X_END2) + 15) & ~15;
     static constexpr int OFF_SIDX = OFF_STEP + 4 * STEP_CAP;
-    static constexpr int OFF_SINFO = OFF_SIDX + 4 * STEP_CAP;
-    static constexpr int OFF_OPS = OFF_SINFO + 4 * (STEP_CAP + 4);
-    static constexpr int OFF_LINES = OFF_OPS + 4 * OPS_CAP;
-    static constexpr int OFF_REC = (OFF_LINES + 2 * LINE_CAP + 7) & ~7;
+    static constexpr int OFF_OPS = OFF_SIDX + 4 * STEP_CAP;
+    static constexpr int OFF_REC = (OFF_OPS + 4 * OPS_CAP + 7) & ~7;
     static constexpr int SMEM_BYTES = (OFF_REC + (int)sizeof(LineRecF) * LINE_CAP + 127) & ~127;
     static constexpr int FIT = (227 * 1024) / (SMEM_BYTES + 1024);                    // CTAs per SM by shared memory
     static constexpr int REG = 1024 / THREADS < 1 ? 1 : 1024 / THREADS;               // ... leaving >= 64 registers per thread
     static constexpr int MIN_CTAS = FIT < 1 ? 1 : (FIT < REG ? FIT : REG);
-    static_assert(BUF <= 65536, "step entries hold 16-bit positions");
+    static_assert(BUF < 65536, "step entries and prefix words hold 16-bit positions");
     static_assert(LINE_CAP <= 512, "step entries hold 9-bit record slots");
     static_assert(STEP_CAP < 65536 && OPS_CAP < 65536, "records hold 16-bit list offsets");
 };
@@ -214,38 +235,52 @@ __device__ __forceinline__ unsigned long long sep_word(const unsigned long long*
 
 __device__ __forceinline__ bool is_lower(uint32_t c) { return c - 'a' <= 25u; }
 
-// status of a record = the worse of its two roles
-__device__ __forceinline__ uint32_t rec_status(const LineRecF& R) { return max((uint32_t)R.stA, (uint32_t)R.stB); }
+__device__ __forceinline__ uint32_t flag_nl(uint32_t x) { return flag_eq7(x ^ 0x0A0A0A0Au); }
+
+// status of a record: T0's verdict (shape, MAPQ, '*') comes first -- the reference `continue`s there
+// before it looks at anything else (REF:143-148); otherwise the worse of the other two roles
+__device__ __forceinline__ uint32_t rec_status(const LineRecF& R) {
+    return R.stB != ST_FAST ? (uint32_t)R.stB : max((uint32_t)R.stA, (uint32_t)R.stC);
+}
+__device__ __forceinline__ int rec_why(const LineRecF& R) {
+    return R.stB == ST_DEFER ? (int)R.whyB : (R.stC == ST_DEFER ? (int)WHY_INTS : (int)R.whyA);
+}
 
 template <class G>
 __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(ChunkArgs A, Tables T) {
     constexpr uint32_t THREADS = G::THREADS;
     constexpr uint32_t NWARPS = THREADS / 32;
+    constexpr uint32_t NCOLS = G::NCOLS;
     PT_DYNAMIC_SMEM(smem);
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t s_nlines, s_nsteps, s_nops, s_nfar, s_ndel;
+    __shared__ uint32_t s_nops, s_nfar, s_ndel, s_oth;
+    __shared__ unsigned long long s_wsum64[NWARPS];
+    __shared__ uint32_t s_wmax[NWARPS];
     __shared__ uint32_t s_wsum[NWARPS];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint8_t* const buf = smem;
     unsigned long long* const wm64 = reinterpret_cast<unsigned long long*>(smem + G::OFF_WM);
+    unsigned long long* const nl64 = reinterpret_cast<unsigned long long*>(smem + G::OFF_NL);
     unsigned long long* const sm64 = reinterpret_cast<unsigned long long*>(smem + G::OFF_SM);
-    uint32_t* const far = reinterpret_cast<uint32_t*>(smem + G::OFF_FAR);      // {from, to, separator position} (reuses the masks)
-    uint32_t* const dels = reinterpret_cast<uint32_t*>(smem + G::OFF_DEL);     // {step, first del, last del}     (reuses the masks)
+    unsigned long long* const gpre = reinterpret_cast<unsigned long long*>(smem + G::OFF_PRE);
+    uint16_t* const ecol = reinterpret_cast<uint16_t*>(smem + G::OFF_ECOL);    // [record][NCOLS]: [0] = start - 1, [c] = c-th whitespace
+    uint16_t* const lines = reinterpret_cast<uint16_t*>(smem + G::OFF_LINES);  // first byte of record r
+    uint8_t* const ncol = smem + G::OFF_NCOL;                                  // whitespace bytes of record r incl. its newline (0: not terminated)
+    uint32_t* const sinfo = reinterpret_cast<uint32_t*>(smem + G::OFF_SINFO);  // step-length prefix           (second life of region X)
+    uint32_t* const far = reinterpret_cast<uint32_t*>(smem + G::OFF_FAR);      // {from, to, separator position}
+    uint32_t* const dels = reinterpret_cast<uint32_t*>(smem + G::OFF_DEL);     // {step, first del, last del}
     uint32_t* const steps = reinterpret_cast<uint32_t*>(smem + G::OFF_STEP);
     uint32_t* const sidx = reinterpret_cast<uint32_t*>(smem + G::OFF_SIDX);
-    uint32_t* const sinfo = reinterpret_cast<uint32_t*>(smem + G::OFF_SINFO);  // step-length prefix
     uint32_t* const ops = reinterpret_cast<uint32_t*>(smem + G::OFF_OPS);
-    uint16_t* const lines = reinterpret_cast<uint16_t*>(smem + G::OFF_LINES);
     LineRecF* const recs = reinterpret_cast<LineRecF*>(smem + G::OFF_REC);
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
-        s_nlines = 0;
-        s_nsteps = 0;
         s_nops = 0;
         s_nfar = 0;
         s_ndel = 0;
+        s_oth = 0;
     }
     __syncthreads();
 
@@ -263,6 +298,21 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         mbar_expect_tx(&mbar, bytes);
         tma_load_1d(buf + (tile ? 0u : 16u), A.gaf + lo, bytes, &mbar);
     };
+    // counts strictly below buffer position pos (< 64 * nwords): whitespace | separators << 16 | record starts << 32
+    auto pre_at = [&](uint32_t pos) -> unsigned long long {
+        const uint32_t w = pos >> 6;
+        const unsigned long long below = ~(~0ull << (pos & 63u));
+        return (gpre[w] & PRE_SUMS) + ((unsigned long long)__popcll(wm64[w] & below) | ((unsigned long long)__popcll(sm64[w] & below) << 16) |
+                                       ((unsigned long long)__popcll(nl64[w] & below) << 32));
+    };
+    auto ws_at = [&](uint32_t pos) -> uint32_t {
+        const uint32_t w = pos >> 6;
+        return ((uint32_t)gpre[w] & 0xFFFFu) + (uint32_t)__popcll(wm64[w] & ~(~0ull << (pos & 63u)));
+    };
+    auto sep_at = [&](uint32_t pos) -> uint32_t {
+        const uint32_t w = pos >> 6;
+        return ((uint32_t)(gpre[w] >> 16) & 0xFFFFu) + (uint32_t)__popcll(sm64[w] & ~(~0ull << (pos & 63u)));
+    };
 
     uint32_t tile = blockIdx.x;
     if (tile < A.n_tiles && tid == 0) issue_load(tile);
@@ -278,194 +328,169 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         mbar_wait(&mbar, parity);
         parity ^= 1;
 
-        // ================= scan: whitespace / separator masks, record starts =================
-        for (uint32_t g = tid; g < nwords; g += THREADS) {
-            unsigned long long wm = 0, sm = 0;
-            uint32_t oth = 0, hib = 0;
-            uint4 q[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) q[u] = *reinterpret_cast<const uint4*>(buf + 64u * g + 16u * u);
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t w0 = flag_ws(q[u].x), w1 = flag_ws(q[u].y), w2 = flag_ws(q[u].z), w3 = flag_ws(q[u].w);
-                wm |= (unsigned long long)mask16(w0, w1, w2, w3) << (16 * u);
-                sm |= (unsigned long long)mask16(flag_sep(q[u].x), flag_sep(q[u].y), flag_sep(q[u].z), flag_sep(q[u].w)) << (16 * u);
-                // whitespace that is not a tab: '\n' (record start), '\r' (lone: error); the rest only matters to the walkers
-                oth |= (w0 & ~flag_tab(q[u].x)) | (w1 & ~flag_tab(q[u].y)) | (w2 & ~flag_tab(q[u].z)) | (w3 & ~flag_tab(q[u].w));
-                hib |= q[u].x | q[u].y | q[u].z | q[u].w;
-            }
-            const uint32_t room = lim > 64u * g ? lim - 64u * g : 0u;       // loaded bytes in this group
-            unsigned long long keep = room < 64u ? ~(~0ull << room) : ~0ull;
-            if (g == 0) keep &= ~0xFFFFull;                                 // positions 0..15 are before the tile
-            wm &= keep;
-            sm &= keep;
-            wm64[g] = wm;
-            sm64[g] = sm;
-            if (g == 0 && tile == 0 && owned > 0u) {                        // the chunk starts at a record start
-                const uint32_t j = atomicAdd(&s_nlines, 1u);
-                if (j < (uint32_t)G::LINE_CAP) lines[j] = 16;
-            }
-            if (oth != 0u) {
-                unsigned long long om = 0;
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-                    om |= (unsigned long long)mask16(flag_ws(q[u].x) & ~flag_tab(q[u].x), flag_ws(q[u].y) & ~flag_tab(q[u].y),
-                                                     flag_ws(q[u].z) & ~flag_tab(q[u].z), flag_ws(q[u].w) & ~flag_tab(q[u].w)) << (16 * u);
-                if (g == 0 && tile != 0) keep |= 0x8000ull;                 // is the byte before the tile a newline?
-                om &= keep;
-                while (om) {
-                    const uint32_t p = 64u * g + (uint32_t)(__ffsll((long long)om) - 1);
-                    om &= om - 1ull;
-                    const uint32_t c = buf[p];
-                    if (c == '\n') {
-                        if (p + 1u < own_end) {
-                            const uint32_t j = atomicAdd(&s_nlines, 1u);
-                            if (j < (uint32_t)G::LINE_CAP) lines[j] = (uint16_t)(p + 1u);
+        // ================= scan: one thread per 16-byte vector -> 16-bit pieces of the three masks =================
+        for (uint32_t i = tid; i < (uint32_t)G::LINE_CAP / 4u; i += THREADS) reinterpret_cast<uint32_t*>(ncol)[i] = 0u;
+        {
+            uint16_t* const wm16 = reinterpret_cast<uint16_t*>(wm64);
+            uint16_t* const nl16 = reinterpret_cast<uint16_t*>(nl64);
+            uint16_t* const sm16 = reinterpret_cast<uint16_t*>(sm64);
+            for (uint32_t v = tid; v < 4u * nwords; v += THREADS) {
+                const uint4 q = *reinterpret_cast<const uint4*>(buf + 16u * v);
+                const uint32_t w0 = flag_ws(q.x), w1 = flag_ws(q.y), w2 = flag_ws(q.z), w3 = flag_ws(q.w);
+                const uint32_t n0 = flag_nl(q.x), n1 = flag_nl(q.y), n2 = flag_nl(q.z), n3 = flag_nl(q.w);
+                // whitespace that is neither tab nor newline ('\r', ' ', ...): rare, see below
+                const uint32_t o0 = w0 ^ (flag_tab(q.x) | n0), o1 = w1 ^ (flag_tab(q.y) | n1), o2 = w2 ^ (flag_tab(q.z) | n2),
+                               o3 = w3 ^ (flag_tab(q.w) | n3);
+                uint32_t w16 = mask16(w0, w1, w2, w3), n16 = mask16(n0, n1, n2, n3);
+                uint32_t s16 = mask16(flag_sep(q.x), flag_sep(q.y), flag_sep(q.z), flag_sep(q.w));
+                uint32_t oth = o0 | o1 | o2 | o3, hib = (q.x | q.y | q.z | q.w) & 0x80808080u;
+                const uint32_t room = lim > 16u * v ? lim - 16u * v : 0u;   // loaded bytes in this vector
+                const uint32_t keep = room >= 16u ? 0xFFFFu : ((1u << room) - 1u);
+                if (v == 0u) {
+                    // positions 0..15 are before the tile: all that matters is whether a record starts at 16
+                    // (the chunk starts at a record start; otherwise: is the byte before the tile a newline?)
+                    n16 = tile == 0u ? 0x8000u : (n16 & 0x8000u);
+                    w16 = n16;
+                    s16 = 0u;
+                    oth = 0u;
+                    hib = 0u;
+                } else {
+                    w16 &= keep;
+                    n16 &= keep;
+                    s16 &= keep;
+                }
+                wm16[v] = (uint16_t)w16;
+                nl16[v] = (uint16_t)n16;
+                sm16[v] = (uint16_t)s16;
+                if (oth != 0u) {
+                    uint32_t om = mask16(o0, o1, o2, o3) & keep;
+                    if (om) s_oth = 1u;                                     // fields: check every column boundary byte
+                    while (om) {
+                        const uint32_t p = 16u * v + (uint32_t)(__ffs((int)om) - 1);
+                        om &= om - 1u;
+                        if (buf[p] == '\r' && p < own_end) {
+                            const uint64_t abs_pos = t0 + p - 16u;
+                            if (abs_pos + 1 < A.nbytes && buf[p + 1] != '\n') report_error(T, pt::PT_U_BARE_CR, base_off + (int64_t)p);
                         }
-                    } else if (c == '\r' && p >= 16u && p < own_end) {
-                        const uint64_t abs_pos = t0 + p - 16u;
-                        if (abs_pos + 1 < A.nbytes && buf[p + 1] != '\n')
-                            report_error(T, pt::PT_U_BARE_CR, base_off + (int64_t)p);
                     }
                 }
-            }
-            if ((hib & 0x80808080u) != 0u) {                                // non-ASCII byte: not modelled
-                for (uint32_t p = max(64u * g, 16u); p < min(64u * g + 64u, min(lim, own_end)); p++)
-                    if (buf[p] >= 0x80u) { report_error(T, pt::PT_U_NON_ASCII, base_off + (int64_t)p); break; }
+                if (hib != 0u) {                                            // non-ASCII byte: not modelled
+                    for (uint32_t p = 16u * v; p < min(16u * v + 16u, min(lim, own_end)); p++)
+                        if (buf[p] >= 0x80u) { report_error(T, pt::PT_U_NON_ASCII, base_off + (int64_t)p); break; }
+                }
             }
         }
-        __syncthreads();                                                    // ---- masks + record list complete
-        const uint32_t n_lines_all = s_nlines;
-        if (tid == 0) { my_lines += n_lines_all; my_tiles++; }
+        __syncthreads();                                                    // ---- masks complete
 
-        if (n_lines_all > (uint32_t)G::LINE_CAP) {
-            // more records than the list holds (pathological input): all of them take the slow path
-            for (uint32_t p = 15u + tid; p + 1u < own_end; p += THREADS) {
-                const bool nl = p == 15u ? (tile == 0 || buf[p] == '\n') : buf[p] == '\n';
-                if (nl) defer_line(T, t0 + p + 1u - 16u, A.file_off, WHY_LINES_FULL);
+        // ================= prefix: counts before every mask word, start of the record open there =================
+        const uint32_t per_w = (nwords + THREADS - 1u) / THREADS;          // consecutive words per thread
+        const uint32_t wa = min(tid * per_w, nwords), wb = min(wa + per_w, nwords);
+        unsigned long long tot = 0;
+        {
+            unsigned long long local = 0;
+            uint32_t lmax = 0;
+            for (uint32_t w = wa; w < wb; w++) {
+                const unsigned long long nlv = nl64[w];
+                gpre[w] = local | ((unsigned long long)lmax << PRE_LS_SHIFT);
+                local += (unsigned long long)__popcll(wm64[w]) | ((unsigned long long)__popcll(sm64[w]) << 16) |
+                         ((unsigned long long)__popcll(nlv) << 32);
+                if (nlv) lmax = 64u * w + 64u - (uint32_t)__clzll((long long)nlv);      // last newline + 1
             }
+            unsigned long long incl = local;
+            uint32_t imax = lmax;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o);
+                const uint32_t m = __shfl_up_sync(0xffffffffu, imax, o);
+                if (lane >= (uint32_t)o) { incl += y; imax = max(imax, m); }
+            }
+            if (lane == 31u) { s_wsum64[warp] = incl; s_wmax[warp] = imax; }
+            unsigned long long basev = incl - local;
+            uint32_t bmax = __shfl_up_sync(0xffffffffu, imax, 1);
+            if (lane == 0u) bmax = 0u;
+            __syncthreads();
+#pragma unroll
+            for (uint32_t w = 0; w < NWARPS; w++) {
+                const unsigned long long sw = s_wsum64[w];
+                if (w < warp) { basev += sw; bmax = max(bmax, s_wmax[w]); }
+                tot += sw;
+            }
+            for (uint32_t w = wa; w < wb; w++) {
+                const unsigned long long g = gpre[w];
+                gpre[w] = ((g & PRE_SUMS) + basev) | ((unsigned long long)max((uint32_t)(g >> PRE_LS_SHIFT), bmax) << PRE_LS_SHIFT);
+            }
+            if (tid == 0) gpre[nwords] = tot & PRE_SUMS;                    // counts before a position just past the last word
+        }
+        const uint32_t n_sep_all = (uint32_t)(tot >> 16) & 0xFFFFu;         // separators in the loaded bytes
+        const uint32_t n_rec_all = (uint32_t)(tot >> 32) & 0xFFFFu;         // records starting in the loaded bytes (ours + look-ahead)
+        __syncthreads();                                                    // ---- prefix complete
+
+        if (n_rec_all > (uint32_t)G::LINE_CAP || n_sep_all + n_rec_all > (uint32_t)G::STEP_CAP) {
+            // more records / separators than the lists hold (pathological input): the whole tile takes the slow path
+            for (uint32_t w = tid; w < nwords; w += THREADS) {
+                unsigned long long m = nl64[w];
+                while (m) {
+                    const uint32_t p = 64u * w + (uint32_t)(__ffsll((long long)m) - 1);
+                    m &= m - 1ull;
+                    if (p + 1u < own_end) defer_line(T, t0 + p + 1u - 16u, A.file_off, WHY_LINES_FULL);
+                }
+            }
+            if (tid == 0) my_tiles++;
             __syncthreads();
             if (tid == 0) {
-                s_nlines = 0;
+                s_oth = 0;
                 const uint32_t nxt = tile + gridDim.x;
                 if (nxt < A.n_tiles) issue_load(nxt);
             }
             __syncthreads();
             continue;
         }
-        const uint32_t n_lines = n_lines_all;
 
-        // ================= records: two threads per record =================
-        for (uint32_t item = tid; item < 2u * n_lines; item += THREADS) {
-            const bool roleA = item >= n_lines;
-            const uint32_t l = roleA ? item - n_lines : item;
-            LineRecF& R = recs[l];
-            const uint32_t ls = lines[l];
-            uint32_t wi = ls >> 6;
-            unsigned long long wmk = wm64[wi] & (~0ull << (ls & 63u));
-            uint32_t st = ST_FAST;
-            int why = WHY_LONG;
-            if (!roleA) {
-                // ---------------- role B: columns, filters, coordinates, path steps
-                uint32_t e[13];
-                e[0] = ls - 1u;
-                bool ran_off = false, gaps_ok = true;
-                uint32_t tabs = 0xFFFFFFFFu;                  // AND of (byte == '\t') over the first 11 boundaries
-#pragma unroll
-                for (int j = 1; j <= 12; j++) {
-                    e[j] = 0;
-                    if (!ran_off) {
-                        if (!next_ws(wm64, nwords, wi, wmk, e[j])) ran_off = true;   // record runs past the look-ahead
-                        else {
-                            gaps_ok &= e[j] - e[j - 1] >= 2u;                        // no empty column
-                            if (j < 12) tabs &= buf[e[j]] == '\t' ? 0xFFFFFFFFu : 0u;
-                        }
-                    }
+        // ================= columns: one thread per mask word: whitespace bit -> (record, column) =================
+        for (uint32_t g = tid; g < nwords; g += THREADS) {
+            unsigned long long m = wm64[g];
+            if (m == 0ull) continue;
+            const unsigned long long gp = gpre[g], nlv = nl64[g];
+            int32_t j = (int32_t)((uint32_t)(gp >> 32) & 0xFFFFu) - 1;     // record open at the start of the word (-1: none of ours)
+            uint32_t c = 0;
+            if (j >= 0) c = ((uint32_t)gp & 0xFFFFu) - ws_at((uint32_t)(gp >> PRE_LS_SHIFT));   // its whitespace bytes so far
+            while (m) {
+                const uint32_t b = (uint32_t)(__ffsll((long long)m) - 1);
+                m &= m - 1ull;
+                const uint32_t q = 64u * g + b;
+                c++;
+                if (j >= 0 && c < NCOLS) ecol[(uint32_t)j * NCOLS + c] = (uint16_t)q;
+                if ((nlv >> b) & 1ull) {
+                    if (j >= 0) ncol[j] = (uint8_t)min(c, 255u);
+                    j++;
+                    c = 0;
+                    lines[j] = (uint16_t)(q + 1u);
+                    ecol[(uint32_t)j * NCOLS] = (uint16_t)q;
                 }
-                bool slow = ran_off, done = false, no_tags = false;
-                int32_t mapq = 0, plen = 0, start = 0, pend = 0;
-                if (!slow) {
-                    // 11 single tabs, then a tab (tags follow) or the end of a 12-column record
-                    const uint32_t c12 = buf[e[12]];
-                    no_tags = c12 == '\n';
-                    if (!gaps_ok || tabs == 0u || (c12 != '\t' && !no_tags)) { slow = true; why = WHY_COLUMNS; }
-                }
-                if (!slow) {
-                    why = WHY_INTS;
-                    slow = !small_uint(buf, e[11] + 1u, e[12], mapq);
-                    if (!slow) {
-                        if ((int64_t)mapq < A.thr) { sink.reject(); done = true; }                   // REF:143-146
-                        else if (e[6] - e[5] == 2u && buf[e[5] + 1u] == '*') done = true;             // REF:147-148
-                    }
-                }
-                if (!slow && !done)
-                    slow = !small_uint(buf, e[6] + 1u, e[7], plen) || !small_uint(buf, e[7] + 1u, e[8], start) ||
-                           !small_uint(buf, e[8] + 1u, e[9], pend);
-                if (!slow && !done && no_tags) { slow = true; why = WHY_TAGS; }   // no dv tag: ValueError (REF:179), slow path reports
-                // ---- path column (REF:185-197): it must start with a separator; count the steps
-                uint32_t ns = 0, off = 0, a5 = 0, b5 = 0;
-                if (!slow && !done) {
-                    why = WHY_PATH;
-                    a5 = e[5] + 1u;
-                    b5 = e[6];
-                    for (uint32_t w = a5 >> 6; w <= ((b5 - 1u) >> 6); w++) ns += (uint32_t)__popcll(sep_word(sm64, w, a5, b5));
-                    if (ns == 0u || ns > (uint32_t)MAX_STEPS || !((sm64[a5 >> 6] >> (a5 & 63u)) & 1ull)) {
-                        slow = true;
-                    } else {
-                        off = atomicAdd(&s_nsteps, ns + 1u);                      // any order: a record only needs a contiguous range
-                        if (off + ns + 1u > (uint32_t)G::STEP_CAP) {              // list full: slow path
-                            slow = true;
-                            why = WHY_STEPS_FULL;
-                            for (uint32_t i = off; i < (uint32_t)G::STEP_CAP; i++) steps[i] = SE_INVALID;
-                        }
-                    }
-                }
-                st = slow ? ST_DEFER : (done ? ST_DONE : ST_FAST);
-                R.ls = (uint16_t)ls;
-                R.stB = (uint8_t)st;
-                R.whyB = (uint8_t)why;
-                R.nsteps = 0;
-                R.s0 = 0;
-                if (st == ST_FAST) {
-                    R.start = start;
-                    R.end_rel1 = plen - pend - 1;
-                    R.s0 = (uint16_t)off;
-                    R.nsteps = (uint16_t)ns;
-                    // ---- one entry per path step, then the sentinel (end of the column)
-                    const uint32_t common = (l << SE_SLOT_SHIFT) | (buf[a5] == '<' ? SE_REV : 0u);
-                    uint32_t i = off;
-                    for (uint32_t w = a5 >> 6; w <= ((b5 - 1u) >> 6); w++) {
-                        unsigned long long m = sep_word(sm64, w, a5, b5);
-                        while (m) {
-                            const uint32_t q = 64u * w + (uint32_t)(__ffsll((long long)m) - 1);
-                            m &= m - 1ull;
-                            steps[i] = q | common | (i == off ? SE_FIRST : 0u) | (i + 1u == off + ns ? SE_LAST : 0u);
-                            i++;
-                        }
-                    }
-                    steps[off + ns] = b5 | (l << SE_SLOT_SHIFT) | SE_SENT;
-                }
-            } else {
+            }
+        }
+        __syncthreads();                                                    // ---- column boundaries, record starts complete
+
+        // records that start in the owned bytes; step-list entries up to the sentinel of the last one
+        const uint32_t n_own = (uint32_t)(pre_at(own_end - 1u) >> 32) & 0xFFFFu;
+        const uint32_t n_ent = n_own == 0u ? 0u : (n_own < n_rec_all ? sep_at(lines[n_own]) : n_sep_all) + n_own;
+        if (tid == 0) { my_lines += n_own; my_tiles++; }
+
+        // ================= fields: A (tags), T0 (shape, filters, path shape), T1 (coordinates), S (step entries) =================
+        for (uint32_t item = tid; item < 3u * n_own + nwords; item += THREADS) {
+            if (item < n_own) {
                 // ---------------- role A: tags -> dv filter, cs ops
-                uint32_t e11 = 0, e12 = 0, pos = 0;
-                bool ran_off = false;
-#pragma unroll 1
-                for (int j = 1; j <= 12 && !ran_off; j++) {
-                    if (!next_ws(wm64, nwords, wi, wmk, pos)) ran_off = true;
-                    e11 = e12;
-                    e12 = pos;
-                }
-                // role B decides about everything up to column 12; here: is there anything left to do?
-                int32_t mapq = 0;
-                bool idle = ran_off || buf[e12] != '\t' || !small_uint(buf, e11 + 1u, e12, mapq) || (int64_t)mapq < A.thr;
-                bool slow = false, done = false;
+                const uint32_t l = item;
+                LineRecF& R = recs[l];
+                const uint16_t* const e = ecol + l * NCOLS;
+                const uint32_t nc = ncol[l];
+                int why = WHY_TAGS;
+                bool slow = nc < 13u, done = false;                          // no tags: no dv, ValueError (REF:179); the slow path reports
                 uint32_t cs_a = 0, cs_b = 0, dv_a = 0, dv_b = 0;
-                if (!idle) {
-                    // ---- tags: [inert]* cs [inert]* dv in any order, within the first few tags
-                    why = WHY_TAGS;
-                    uint32_t a = e12 + 1u, b = 0;
-                    if (!next_ws(wm64, nwords, wi, wmk, b)) slow = true;
-                    for (int j = 13; !slow; j++) {
+                if (!slow) {
+                    // ---- tags: [inert]* cs [inert]* dv in any order, within the first six tags
+                    uint32_t a = (uint32_t)e[12] + 1u, b = e[13];
+                    for (uint32_t t = 0;; t++) {
                         if (!cs_b && b - a >= 3u && buf[a] == 'c' && buf[a + 1] == 's' && buf[a + 2] == ':') {
                             cs_a = a;
                             cs_b = b;
@@ -479,106 +504,219 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                             break;
                         }
                         if (cs_b && dv_b) break;
-                        if (buf[b] == '\n' || j >= 18) { slow = true; break; }      // end of the record: a tag is missing
+                        if (13u + t == nc || t == 5u) { slow = true; break; }   // end of the record: a tag is missing
                         a = b + 1u;
-                        if (!next_ws(wm64, nwords, wi, wmk, b)) { slow = true; break; }
-                    }
-                    // ---- dv filter (REF:172-180).  The reference parses cs first, but that has no side effects and
-                    //      cannot raise, so a record that dv filters out needs no cs class
-                    if (!slow) {
-                        const uint32_t f = buf[dv_a], g = dv_a + 1u < dv_b ? buf[dv_a + 1u] : 0u, h = dv_a + 2u < dv_b ? buf[dv_a + 2u] : 0u;
-                        if (f == '0' && g == '.' && h == '0') {
-                            // 0.0xxx: never greater
-                        } else if (pt::dv_token_greater(buf, (int)dv_a, (int)dv_b)) {
-                            done = true;
-                        }
-                    }
-                    // ---- cs string (REF:10-37): "cs:Z:" then ops spelled the way an aligner spells them:
-                    //      ':'<digits>  '*'<2 letters>  '-'<letters>  '+'<letters>  '='<LETTERS>, every length >= 1
-                    if (!slow && !done) {
-                        why = WHY_CS;
-                        uint32_t n_tot = 0, nops = 0, op_off = 0;
-                        int32_t start_add = 0;
-                        if (cs_b - cs_a < 7u || buf[cs_a + 3] != 'Z' || buf[cs_a + 4] != ':') slow = true;
-                        uint32_t q = cs_a + 5u;
-                        uint64_t one;
-                        if (!slow && buf[q] == ':' && cs_b - q - 1u <= 7u && step_id(buf, q + 1u, cs_b - q - 1u, one) && one != 0u) {
-                            // cs:Z::<n> -- a perfect match
-                            op_off = atomicAdd(&s_nops, 1u);
-                            if (op_off < (uint32_t)G::OPS_CAP) ops[op_off] = OP_MATCH | ((uint32_t)one << 3);
-                            else slow = true;
-                            nops = 1;
-                            n_tot = (uint32_t)one;
-                        } else if (!slow) {
-                            // every op takes at least two bytes: room for (bytes / 2) ops is enough
-                            const uint32_t room = min((cs_b - q) >> 1, (uint32_t)MAX_OPS);
-                            op_off = atomicAdd(&s_nops, room);
-                            if (op_off + room > (uint32_t)G::OPS_CAP) slow = true;
-                            while (!slow && q < cs_b) {
-                                const uint32_t c = buf[q++];
-                                uint32_t kind, len = 0;
-                                if (c == ':') {
-                                    kind = OP_MATCH;
-                                    uint32_t nd = 0;
-                                    while (q < cs_b && pt::is_digit(buf[q])) { len = len * 10u + (buf[q] - '0'); q++; nd++; }
-                                    if (nd == 0u || nd > 7u) slow = true;
-                                } else if (c == '*') {
-                                    kind = OP_SUB;
-                                    if (q + 2u > cs_b || !is_lower(buf[q]) || !is_lower(buf[q + 1])) slow = true;
-                                    q += 2u;
-                                    len = 1;
-                                } else if (c == '-' || c == '+') {
-                                    kind = c == '-' ? OP_DEL : OP_INS;
-                                    while (q < cs_b && is_lower(buf[q])) { q++; len++; }
-                                } else if (c == '=') {
-                                    kind = OP_EQ;
-                                    while (q < cs_b && buf[q] - 'A' <= 24u) { q++; len++; }      // 'A'..'Y': "cs:Z:" cannot hide in here
-                                } else {
-                                    slow = true;
-                                    kind = 0;
-                                }
-                                // the text must end where the next op starts
-                                if (q < cs_b) {
-                                    const uint32_t d = buf[q];
-                                    if (d != ':' && d != '*' && d != '-' && d != '+' && d != '=') slow = true;
-                                }
-                                if (len == 0u || len > (uint32_t)MAX_NTOT || nops >= room) slow = true;
-                                if (!slow) {
-                                    ops[op_off + nops] = kind | (len << 3);
-                                    nops++;
-                                    n_tot += len;
-                                    if (n_tot > (uint32_t)MAX_NTOT) slow = true;
-                                }
-                            }
-                            if (nops == 0u) slow = true;
-                            // cigar_clipping (REF:40-50): only when there are exactly two ops
-                            if (!slow && nops == 2u) {
-                                const uint32_t o0 = ops[op_off], o1 = ops[op_off + 1u];
-                                if ((o0 & 7u) == OP_INS && (o1 & 7u) == OP_MATCH) {
-                                    start_add = (int32_t)(o0 >> 3);
-                                    ops[op_off] = o1;
-                                    nops = 1;
-                                    n_tot = o1 >> 3;
-                                } else if ((o0 & 7u) == OP_MATCH && (o1 & 7u) == OP_INS) {
-                                    nops = 1;
-                                    n_tot = o0 >> 3;
-                                }
-                            }
-                        }
-                        R.n_tot = n_tot;
-                        R.op_off = (uint16_t)op_off;
-                        R.nops = (uint8_t)nops;
-                        R.start_add = start_add;
+                        b = e[14u + t];
                     }
                 }
-                st = slow ? ST_DEFER : (done ? ST_DONE : ST_FAST);
-                R.stA = (uint8_t)st;
+                // ---- dv filter (REF:172-180).  The reference parses cs first, but that has no side effects and
+                //      cannot raise, so a record that dv filters out needs no cs class
+                if (!slow) {
+                    const uint32_t f = buf[dv_a], g = dv_a + 1u < dv_b ? buf[dv_a + 1u] : 0u, h = dv_a + 2u < dv_b ? buf[dv_a + 2u] : 0u;
+                    if (f == '0' && g == '.' && h == '0') {
+                        // 0.0xxx: never greater
+                    } else if (pt::dv_token_greater(buf, (int)dv_a, (int)dv_b)) {
+                        done = true;
+                    }
+                }
+                // ---- cs string (REF:10-37): "cs:Z:" then ops spelled the way an aligner spells them:
+                //      ':'<digits>  '*'<2 letters>  '-'<letters>  '+'<letters>  '='<LETTERS>, every length >= 1
+                if (!slow && !done) {
+                    why = WHY_CS;
+                    uint32_t n_tot = 0, nops = 0, op_off = 0;
+                    int32_t start_add = 0;
+                    if (cs_b - cs_a < 7u || buf[cs_a + 3] != 'Z' || buf[cs_a + 4] != ':') slow = true;
+                    uint32_t q = cs_a + 5u;
+                    uint64_t one;
+                    if (!slow && buf[q] == ':' && cs_b - q - 1u <= 7u && step_id(buf, q + 1u, cs_b - q - 1u, one) && one != 0u) {
+                        // cs:Z::<n> -- a perfect match
+                        op_off = atomicAdd(&s_nops, 1u);
+                        if (op_off < (uint32_t)G::OPS_CAP) ops[op_off] = OP_MATCH | ((uint32_t)one << 3);
+                        else slow = true;
+                        nops = 1;
+                        n_tot = (uint32_t)one;
+                    } else if (!slow) {
+                        // every op takes at least two bytes: room for (bytes / 2) ops is enough
+                        const uint32_t room = min((cs_b - q) >> 1, (uint32_t)MAX_OPS);
+                        op_off = atomicAdd(&s_nops, room);
+                        if (op_off + room > (uint32_t)G::OPS_CAP) slow = true;
+                        while (!slow && q < cs_b) {
+                            const uint32_t c = buf[q++];
+                            uint32_t kind, len = 0;
+                            if (c == ':') {
+                                kind = OP_MATCH;
+                                uint32_t nd = 0;
+                                while (q < cs_b && pt::is_digit(buf[q])) { len = len * 10u + (buf[q] - '0'); q++; nd++; }
+                                if (nd == 0u || nd > 7u) slow = true;
+                            } else if (c == '*') {
+                                kind = OP_SUB;
+                                if (q + 2u > cs_b || !is_lower(buf[q]) || !is_lower(buf[q + 1])) slow = true;
+                                q += 2u;
+                                len = 1;
+                            } else if (c == '-' || c == '+') {
+                                kind = c == '-' ? OP_DEL : OP_INS;
+                                while (q < cs_b && is_lower(buf[q])) { q++; len++; }
+                            } else if (c == '=') {
+                                kind = OP_EQ;
+                                while (q < cs_b && buf[q] - 'A' <= 24u) { q++; len++; }      // 'A'..'Y': "cs:Z:" cannot hide in here
+                            } else {
+                                slow = true;
+                                kind = 0;
+                            }
+                            // the text must end where the next op starts
+                            if (q < cs_b) {
+                                const uint32_t d = buf[q];
+                                if (d != ':' && d != '*' && d != '-' && d != '+' && d != '=') slow = true;
+                            }
+                            if (len == 0u || len > (uint32_t)MAX_NTOT || nops >= room) slow = true;
+                            if (!slow) {
+                                ops[op_off + nops] = kind | (len << 3);
+                                nops++;
+                                n_tot += len;
+                                if (n_tot > (uint32_t)MAX_NTOT) slow = true;
+                            }
+                        }
+                        if (nops == 0u) slow = true;
+                        // cigar_clipping (REF:40-50): only when there are exactly two ops
+                        if (!slow && nops == 2u) {
+                            const uint32_t o0 = ops[op_off], o1 = ops[op_off + 1u];
+                            if ((o0 & 7u) == OP_INS && (o1 & 7u) == OP_MATCH) {
+                                start_add = (int32_t)(o0 >> 3);
+                                ops[op_off] = o1;
+                                nops = 1;
+                                n_tot = o1 >> 3;
+                            } else if ((o0 & 7u) == OP_MATCH && (o1 & 7u) == OP_INS) {
+                                nops = 1;
+                                n_tot = o0 >> 3;
+                            }
+                        }
+                    }
+                    R.n_tot = n_tot;
+                    R.op_off = (uint16_t)op_off;
+                    R.nops = (uint8_t)nops;
+                    R.start_add = start_add;
+                }
+                R.stA = (uint8_t)(slow ? ST_DEFER : (done ? ST_DONE : ST_FAST));
                 R.whyA = (uint8_t)why;
+            } else if (item < 2u * n_own) {
+                // ---------------- role T0: column shape, MAPQ and '*' filters, path column shape, sentinel
+                const uint32_t l = item - n_own;
+                LineRecF& R = recs[l];
+                const uint16_t* const e = ecol + l * NCOLS;
+                const uint32_t nc = ncol[l];
+                int why = WHY_LONG;                                         // nc == 0: the record runs past the look-ahead
+                bool slow = nc < 12u, done = false;
+                uint32_t e6 = 0;
+                if (nc != 0u && nc < 12u) why = WHY_COLUMNS;                // fewer than 12 columns: IndexError (REF:143), slow path reports
+                if (nc >= 6u) e6 = e[6];
+                if (!slow) {
+                    // 11 single tabs, then a tab (tags follow) or the end of a 12-column record; no empty column
+                    why = WHY_COLUMNS;
+                    uint32_t prev = e[0];
+                    bool ok = true;
+#pragma unroll
+                    for (int j = 1; j <= 12; j++) {
+                        const uint32_t cur = e[j];
+                        ok &= cur - prev >= 2u;
+                        prev = cur;
+                    }
+                    if (s_oth != 0u) {                                      // the tile holds whitespace other than tab / newline
+#pragma unroll
+                        for (int j = 1; j <= 11; j++) ok &= buf[e[j]] == '\t';
+                        const uint32_t c12 = buf[e[12]];
+                        ok &= c12 == '\t' || c12 == '\n';
+                    }
+                    slow = !ok;
+                }
+                if (!slow) {
+                    why = WHY_INTS;
+                    int32_t mapq = 0;
+                    const uint32_t e5 = e[5];
+                    slow = !small_uint(buf, (uint32_t)e[11] + 1u, e[12], mapq);
+                    if (!slow) {
+                        if ((int64_t)mapq < A.thr) { sink.reject(); done = true; }               // REF:143-146
+                        else if (e6 - e5 == 2u && buf[e5 + 1u] == '*') done = true;               // REF:147-148
+                    }
+                    if (!slow && !done) {
+                        // ---- path column (REF:185-197): it must start with a separator; count the steps
+                        why = WHY_PATH;
+                        const uint32_t a5 = e5 + 1u;
+                        const uint32_t ns = sep_at(e6) - sep_at(a5);
+                        if (ns == 0u || ns > (uint32_t)MAX_STEPS || !((sm64[a5 >> 6] >> (a5 & 63u)) & 1ull)) slow = true;
+                    }
+                }
+                // the record's sentinel closes its range of the step list (role S fills the rest)
+                steps[(l + 1u < n_rec_all ? sep_at(lines[l + 1u]) : n_sep_all) + l] = e6 | (l << SE_SLOT_SHIFT) | SE_SENT;
+                R.ls = lines[l];
+                R.stB = (uint8_t)(slow ? ST_DEFER : (done ? ST_DONE : ST_FAST));
+                R.whyB = (uint8_t)why;
+            } else if (item < 3u * n_own) {
+                // ---------------- role T1: the three coordinates (REF:151-153)
+                const uint32_t l = item - 2u * n_own;
+                LineRecF& R = recs[l];
+                const uint16_t* const e = ecol + l * NCOLS;
+                uint32_t st = ST_FAST;
+                if (ncol[l] >= 12u) {
+                    int32_t plen = 0, start = 0, pend = 0;
+                    const uint32_t e7 = e[7], e8 = e[8];
+                    if (small_uint(buf, (uint32_t)e[6] + 1u, e7, plen) && small_uint(buf, e7 + 1u, e8, start) &&
+                        small_uint(buf, e8 + 1u, e[9], pend)) {
+                        R.start = start;
+                        R.end_rel1 = plen - pend - 1;
+                    } else {
+                        st = ST_DEFER;
+                    }
+                }
+                R.stC = (uint8_t)st;
+            } else {
+                // ---------------- role S: one mask word: separator bit -> step-list entry
+                //   slot = (separators before it) + (its record's number): every record's entries are contiguous
+                //   and followed by one free slot, its sentinel
+                const uint32_t g = item - 3u * n_own;
+                unsigned long long m = sm64[g];
+                if (m == 0ull) continue;
+                const unsigned long long gp = gpre[g], nlv = nl64[g];
+                uint32_t o = (uint32_t)(gp >> 16) & 0xFFFFu;               // ordinal of the word's first separator
+                const int32_t k = (int32_t)((uint32_t)(gp >> 32) & 0xFFFFu);
+                int32_t jc = -2;
+                uint32_t a5 = 0, b5 = 0, common = 0;
+                bool shape = false;
+                while (m) {
+                    const uint32_t b = (uint32_t)(__ffsll((long long)m) - 1);
+                    m &= m - 1ull;
+                    const uint32_t q = 64u * g + b;
+                    const int32_t j = k + __popcll(nlv & ~(~0ull << b)) - 1;            // the record the byte is in
+                    const uint32_t slot = o + (uint32_t)max(j, 0);
+                    o++;
+                    if (slot >= n_ent) break;                               // look-ahead records: not ours
+                    if (j < 0) { steps[slot] = SE_INVALID; continue; }      // tail of a record of the previous tile
+                    if (j != jc) {
+                        jc = j;
+                        shape = ncol[j] >= 6u;
+                        if (shape) {
+                            a5 = (uint32_t)ecol[(uint32_t)j * NCOLS + 5u] + 1u;
+                            b5 = ecol[(uint32_t)j * NCOLS + 6u];
+                            common = ((uint32_t)j << SE_SLOT_SHIFT) | (buf[a5] == '<' ? SE_REV : 0u);
+                        }
+                    }
+                    uint32_t ent;
+                    if (!shape || q < a5) ent = SE_INVALID;                 // not in the path column (read names ...)
+                    else if (q >= b5) ent = b5 | ((uint32_t)j << SE_SLOT_SHIFT) | SE_SENT;
+                    else {
+                        uint32_t nq = b5;                                   // the next separator
+                        if (m) nq = 64u * g + (uint32_t)(__ffsll((long long)m) - 1);
+                        else
+                            for (uint32_t w = g + 1u; 64u * w < b5; w++) {
+                                const unsigned long long mm = sm64[w];
+                                if (mm) { nq = 64u * w + (uint32_t)(__ffsll((long long)mm) - 1); break; }
+                            }
+                        ent = q | common | (q == a5 ? SE_FIRST : 0u) | (nq >= b5 ? SE_LAST : 0u);
+                    }
+                    steps[slot] = ent;
+                }
             }
         }
         __syncthreads();                                                    // ---- records, ops, step list complete
-        const uint32_t n_ent = min(s_nsteps, (uint32_t)G::STEP_CAP);       // step entries incl. sentinels
-        if (tid == 0) s_nlines = 0;                                         // everyone has read it
 
         // ================= ids: one thread per path step: id -> node index =================
         for (uint32_t s = tid; s < n_ent; s += THREADS) {
@@ -598,10 +736,10 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         }
         __syncthreads();                                                    // ---- node indices complete; the bytes and the masks are dead
         if (tid == 0) {
-            s_nsteps = 0;
             s_nops = 0;
             s_nfar = 0;
             s_ndel = 0;
+            s_oth = 0;
             const uint32_t nxt = tile + gridDim.x;
             if (nxt < A.n_tiles) issue_load(nxt);                           // overlaps walk + count
         }
@@ -671,9 +809,15 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 R.whyB = WHY_WALK;
                 continue;
             }
-            const uint32_t Bk = min(Ak + Lk, n_tot);
             const uint32_t* op = ops + R.op_off;
             const uint32_t nops = R.nops;
+            if (nops == 1u) {                                               // one op (a perfect match, mostly): its piece is the whole slice
+                const uint32_t kind = op[0] & 7u;
+                steps[s] = (kind == OP_DEL || kind == OP_INS) ? (se | SE_DROPPED)                       // REF:101-102
+                                                              : (se | ((kind != OP_SUB ? 1u : 0u) << SE_NCNT_SHIFT));
+                continue;
+            }
+            const uint32_t Bk = min(Ak + Lk, n_tot);
             // pieces of the node = ops overlapping [Ak, Bk), clipped; compact_align as a running fold (REF:63-94)
             uint32_t j = 0, o_start = 0, o_end = op[0] >> 3;
             while (o_end <= Ak) {                                           // ends before the node starts (j < nops: Ak < n_tot)
@@ -729,9 +873,9 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             }
         }
         __syncthreads();                                                    // ---- every hand-over decision is made; nothing counted so far
-        for (uint32_t l = tid; l < n_lines; l += THREADS) {
+        for (uint32_t l = tid; l < n_own; l += THREADS) {
             const LineRecF& R = recs[l];
-            if (rec_status(R) == ST_DEFER) defer_line(T, t0 + R.ls - 16u, A.file_off, R.stB == ST_DEFER ? R.whyB : R.whyA);
+            if (rec_status(R) == ST_DEFER) defer_line(T, t0 + R.ls - 16u, A.file_off, rec_why(R));
         }
 
         // surviving neighbours of step s inside its record (dropped nodes are skipped)

@@ -347,7 +347,7 @@ int pt_create(int device, pt_ctx** out) {
         ctx->threads != 512)
         ctx->threads = 256;
     ctx->kernel_ver = env_u32("PANTAS_KERNEL", 2);
-    ctx->fast_geo = env_u32("PANTAS_FAST_T", 24576);
+    ctx->fast_geo = env_u32("PANTAS_FAST_T", 16384);
     *out = ctx;
     return 0;
 }
@@ -549,6 +549,9 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
         typedef fastp::Geo<12288, 1024, 128> GD;
         typedef fastp::Geo<16384, 1024, 128> GE;
         typedef fastp::Geo<32768, 1024, 256> GF;
+        typedef fastp::Geo<20480, 1024, 256> GG;
+        typedef fastp::Geo<8192, 1024, 128> GH;
+        typedef fastp::Geo<8192, 1024, 256> GI;
         typedef fastp::Geo<1024, 256, 64> GT;    // tests: many tile boundaries, records longer than the look-ahead
         uint32_t ft;
 #define PT_PICK(Gx) { fkern = fastp::augment_fast_kernel<Gx>; fsmem = (size_t)Gx::SMEM_BYTES; ft = Gx::TILE; f_threads = Gx::THREADS; }
@@ -558,7 +561,11 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
         else if (ctx->fast_geo == 12288) PT_PICK(GD)
         else if (ctx->fast_geo == 16385) PT_PICK(GE)
         else if (ctx->fast_geo == 32769) PT_PICK(GF)
-        else PT_PICK(GA)
+        else if (ctx->fast_geo == 20480) PT_PICK(GG)
+        else if (ctx->fast_geo == 8192) PT_PICK(GH)
+        else if (ctx->fast_geo == 8193) PT_PICK(GI)
+        else if (ctx->fast_geo == 24576) PT_PICK(GA)
+        else PT_PICK(GC)
 #undef PT_PICK
         if (ctx->fast_ctas_per_sm == 0) {
             CK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));

@@ -87,7 +87,7 @@ def _fload():
     global _flib
     if _flib is None:
         if not os.path.exists(FSO) or os.path.getmtime(FSO) < max(os.path.getmtime(d) for d in FDEPS):
-            subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused", "-o", FSO, FSRC],
+            subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused", "-Wno-unknown-pragmas", "-o", FSO, FSRC],
                            check=True)
         lib = ctypes.CDLL(FSO)
         lib.fastsim_run.restype = ctypes.c_int

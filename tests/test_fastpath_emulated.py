@@ -101,3 +101,30 @@ def test_synthetic_reads_stay_on_the_fast_path(tmp_path):
         assert res[0] == "ok" and res[1] == orc.out and res[2] == orc.rej
         assert st["lines"] == n
         assert st["deferred"] <= n // 50, st
+
+
+def test_dense_short_records_overflow_the_tile_lists(tmp_path):
+    """More records per tile than the record list holds: the whole tile takes the per-record kernel."""
+    gfa = "H\tVN:Z:1.1\nS\t1\tACGTACGTAC\nS\t2\tGGGGG\nL\t1\t+\t2\t+\t*\n"
+    rec = ["q\t10\t0\t10\t+\t>1\t10\t0\t10\t10\t10\t60\tcs:Z::10\tdv:f:0\n",
+           "r\t12\t0\t12\t+\t>1>2\t15\t0\t12\t12\t12\t60\tcs:Z::12\tdv:f:0\n",
+           "s\t12\t0\t12\t+\t<2<1\t15\t3\t15\t12\t12\t7\tcs:Z::12\tdv:f:0\n"]
+    gaf = "".join(rec[i % 3] for i in range(240))
+    orc = run_oracle(gaf.encode(), gfa.encode())
+    assert orc.rc == 0
+    for geo in (0, 1):
+        st = {}
+        res = pipeline(tmp_path, gfa, gaf, geo=geo, stats=st)
+        assert res[0] == "ok" and res[1] == orc.out and res[2] == orc.rej
+        assert st["deferred"] > 0
+
+
+@pytest.mark.parametrize("seed", range(7500, 7506))
+def test_fuzz_production_geometry(seed, tmp_path):
+    gfa, gaf = fuzzgen.make_case(seed, n_nodes=30, n_reads=400, weird=(seed % 2 == 0), crlf=(seed % 3 == 0))
+    orc = run_oracle(gaf.encode(), gfa.encode())
+    res = pipeline(tmp_path, gfa, gaf, geo=2, grid=1 + seed % 3)
+    assert orc.rc == 0
+    assert res[0] == "ok", res
+    assert res[1] == orc.out
+    assert res[2] == orc.rej
