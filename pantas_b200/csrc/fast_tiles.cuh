@@ -14,23 +14,23 @@
 //            tile flag that switches on the per-column tab check below.
 //   prefix   per 64-byte mask word: exclusive counts of whitespace, separators and record starts
 //            before the word, and the start of the record that is open there (block-wide scan).
-//   columns  one thread per mask word walks its whitespace bits: bit -> (record, column number) from
-//            the prefix counts -> the column-boundary table ecol[record][column]; newlines open the
-//            next record (lines[], ncol[]).
+//   scatter  one thread per 16-byte vector (32-bit arithmetic on its 16-bit mask pieces): every whitespace
+//            position goes to a flat list at its ordinal (prefix count), every separator to the step list
+//            at its ordinal, tagged with its record; newlines open the next record (its first byte, its
+//            first whitespace ordinal).  Column c of record r ends at wslist[recws[r] + c - 1]: no table
+//            of column boundaries is ever built, nothing walks a record.
 //   fields   small independent items, one thread each:
 //              A   tags of a record: first cs token, first dv:f: token (REF:154-160,172-180), the dv
 //                  filter, the cs string parsed into the tile's op pool (REF:10-50, cigar_clipping)
-//              T0  column shape, MAPQ and '*' filters (REF:143-148), path column shape, the record's
-//                  sentinel in the step list
+//              T0  column shape, MAPQ and '*' filters (REF:143-148), path column shape
 //              T1  the three coordinates (REF:151-153)
-//              S   one thread per mask word walks its separator bits: bit -> step-list slot
-//                  (separator ordinal + record number), entry = position | record | first/last/rev
 //            Anything unusual -- other whitespace in the columns, integers that are not plain
 //            digits, tags that could confuse the reference's regexes, '~' or zero-length or oddly
 //            spelled cs ops -- hands the record to the exact per-record path (line_core.cuh via
 //            augment_deferred_kernel).
-//   ids      one thread per path step: SWAR decimal parse of the id out of shared memory, node
-//            index, L2 prefetch of the node record.  After this phase the bytes are dead and the
+//   ids      one thread per separator of the step list: inside its record's path column?  first / last
+//            step?  then the SWAR decimal parse of the id out of shared memory, node index, node length
+//            (the load also pulls the node's sector into L2).  After this phase the bytes are dead and the
 //            next tile's TMA copy is issued: it overlaps the table traffic of the remaining phases.
 //   walk     one thread per path step.  The reference's merge walk (REF:205-255) gives node k the
 //            ops that overlap [A_k, A_k + L_k) in cs coordinates, where A is the prefix sum of the
@@ -67,10 +67,11 @@ struct __align__(8) LineRecF {
     uint16_t op_off;      // first op of the record in the op pool             (role A)
     uint8_t nops;         //                                                   (role A)
     uint8_t stA, stB, stC;   // ST_* per role; walk raises stB
+    uint16_t a5, b5;      // the path column [a5, b5) (0xFFFF, 0xFFFF: the record has none)   (role T0)
     uint8_t whyA, whyB;   // WHY_* when the role says ST_DEFER (T1: always WHY_INTS)
-    uint8_t pad[2];
+    uint8_t pad[6];
 };
-static_assert(sizeof(LineRecF) == 32, "record layout");
+static_assert(sizeof(LineRecF) == 40, "record layout");
 
 // step list entry
 constexpr uint32_t SE_POS_MASK = 0xFFFFu;     // bits 0..15  buffer position of the separator (sentinel: end of the path column)
@@ -89,24 +90,24 @@ struct Geo {
     static constexpr int TILE = TILE_;
     static constexpr int OV = OV_;
     static constexpr int THREADS = THREADS_;
-    static constexpr int NCOLS = 20;                              // column boundaries kept per record: 12 columns + 6 tags
     static constexpr int BUF = 16 + TILE + OV + 16;               // [pre 16][tile][look-ahead][pad 16]
     static constexpr int NV = ((16 + TILE + OV) / 16 + 3) & ~3;   // 16-byte vectors, padded to whole 64-bit mask words
     static constexpr int NW = NV / 4;                             // 64-bit mask words
     static constexpr int LINE_CAP = ((TILE + OV + 111) / 112 + 7) & ~7;   // typical: one record per 300 bytes
-    static constexpr int STEP_CAP = (((TILE + OV) / 12 + LINE_CAP) + 63) & ~63;   // typical: 14 steps per 300 bytes, + sentinels
+    static constexpr int STEP_CAP = (((TILE + OV) / 12) + 63) & ~63;  // separators; typical: 14 steps per 300 bytes
+    static constexpr int WS_CAP = (((TILE + OV) / 8) + 63) & ~63;     // whitespace bytes; typical: 17 per 300 bytes
     static constexpr int OPS_CAP = (LINE_CAP * 4 + 63) & ~63;
     static constexpr int FAR_CAP = (STEP_CAP / 8 + 31) & ~31;     // links that are not inline: typically 1-2 per record
     static constexpr int DEL_CAP = (LINE_CAP / 2 + 31) & ~31;     // steps with deletion-derived keys
-    // region X, first life (scan .. fields): three masks, the per-word prefix, column boundaries, record starts
+    // region X, first life (scan .. fields): three masks, the per-word prefix, whitespace list, record starts
     static constexpr int OFF_WM = (BUF + 127) & ~127;
     static constexpr int OFF_NL = OFF_WM + 8 * NW;
     static constexpr int OFF_SM = OFF_NL + 8 * NW;
     static constexpr int OFF_PRE = OFF_SM + 8 * NW;
-    static constexpr int OFF_ECOL = OFF_PRE + 8 * (NW + 1);        // + one word of totals (a position may be the end of the data)
-    static constexpr int OFF_LINES = OFF_ECOL + 2 * NCOLS * LINE_CAP;
-    static constexpr int OFF_NCOL = OFF_LINES + 2 * LINE_CAP;
-    static constexpr int X_END1 = OFF_NCOL + LINE_CAP;
+    static constexpr int OFF_WSL = OFF_PRE + 8 * (NW + 1);        // + one word of totals (a position may be the end of the data)
+    static constexpr int OFF_LINES = OFF_WSL + 2 * WS_CAP;
+    static constexpr int OFF_RECWS = OFF_LINES + 2 * LINE_CAP;
+    static constexpr int X_END1 = OFF_RECWS + 2 * LINE_CAP;
     // region X, second life (walk .. count): step-length prefix and the two end-of-tile lists
     static constexpr int OFF_SINFO = OFF_WM;
     static constexpr int OFF_FAR = OFF_SINFO + 4 * (STEP_CAP + 4);
@@ -123,6 +124,7 @@ struct Geo {
     static_assert(BUF < 65536, "step entries and prefix words hold 16-bit positions");
     static_assert(LINE_CAP <= 512, "step entries hold 9-bit record slots");
     static_assert(STEP_CAP < 65536 && OPS_CAP < 65536, "records hold 16-bit list offsets");
+    static_assert(OFF_SINFO + 4 * (STEP_CAP + 4) <= OFF_WSL, "ids writes node lengths while the whitespace list is still read");
 };
 
 // 0x80 flags at bits 7/15/23/31 -> 4-bit mask in the top nibble (no carries: the partial products
@@ -240,7 +242,9 @@ __device__ __forceinline__ uint32_t flag_nl(uint32_t x) { return flag_eq7(x ^ 0x
 // status of a record: T0's verdict (shape, MAPQ, '*') comes first -- the reference `continue`s there
 // before it looks at anything else (REF:143-148); otherwise the worse of the other two roles
 __device__ __forceinline__ uint32_t rec_status(const LineRecF& R) {
-    return R.stB != ST_FAST ? (uint32_t)R.stB : max((uint32_t)R.stA, (uint32_t)R.stC);
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(&R.nops);        // nops | stA << 8 | stB << 16 | stC << 24: one LDS
+    const uint32_t a = (w >> 8) & 0xFFu, b = (w >> 16) & 0xFFu, c = w >> 24;
+    return b != ST_FAST ? b : max(a, c);
 }
 __device__ __forceinline__ int rec_why(const LineRecF& R) {
     return R.stB == ST_DEFER ? (int)R.whyB : (R.stC == ST_DEFER ? (int)WHY_INTS : (int)R.whyA);
@@ -250,7 +254,6 @@ template <class G>
 __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(ChunkArgs A, Tables T) {
     constexpr uint32_t THREADS = G::THREADS;
     constexpr uint32_t NWARPS = THREADS / 32;
-    constexpr uint32_t NCOLS = G::NCOLS;
     PT_DYNAMIC_SMEM(smem);
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t s_nops, s_nfar, s_ndel, s_oth;
@@ -264,9 +267,9 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
     unsigned long long* const nl64 = reinterpret_cast<unsigned long long*>(smem + G::OFF_NL);
     unsigned long long* const sm64 = reinterpret_cast<unsigned long long*>(smem + G::OFF_SM);
     unsigned long long* const gpre = reinterpret_cast<unsigned long long*>(smem + G::OFF_PRE);
-    uint16_t* const ecol = reinterpret_cast<uint16_t*>(smem + G::OFF_ECOL);    // [record][NCOLS]: [0] = start - 1, [c] = c-th whitespace
+    uint16_t* const wslist = reinterpret_cast<uint16_t*>(smem + G::OFF_WSL);   // positions of the whitespace bytes, in order
     uint16_t* const lines = reinterpret_cast<uint16_t*>(smem + G::OFF_LINES);  // first byte of record r
-    uint8_t* const ncol = smem + G::OFF_NCOL;                                  // whitespace bytes of record r incl. its newline (0: not terminated)
+    uint16_t* const recws = reinterpret_cast<uint16_t*>(smem + G::OFF_RECWS);  // whitespace ordinal at the start of record r
     uint32_t* const sinfo = reinterpret_cast<uint32_t*>(smem + G::OFF_SINFO);  // step-length prefix           (second life of region X)
     uint32_t* const far = reinterpret_cast<uint32_t*>(smem + G::OFF_FAR);      // {from, to, separator position}
     uint32_t* const dels = reinterpret_cast<uint32_t*>(smem + G::OFF_DEL);     // {step, first del, last del}
@@ -329,7 +332,6 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         parity ^= 1;
 
         // ================= scan: one thread per 16-byte vector -> 16-bit pieces of the three masks =================
-        for (uint32_t i = tid; i < (uint32_t)G::LINE_CAP / 4u; i += THREADS) reinterpret_cast<uint32_t*>(ncol)[i] = 0u;
         {
             uint16_t* const wm16 = reinterpret_cast<uint16_t*>(wm64);
             uint16_t* const nl16 = reinterpret_cast<uint16_t*>(nl64);
@@ -421,11 +423,12 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             }
             if (tid == 0) gpre[nwords] = tot & PRE_SUMS;                    // counts before a position just past the last word
         }
+        const uint32_t n_ws_all = (uint32_t)tot & 0xFFFFu;                  // whitespace bytes in the loaded bytes
         const uint32_t n_sep_all = (uint32_t)(tot >> 16) & 0xFFFFu;         // separators in the loaded bytes
         const uint32_t n_rec_all = (uint32_t)(tot >> 32) & 0xFFFFu;         // records starting in the loaded bytes (ours + look-ahead)
         __syncthreads();                                                    // ---- prefix complete
 
-        if (n_rec_all > (uint32_t)G::LINE_CAP || n_sep_all + n_rec_all > (uint32_t)G::STEP_CAP) {
+        if (n_rec_all > (uint32_t)G::LINE_CAP || n_sep_all > (uint32_t)G::STEP_CAP || n_ws_all > (uint32_t)G::WS_CAP) {
             // more records / separators than the lists hold (pathological input): the whole tile takes the slow path
             for (uint32_t w = tid; w < nwords; w += THREADS) {
                 unsigned long long m = nl64[w];
@@ -446,44 +449,51 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             continue;
         }
 
-        // ================= columns: one thread per mask word: whitespace bit -> (record, column) =================
-        for (uint32_t g = tid; g < nwords; g += THREADS) {
-            unsigned long long m = wm64[g];
-            if (m == 0ull) continue;
-            const unsigned long long gp = gpre[g], nlv = nl64[g];
-            int32_t j = (int32_t)((uint32_t)(gp >> 32) & 0xFFFFu) - 1;     // record open at the start of the word (-1: none of ours)
-            uint32_t c = 0;
-            if (j >= 0) c = ((uint32_t)gp & 0xFFFFu) - ws_at((uint32_t)(gp >> PRE_LS_SHIFT));   // its whitespace bytes so far
-            while (m) {
-                const uint32_t b = (uint32_t)(__ffsll((long long)m) - 1);
-                m &= m - 1ull;
-                const uint32_t q = 64u * g + b;
-                c++;
-                if (j >= 0 && c < NCOLS) ecol[(uint32_t)j * NCOLS + c] = (uint16_t)q;
-                if ((nlv >> b) & 1ull) {
-                    if (j >= 0) ncol[j] = (uint8_t)min(c, 255u);
-                    j++;
-                    c = 0;
-                    lines[j] = (uint16_t)(q + 1u);
-                    ecol[(uint32_t)j * NCOLS] = (uint16_t)q;
+        // ================= scatter: one thread per vector: whitespace / separator bit -> flat lists at its ordinal =================
+        for (uint32_t v = tid; v < 4u * nwords; v += THREADS) {
+            const uint32_t w = v >> 2, sh = 16u * (v & 3u);
+            const unsigned long long wmw = wm64[w], smw = sm64[w];
+            uint32_t w16 = (uint32_t)(wmw >> sh) & 0xFFFFu, s16 = (uint32_t)(smw >> sh) & 0xFFFFu;
+            if ((w16 | s16) == 0u) continue;
+            const unsigned long long nlw = nl64[w], gp = gpre[w], below = ~(~0ull << sh);
+            const uint32_t n16 = (uint32_t)(nlw >> sh) & 0xFFFFu;
+            uint32_t ows = ((uint32_t)gp & 0xFFFFu) + (uint32_t)__popcll(wmw & below);
+            uint32_t osep = ((uint32_t)(gp >> 16) & 0xFFFFu) + (uint32_t)__popcll(smw & below);
+            uint32_t rec = ((uint32_t)(gp >> 32) & 0xFFFFu) + (uint32_t)__popcll(nlw & below);   // records started before the vector
+            while (s16) {
+                const uint32_t b = (uint32_t)(__ffs((int)s16) - 1);
+                s16 &= s16 - 1u;
+                const uint32_t k = rec + (uint32_t)__popc(n16 & ((1u << b) - 1u));      // records started before the byte
+                steps[osep++] = k == 0u ? SE_INVALID : ((16u * v + b) | ((k - 1u) << SE_SLOT_SHIFT));   // k == 0: tail of a record of the previous tile
+            }
+            while (w16) {
+                const uint32_t b = (uint32_t)(__ffs((int)w16) - 1);
+                w16 &= w16 - 1u;
+                const uint32_t pos = 16u * v + b;
+                wslist[ows++] = (uint16_t)pos;
+                if ((n16 >> b) & 1u) {
+                    lines[rec] = (uint16_t)(pos + 1u);
+                    recws[rec] = (uint16_t)ows;
+                    rec++;
                 }
             }
         }
-        __syncthreads();                                                    // ---- column boundaries, record starts complete
+        __syncthreads();                                                    // ---- whitespace list, raw step list, record starts complete
 
-        // records that start in the owned bytes; step-list entries up to the sentinel of the last one
+        // records that start in the owned bytes; their separators = the step-list entries that matter
         const uint32_t n_own = (uint32_t)(pre_at(own_end - 1u) >> 32) & 0xFFFFu;
-        const uint32_t n_ent = n_own == 0u ? 0u : (n_own < n_rec_all ? sep_at(lines[n_own]) : n_sep_all) + n_own;
+        const uint32_t n_ent = n_own == 0u ? 0u : (n_own < n_rec_all ? sep_at(lines[n_own]) : n_sep_all);
         if (tid == 0) { my_lines += n_own; my_tiles++; }
 
-        // ================= fields: A (tags), T0 (shape, filters, path shape), T1 (coordinates), S (step entries) =================
-        for (uint32_t item = tid; item < 3u * n_own + nwords; item += THREADS) {
+        // ================= fields: A (tags), T0 (shape, filters, path shape), T1 (coordinates) =================
+        for (uint32_t item = tid; item < 3u * n_own; item += THREADS) {
             if (item < n_own) {
                 // ---------------- role A: tags -> dv filter, cs ops
                 const uint32_t l = item;
                 LineRecF& R = recs[l];
-                const uint16_t* const e = ecol + l * NCOLS;
-                const uint32_t nc = ncol[l];
+                const uint32_t rw = recws[l];
+                const uint16_t* const e = wslist + rw - 1u;               // e[c]: end of column c (e[0]: the newline before the record)
+                const uint32_t nc = l + 1u < n_rec_all ? (uint32_t)recws[l + 1u] - rw : 0u;   // whitespace bytes incl. the newline; 0: not terminated
                 int why = WHY_TAGS;
                 bool slow = nc < 13u, done = false;                          // no tags: no dv, ValueError (REF:179); the slow path reports
                 uint32_t cs_a = 0, cs_b = 0, dv_a = 0, dv_b = 0;
@@ -602,8 +612,9 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 // ---------------- role T0: column shape, MAPQ and '*' filters, path column shape, sentinel
                 const uint32_t l = item - n_own;
                 LineRecF& R = recs[l];
-                const uint16_t* const e = ecol + l * NCOLS;
-                const uint32_t nc = ncol[l];
+                const uint32_t rw = recws[l];
+                const uint16_t* const e = wslist + rw - 1u;               // e[c]: end of column c (e[0]: the newline before the record)
+                const uint32_t nc = l + 1u < n_rec_all ? (uint32_t)recws[l + 1u] - rw : 0u;   // whitespace bytes incl. the newline; 0: not terminated
                 int why = WHY_LONG;                                         // nc == 0: the record runs past the look-ahead
                 bool slow = nc < 12u, done = false;
                 uint32_t e6 = 0;
@@ -645,18 +656,20 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                         if (ns == 0u || ns > (uint32_t)MAX_STEPS || !((sm64[a5 >> 6] >> (a5 & 63u)) & 1ull)) slow = true;
                     }
                 }
-                // the record's sentinel closes its range of the step list (role S fills the rest)
-                steps[(l + 1u < n_rec_all ? sep_at(lines[l + 1u]) : n_sep_all) + l] = e6 | (l << SE_SLOT_SHIFT) | SE_SENT;
+                R.a5 = (uint16_t)(nc >= 6u ? (uint32_t)e[5] + 1u : 0xFFFFu);            // `ids`: which separators are path steps
+                R.b5 = (uint16_t)(nc >= 6u ? e6 : 0xFFFFu);
                 R.ls = lines[l];
                 R.stB = (uint8_t)(slow ? ST_DEFER : (done ? ST_DONE : ST_FAST));
                 R.whyB = (uint8_t)why;
-            } else if (item < 3u * n_own) {
+            } else {
                 // ---------------- role T1: the three coordinates (REF:151-153)
                 const uint32_t l = item - 2u * n_own;
                 LineRecF& R = recs[l];
-                const uint16_t* const e = ecol + l * NCOLS;
+                const uint32_t rw = recws[l];
+                const uint16_t* const e = wslist + rw - 1u;               // e[c]: end of column c (e[0]: the newline before the record)
+                const uint32_t nc = l + 1u < n_rec_all ? (uint32_t)recws[l + 1u] - rw : 0u;   // whitespace bytes incl. the newline; 0: not terminated
                 uint32_t st = ST_FAST;
-                if (ncol[l] >= 12u) {
+                if (nc >= 12u) {
                     int32_t plen = 0, start = 0, pend = 0;
                     const uint32_t e7 = e[7], e8 = e[8];
                     if (small_uint(buf, (uint32_t)e[6] + 1u, e7, plen) && small_uint(buf, e7 + 1u, e8, start) &&
@@ -668,71 +681,50 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                     }
                 }
                 R.stC = (uint8_t)st;
-            } else {
-                // ---------------- role S: one mask word: separator bit -> step-list entry
-                //   slot = (separators before it) + (its record's number): every record's entries are contiguous
-                //   and followed by one free slot, its sentinel
-                const uint32_t g = item - 3u * n_own;
-                unsigned long long m = sm64[g];
-                if (m == 0ull) continue;
-                const unsigned long long gp = gpre[g], nlv = nl64[g];
-                uint32_t o = (uint32_t)(gp >> 16) & 0xFFFFu;               // ordinal of the word's first separator
-                const int32_t k = (int32_t)((uint32_t)(gp >> 32) & 0xFFFFu);
-                int32_t jc = -2;
-                uint32_t a5 = 0, b5 = 0, common = 0;
-                bool shape = false;
-                while (m) {
-                    const uint32_t b = (uint32_t)(__ffsll((long long)m) - 1);
-                    m &= m - 1ull;
-                    const uint32_t q = 64u * g + b;
-                    const int32_t j = k + __popcll(nlv & ~(~0ull << b)) - 1;            // the record the byte is in
-                    const uint32_t slot = o + (uint32_t)max(j, 0);
-                    o++;
-                    if (slot >= n_ent) break;                               // look-ahead records: not ours
-                    if (j < 0) { steps[slot] = SE_INVALID; continue; }      // tail of a record of the previous tile
-                    if (j != jc) {
-                        jc = j;
-                        shape = ncol[j] >= 6u;
-                        if (shape) {
-                            a5 = (uint32_t)ecol[(uint32_t)j * NCOLS + 5u] + 1u;
-                            b5 = ecol[(uint32_t)j * NCOLS + 6u];
-                            common = ((uint32_t)j << SE_SLOT_SHIFT) | (buf[a5] == '<' ? SE_REV : 0u);
-                        }
-                    }
-                    uint32_t ent;
-                    if (!shape || q < a5) ent = SE_INVALID;                 // not in the path column (read names ...)
-                    else if (q >= b5) ent = b5 | ((uint32_t)j << SE_SLOT_SHIFT) | SE_SENT;
-                    else {
-                        uint32_t nq = b5;                                   // the next separator
-                        if (m) nq = 64u * g + (uint32_t)(__ffsll((long long)m) - 1);
-                        else
-                            for (uint32_t w = g + 1u; 64u * w < b5; w++) {
-                                const unsigned long long mm = sm64[w];
-                                if (mm) { nq = 64u * w + (uint32_t)(__ffsll((long long)mm) - 1); break; }
-                            }
-                        ent = q | common | (q == a5 ? SE_FIRST : 0u) | (nq >= b5 ? SE_LAST : 0u);
-                    }
-                    steps[slot] = ent;
-                }
             }
         }
-        __syncthreads();                                                    // ---- records, ops, step list complete
+        __syncthreads();                                                    // ---- records, ops complete
 
-        // ================= ids: one thread per path step: id -> node index =================
-        for (uint32_t s = tid; s < n_ent; s += THREADS) {
-            const uint32_t se = steps[s];
-            uint32_t idx = NONE32;
-            if (se != SE_INVALID && !(se & SE_SENT)) {
-                const uint32_t p = se & SE_POS_MASK;
-                const uint32_t end = steps[s + 1u] & SE_POS_MASK;           // next separator, or the sentinel
-                uint64_t id;
-                uint32_t ix;
-                if (buf[p] == ((se & SE_REV) ? '<' : '>') && step_id(buf, p + 1u, end - p - 1u, id) && sink.id_to_idx(id, ix)) {
-                    idx = ix;
-                    sink.prefetch_node(ix);
+        // ================= ids: one thread per separator: path step or not, first / last, id -> node index, node length =================
+        // UI entries per thread and iteration: their node-record loads are all in flight before the first is stored
+        // (the load also brings the node's sector into L2 for the count phase).  `sinfo` holds the lengths until walk 1.
+        {
+            constexpr int UI = 4;
+            for (uint32_t s00 = 0; s00 < n_ent; s00 += THREADS * UI) {
+                uint32_t idx_[UI], len_[UI], se_[UI];
+#pragma unroll
+                for (int u = 0; u < UI; u++) {
+                    const uint32_t s = s00 + THREADS * u + tid;
+                    uint32_t idx = NONE32, se = SE_INVALID;
+                    if (s < n_ent) {
+                        const uint32_t raw = steps[s];                      // position | record << 16, from `scatter`
+                        if (raw != SE_INVALID) {
+                            const uint32_t p = raw & SE_POS_MASK;
+                            const LineRecF& R = recs[raw >> SE_SLOT_SHIFT];
+                            const uint32_t ab = *reinterpret_cast<const uint32_t*>(&R.a5), a5 = ab & 0xFFFFu, b5 = ab >> 16;
+                            if (p >= a5 && p < b5) {                        // inside the path column (not: read names, tags ...)
+                                // the next entry is the next separator of the record, or something at / past the end of the column
+                                const uint32_t nxt = s + 1u < n_sep_all ? (steps[s + 1u] & SE_POS_MASK) : SE_POS_MASK;
+                                const uint32_t end = min(nxt, b5);
+                                const bool rev = buf[a5] == '<';
+                                se = raw | (rev ? SE_REV : 0u) | (p == a5 ? SE_FIRST : 0u) | (nxt >= b5 ? SE_LAST : 0u);
+                                uint64_t id;
+                                uint32_t ix;
+                                if (buf[p] == (rev ? '<' : '>') && step_id(buf, p + 1u, end - p - 1u, id) && sink.id_to_idx(id, ix)) idx = ix;
+                            }
+                        }
+                    }
+                    se_[u] = se;
+                    idx_[u] = idx;                                          // NONE32: KeyError in the reference, `walk` hands the record over
+                }
+#pragma unroll
+                for (int u = 0; u < UI; u++) len_[u] = idx_[u] != NONE32 ? sink.load_len(idx_[u]) : 0u;
+#pragma unroll
+                for (int u = 0; u < UI; u++) {
+                    const uint32_t s = s00 + THREADS * u + tid;
+                    if (s < n_ent) { steps[s] = se_[u]; sidx[s] = idx_[u]; sinfo[s] = len_[u]; }
                 }
             }
-            sidx[s] = idx;                                                  // NONE32: KeyError in the reference, `walk` hands the record over
         }
         __syncthreads();                                                    // ---- node indices complete; the bytes and the masks are dead
         if (tid == 0) {
@@ -745,18 +737,19 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         }
 
         // ================= walk 1: step lengths and their block-wide prefix sum =================
-        const uint32_t per = (n_ent + THREADS - 1u) / THREADS;              // consecutive entries per thread
-        const uint32_t sa = min(tid * per, n_ent), sb = min(sa + per, n_ent);
+        // (one entry more than the list holds: walk 2 closes the last step with sinfo[s + 1])
+        const uint32_t per = (n_ent + THREADS) / THREADS;                   // consecutive entries per thread
+        const uint32_t sa = min(tid * per, n_ent + 1u), sb = min(sa + per, n_ent + 1u);
         {
             uint32_t local = 0;
             for (uint32_t s = sa; s < sb; s++) {
-                const uint32_t se = steps[s];
+                const uint32_t se = s < n_ent ? steps[s] : SE_INVALID;
                 uint32_t Lc = 0;
                 if (se != SE_INVALID && !(se & SE_SENT)) {
                     LineRecF& R = recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK];
                     if (rec_status(R) == ST_FAST) {
                         const uint32_t idx = sidx[s];
-                        const uint32_t len = sink.load_len(idx == NONE32 ? 0u : idx);
+                        const uint32_t len = sinfo[s];                      // left there by `ids`
                         // unknown id: KeyError (REF:214); collapsible duplicate (REF:188): the slow path redoes the record
                         if (idx == NONE32 || len == pt::NODE_LEN_ABSENT || (!(se & SE_FIRST) && idx == sidx[s - 1u])) {
                             R.stB = ST_DEFER;
@@ -785,7 +778,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             for (uint32_t s = sa; s < sb; s++) {
                 const uint32_t g = sinfo[s] + basev;
                 sinfo[s] = g;
-                const uint32_t se = steps[s];
+                const uint32_t se = s < n_ent ? steps[s] : SE_INVALID;
                 if (se != SE_INVALID && (se & SE_FIRST)) recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK].base = g;
             }
         }
