@@ -32,16 +32,18 @@
 //            step?  then the SWAR decimal parse of the id out of shared memory, node index, node length
 //            (the load also pulls the node's sector into L2).  After this phase the bytes are dead and the
 //            next tile's TMA copy is issued: it overlaps the table traffic of the remaining phases.
-//   walk     one thread per RECORD, its state in registers, two passes over its entries of the step list.
-//            Pass 1 is the reference's merge walk (REF:205-255) with clear_align / compact_align
-//            (REF:63-107) folded in: node k gets the cs ops that overlap [A, A + L_k) (first / last node
-//            shortened, REF:215-218): dropped or not, number of counting ops, deletion-derived IL/OL keys.
-//            Collapsible duplicate ids (REF:188), unknown ids and a cs string shorter than the path hand
-//            the record over; nothing has been counted yet, so the hand-over is clean.  Pass 2 counts
-//            (REF:263-363): one RED.ADD.64 per surviving node on the node's sector (tables.cuh), RED.MIN
-//            for first-touch stamps only when the tile could lower them.  Links that are not inline and
-//            deletion-derived keys are collected in two short lists and done by all threads at the end
-//            of the tile (hash-table work, all lanes busy).
+//   walk     one thread per path step.  The reference's merge walk (REF:205-255) gives node k the
+//            ops that overlap [A_k, A_k + L_k) in cs coordinates, where A is the prefix sum of the
+//            node lengths L (first / last node shortened, REF:215-218): a block-wide prefix sum,
+//            then every step finds its op pieces independently and folds clear_align /
+//            compact_align (REF:63-107) over them: dropped or not, number of counting ops,
+//            deletion-derived IL/OL keys.  Collapsible duplicate ids (REF:188), unknown ids and a
+//            cs string shorter than the path hand the record over.  Nothing has been counted yet,
+//            so the hand-over is clean.
+//   count    one thread per surviving step: NC / IL / OL / RC events (REF:263-363): one RED.ADD.64
+//            on the node's sector (tables.cuh), RED.MIN for first-touch stamps only when earlier.
+//            Links that are not inline and deletion-derived keys are collected in two short lists
+//            and done by all threads at the end of the tile (hash-table work, all lanes busy).
 #pragma once
 
 namespace fastp {
@@ -60,25 +62,22 @@ struct __align__(8) LineRecF {
     int32_t end_rel1;     // int(tokens[6]) - int(tokens[8]) - 1               (role T1)
     int32_t start_add;    // cigar_clipping: start_pos += len of a leading '+' (role A, REF:46-47)
     uint32_t n_tot;       // sum of the cs op lengths                          (role A)
-    uint16_t s0, ns;      // the record's entries of the step list             (role T0)
+    uint32_t base;        // step-length prefix at the record's first step     (walk)
     uint16_t ls;          // buffer position of the record's first byte        (role T0)
     uint16_t op_off;      // first op of the record in the op pool             (role A)
     uint8_t nops;         //                                                   (role A)
     uint8_t stA, stB, stC;   // ST_* per role; walk raises stB
     uint16_t a5, b5;      // the path column [a5, b5) (0xFFFF, 0xFFFF: the record has none)   (role T0)
     uint8_t whyA, whyB;   // WHY_* when the role says ST_DEFER (T1: always WHY_INTS)
-    uint8_t rev;          // path written with '<'                             (role T0)
-    uint8_t pad[5];
+    uint8_t pad[6];
 };
 static_assert(sizeof(LineRecF) == 40, "record layout");
 
-// step list entry: `scatter` writes position | record << 16 (or SE_INVALID); `ids` rewrites the path steps as
-constexpr uint32_t SE_POS_MASK = 0xFFFFu;     // bits 0..15  buffer position of the separator
-constexpr int SE_SLOT_SHIFT = 16;             // (raw entry) bits 16..24 record slot
-constexpr int SE_LEN_SHIFT = 16;              // bits 16..25 node length (longer nodes: slow path)
-constexpr uint32_t SE_LEN_MASK = 0x3FFu;
-constexpr uint32_t SE_NEED_IL = 1u << 26, SE_NEED_OL = 1u << 27;   // the first-touch stamp may still be lowered by this tile
-constexpr uint32_t SE_DROPPED = 1u << 29;     // the walk: the node is not in `align`
+// step list entry
+constexpr uint32_t SE_POS_MASK = 0xFFFFu;     // bits 0..15  buffer position of the separator (sentinel: end of the path column)
+constexpr int SE_SLOT_SHIFT = 16;             // bits 16..24 record slot
+constexpr uint32_t SE_SLOT_MASK = 0x1FFu;
+constexpr uint32_t SE_FIRST = 1u << 25, SE_LAST = 1u << 26, SE_REV = 1u << 27, SE_SENT = 1u << 28, SE_DROPPED = 1u << 29;
 constexpr int SE_NCNT_SHIFT = 30;             // bits 30..31 counting ops of the compacted slice (0..3)
 constexpr uint32_t SE_INVALID = 0xFFFFFFFFu;
 
@@ -113,7 +112,7 @@ struct Geo {
     static constexpr int OFF_SINFO = OFF_WM;
     static constexpr int OFF_FAR = OFF_SINFO + 4 * (STEP_CAP + 4);
     static constexpr int OFF_DEL = OFF_FAR + 12 * FAR_CAP;
-    static constexpr int X_END2 = OFF_DEL + 16 * DEL_CAP;
+    static constexpr int X_END2 = OFF_DEL + 12 * DEL_CAP;
     static constexpr int OFF_STEP = ((X_END1 > X_END2 ? X_END1 : X_END2) + 15) & ~15;
     static constexpr int OFF_SIDX = OFF_STEP + 4 * STEP_CAP;
     static constexpr int OFF_OPS = OFF_SIDX + 4 * STEP_CAP;
@@ -260,6 +259,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
     __shared__ uint32_t s_nops, s_nfar, s_ndel, s_oth;
     __shared__ unsigned long long s_wsum64[NWARPS];
     __shared__ uint32_t s_wmax[NWARPS];
+    __shared__ uint32_t s_wsum[NWARPS];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint8_t* const buf = smem;
@@ -270,9 +270,9 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
     uint16_t* const wslist = reinterpret_cast<uint16_t*>(smem + G::OFF_WSL);   // positions of the whitespace bytes, in order
     uint16_t* const lines = reinterpret_cast<uint16_t*>(smem + G::OFF_LINES);  // first byte of record r
     uint16_t* const recws = reinterpret_cast<uint16_t*>(smem + G::OFF_RECWS);  // whitespace ordinal at the start of record r
-    uint32_t* const sd01 = reinterpret_cast<uint32_t*>(smem + G::OFF_SINFO);   // inline link deltas of the step's node   (second life of region X)
+    uint32_t* const sinfo = reinterpret_cast<uint32_t*>(smem + G::OFF_SINFO);  // step-length prefix           (second life of region X)
     uint32_t* const far = reinterpret_cast<uint32_t*>(smem + G::OFF_FAR);      // {from, to, separator position}
-    uint32_t* const dels = reinterpret_cast<uint32_t*>(smem + G::OFF_DEL);     // {step, first del, last del, record}
+    uint32_t* const dels = reinterpret_cast<uint32_t*>(smem + G::OFF_DEL);     // {step, first del, last del}
     uint32_t* const steps = reinterpret_cast<uint32_t*>(smem + G::OFF_STEP);
     uint32_t* const sidx = reinterpret_cast<uint32_t*>(smem + G::OFF_SIDX);
     uint32_t* const ops = reinterpret_cast<uint32_t*>(smem + G::OFF_OPS);
@@ -617,8 +617,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 const uint32_t nc = l + 1u < n_rec_all ? (uint32_t)recws[l + 1u] - rw : 0u;   // whitespace bytes incl. the newline; 0: not terminated
                 int why = WHY_LONG;                                         // nc == 0: the record runs past the look-ahead
                 bool slow = nc < 12u, done = false;
-                uint32_t e6 = 0, s0 = 0, ns = 0;
-                bool rev = false;
+                uint32_t e6 = 0;
                 if (nc != 0u && nc < 12u) why = WHY_COLUMNS;                // fewer than 12 columns: IndexError (REF:143), slow path reports
                 if (nc >= 6u) e6 = e[6];
                 if (!slow) {
@@ -653,17 +652,12 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                         // ---- path column (REF:185-197): it must start with a separator; count the steps
                         why = WHY_PATH;
                         const uint32_t a5 = e5 + 1u;
-                        s0 = sep_at(a5);
-                        ns = sep_at(e6) - s0;
-                        rev = buf[a5] == '<';
+                        const uint32_t ns = sep_at(e6) - sep_at(a5);
                         if (ns == 0u || ns > (uint32_t)MAX_STEPS || !((sm64[a5 >> 6] >> (a5 & 63u)) & 1ull)) slow = true;
                     }
                 }
                 R.a5 = (uint16_t)(nc >= 6u ? (uint32_t)e[5] + 1u : 0xFFFFu);            // `ids`: which separators are path steps
                 R.b5 = (uint16_t)(nc >= 6u ? e6 : 0xFFFFu);
-                R.s0 = (uint16_t)s0;
-                R.ns = (uint16_t)ns;
-                R.rev = (uint8_t)rev;
                 R.ls = lines[l];
                 R.stB = (uint8_t)(slow ? ST_DEFER : (done ? ST_DONE : ST_FAST));
                 R.whyB = (uint8_t)why;
@@ -691,22 +685,17 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         }
         __syncthreads();                                                    // ---- records, ops complete
 
-        // ================= ids: one thread per separator: path step or not, id -> node index, the node's record =================
-        // UI entries per thread and iteration: their node-record loads (one 16-byte LDG each) are all in flight before
-        // the first is used.  What the walk needs of the node record is kept in shared memory: the length, the two
-        // inline link deltas, and whether a first-touch stamp could still be lowered by this tile.
+        // ================= ids: one thread per separator: path step or not, first / last, id -> node index, node length =================
+        // UI entries per thread and iteration: their node-record loads are all in flight before the first is stored
+        // (the load also brings the node's sector into L2 for the count phase).  `sinfo` holds the lengths until walk 1.
         {
             constexpr int UI = 4;
-            // a stamp that is already below every stamp this tile can produce needs no RED.MIN (stamps only decrease)
-            const int64_t rel0 = base_off + 16 - T.epoch_base;
-            const uint32_t rel_tile = rel0 < 0 ? 0u : (uint32_t)rel0;
             for (uint32_t s00 = 0; s00 < n_ent; s00 += THREADS * UI) {
-                uint32_t idx_[UI], pf_[UI];
-                DevSink::Hot hot_[UI];
+                uint32_t idx_[UI], len_[UI], se_[UI];
 #pragma unroll
                 for (int u = 0; u < UI; u++) {
                     const uint32_t s = s00 + THREADS * u + tid;
-                    uint32_t idx = NONE32, pf = 0;
+                    uint32_t idx = NONE32, se = SE_INVALID;
                     if (s < n_ent) {
                         const uint32_t raw = steps[s];                      // position | record << 16, from `scatter`
                         if (raw != SE_INVALID) {
@@ -717,178 +706,252 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                                 // the next entry is the next separator of the record, or something at / past the end of the column
                                 const uint32_t nxt = s + 1u < n_sep_all ? (steps[s + 1u] & SE_POS_MASK) : SE_POS_MASK;
                                 const uint32_t end = min(nxt, b5);
+                                const bool rev = buf[a5] == '<';
+                                se = raw | (rev ? SE_REV : 0u) | (p == a5 ? SE_FIRST : 0u) | (nxt >= b5 ? SE_LAST : 0u);
                                 uint64_t id;
                                 uint32_t ix;
-                                pf = p;
-                                if (buf[p] == buf[a5] && step_id(buf, p + 1u, end - p - 1u, id) && sink.id_to_idx(id, ix)) idx = ix;
+                                if (buf[p] == (rev ? '<' : '>') && step_id(buf, p + 1u, end - p - 1u, id) && sink.id_to_idx(id, ix)) idx = ix;
                             }
                         }
                     }
-                    pf_[u] = pf;
-                    idx_[u] = idx;                                          // NONE32: KeyError in the reference, the walk hands the record over
+                    se_[u] = se;
+                    idx_[u] = idx;                                          // NONE32: KeyError in the reference, `walk` hands the record over
                 }
 #pragma unroll
-                for (int u = 0; u < UI; u++) {
-                    hot_[u].len = 0; hot_[u].il = 0; hot_[u].ol = 0; hot_[u].d01 = 0;
-                    if (idx_[u] != NONE32) hot_[u] = sink.load_hot(idx_[u]);
-                }
+                for (int u = 0; u < UI; u++) len_[u] = idx_[u] != NONE32 ? sink.load_len(idx_[u]) : 0u;
 #pragma unroll
                 for (int u = 0; u < UI; u++) {
                     const uint32_t s = s00 + THREADS * u + tid;
-                    if (s < n_ent) {
-                        uint32_t idx = idx_[u];
-                        if (hot_[u].len > SE_LEN_MASK) idx = NONE32;        // no such S line, or a node longer than the entry holds: slow path
-                        steps[s] = pf_[u] | ((hot_[u].len & SE_LEN_MASK) << SE_LEN_SHIFT) | (hot_[u].il > rel_tile ? SE_NEED_IL : 0u) |
-                                   (hot_[u].ol > rel_tile ? SE_NEED_OL : 0u);
-                        sidx[s] = idx;
-                        sd01[s] = hot_[u].d01;
-                    }
+                    if (s < n_ent) { steps[s] = se_[u]; sidx[s] = idx_[u]; sinfo[s] = len_[u]; }
                 }
             }
         }
-        __syncthreads();                                                    // ---- step entries complete; the bytes and the masks are dead
+        __syncthreads();                                                    // ---- node indices complete; the bytes and the masks are dead
         if (tid == 0) {
             s_nops = 0;
+            s_nfar = 0;
+            s_ndel = 0;
             s_oth = 0;
             const uint32_t nxt = tile + gridDim.x;
-            if (nxt < A.n_tiles) issue_load(nxt);                           // overlaps the walk
+            if (nxt < A.n_tiles) issue_load(nxt);                           // overlaps walk + count
         }
 
-        // ================= walk: one thread per record =================
-        // Pass 1 is the reference's merge walk (REF:205-255) with clear_align / compact_align (REF:63-107) folded in:
-        // node k gets the cs ops that overlap [A, A + L_k); nothing is counted, so a record can still be handed over.
-        // Pass 2 counts (REF:263-363): one RED.ADD.64 per surviving node, on the node's own sector.
-        for (uint32_t l = tid; l < n_own; l += THREADS) {
-            LineRecF& R = recs[l];
-            const uint32_t st0 = rec_status(R);
-            if (st0 != ST_FAST) {
-                if (st0 == ST_DEFER) defer_line(T, t0 + R.ls - 16u, A.file_off, rec_why(R));
-                continue;
-            }
-            const uint32_t s0 = R.s0, ns = R.ns, n_tot = R.n_tot, nops = R.nops;
-            const uint32_t* const op = ops + R.op_off;
-            const bool rev = R.rev != 0;
-            const int32_t cut_first = R.start + R.start_add, cut_last = R.end_rel1;
-            // ---- pass 1
-            bool defer = false;
-            {
-                uint32_t Ak = 0, prev_idx = NONE32;
-                uint32_t j = 0, o_start = 0, o_end = op[0] >> 3;            // cs cursor: op j covers [o_start, o_end)
-                const uint32_t kind0 = op[0] & 7u;
-                for (uint32_t k = 0; k < ns; k++) {
-                    const uint32_t s = s0 + k, pf = steps[s], idx = sidx[s];
-                    // unknown id: KeyError (REF:214); collapsible duplicate (REF:188): the slow path redoes the record
-                    if (idx == NONE32 || idx == prev_idx) { defer = true; break; }
-                    prev_idx = idx;
-                    int32_t L = (int32_t)((pf >> SE_LEN_SHIFT) & SE_LEN_MASK);
-                    if (k == 0u) L -= cut_first;                            // REF:215-216
-                    if (k + 1u == ns) L -= cut_last;                        // REF:217-218
-                    if (L <= 0) { steps[s] = pf | SE_DROPPED; continue; }   // no bases left for this node: it is not in `align`
-                    if (Ak >= n_tot) { defer = true; break; }               // cs used up before the path ends: IndexError (REF:227)
-                    const uint32_t Lk = (uint32_t)L;
-                    if (nops == 1u) {                                       // one op (a perfect match, mostly): its piece is the whole slice
-                        steps[s] = (kind0 == OP_DEL || kind0 == OP_INS) ? (pf | SE_DROPPED)              // REF:101-102
-                                                                        : (pf | ((kind0 != OP_SUB ? 1u : 0u) << SE_NCNT_SHIFT));
-                        Ak += Lk;
-                        continue;
-                    }
-                    const uint32_t Bk = min(Ak + Lk, n_tot);
-                    // pieces of the node = ops overlapping [Ak, Bk), clipped; compact_align as a running fold (REF:63-94)
-                    while (o_end <= Ak) {                                   // ends before the node starts (j < nops: Ak < n_tot)
-                        j++;
-                        o_start = o_end;
-                        o_end += op[j] >> 3;
-                    }
-                    uint32_t nP = 0, nQ = 0, p0 = 0, qlast_op = 0, qlast_len = 0, first_op = 0, first_len = 0, n_count = 0;
-                    for (;;) {
-                        const uint32_t kind = op[j] & 7u;
-                        const uint32_t take = min(o_end, Bk) - max(o_start, Ak);
-                        bool push = false;
-                        uint32_t push_len = take;
-                        if (nP == 0u) { p0 = kind; push = kind != OP_SUB; }
-                        else if (nQ == 0u) { push = true; push_len = take + 1u; }
-                        else if (kind == qlast_op || kind == OP_SUB) qlast_len += take;
-                        else push = true;
-                        if (push) {
-                            if (nQ == 1u) { first_op = qlast_op; first_len = qlast_len; }
-                            qlast_op = kind;
-                            qlast_len = push_len;
-                            nQ++;
-                            if (kind != OP_DEL && kind != OP_SUB) n_count++;
+        // ================= walk 1: step lengths and their block-wide prefix sum =================
+        // (one entry more than the list holds: walk 2 closes the last step with sinfo[s + 1])
+        const uint32_t per = (n_ent + THREADS) / THREADS;                   // consecutive entries per thread
+        const uint32_t sa = min(tid * per, n_ent + 1u), sb = min(sa + per, n_ent + 1u);
+        {
+            uint32_t local = 0;
+            for (uint32_t s = sa; s < sb; s++) {
+                const uint32_t se = s < n_ent ? steps[s] : SE_INVALID;
+                uint32_t Lc = 0;
+                if (se != SE_INVALID && !(se & SE_SENT)) {
+                    LineRecF& R = recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK];
+                    if (rec_status(R) == ST_FAST) {
+                        const uint32_t idx = sidx[s];
+                        const uint32_t len = sinfo[s];                      // left there by `ids`
+                        // unknown id: KeyError (REF:214); collapsible duplicate (REF:188): the slow path redoes the record
+                        if (idx == NONE32 || len == pt::NODE_LEN_ABSENT || (!(se & SE_FIRST) && idx == sidx[s - 1u])) {
+                            R.stB = ST_DEFER;
+                            R.whyB = WHY_WALK;
+                        } else {
+                            int64_t L = (int64_t)len;
+                            if (se & SE_FIRST) L -= (int64_t)R.start + R.start_add;           // REF:215-216
+                            if (se & SE_LAST) L -= R.end_rel1;                                // REF:217-218
+                            Lc = L <= 0 ? 0u : (L > (int64_t)L_CLAMP ? L_CLAMP : (uint32_t)L);
                         }
-                        nP++;
-                        if (o_end >= Bk || j + 1u >= nops) break;
-                        j++;
-                        o_start = o_end;
-                        o_end += op[j] >> 3;
-                    }
-                    Ak += Lk;
-                    if (nQ == 1u) { first_op = qlast_op; first_len = qlast_len; }
-                    if (nP == 1u && (p0 == OP_DEL || p0 == OP_INS)) {       // clear_align drops the node (REF:101-102)
-                        steps[s] = pf | SE_DROPPED;
-                        continue;
-                    }
-                    if (n_count > 3u) { defer = true; break; }              // more counting ops than the entry holds: slow path
-                    steps[s] = pf | (n_count << SE_NCNT_SHIFT);
-                    const bool first_del = nQ > 0u && first_op == OP_DEL, last_del = nQ > 0u && qlast_op == OP_DEL;
-                    if (first_del || last_del) {                            // deletion-derived IL/OL keys (REF:281-297,317-333): end of the tile
-                        const uint32_t d = atomicAdd(&s_ndel, 1u);
-                        if (d >= (uint32_t)G::DEL_CAP) { defer = true; break; }     // list full: slow path (nothing counted yet)
-                        dels[4u * d] = s;
-                        dels[4u * d + 1u] = first_len | (first_del ? 0x80000000u : 0u);
-                        dels[4u * d + 2u] = qlast_len | (last_del ? 0x80000000u : 0u);
-                        dels[4u * d + 3u] = l;
                     }
                 }
+                sinfo[s] = local;
+                local += Lc;
             }
-            if (defer) {
-                R.stB = ST_DEFER;                                           // the list of deletion keys looks at this
-                defer_line(T, t0 + R.ls - 16u, A.file_off, WHY_WALK);
+            uint32_t incl = local;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += y;
+            }
+            if (lane == 31u) s_wsum[warp] = incl;
+            __syncthreads();
+            uint32_t basev = incl - local;
+            for (uint32_t w = 0; w < warp; w++) basev += s_wsum[w];
+            for (uint32_t s = sa; s < sb; s++) {
+                const uint32_t g = sinfo[s] + basev;
+                sinfo[s] = g;
+                const uint32_t se = s < n_ent ? steps[s] : SE_INVALID;
+                if (se != SE_INVALID && (se & SE_FIRST)) recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK].base = g;
+            }
+        }
+        __syncthreads();                                                    // ---- prefix sums, record bases, duplicate / unknown ids known
+
+        // ================= walk 2: every step folds the cs ops that overlap its node =================
+        for (uint32_t s = tid; s < n_ent; s += THREADS) {
+            const uint32_t se = steps[s];
+            if (se == SE_INVALID || (se & SE_SENT)) continue;
+            LineRecF& R = recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK];
+            if (rec_status(R) != ST_FAST) continue;
+            const uint32_t Ak = sinfo[s] - R.base;                          // cs coordinate where this node starts
+            const uint32_t Lk = sinfo[s + 1u] - sinfo[s];                   // the sentinel closes the last step
+            if (Lk == 0u) {                                                 // no bases left for this node: it is not in `align`
+                steps[s] = se | SE_DROPPED;
                 continue;
             }
-            // ---- pass 2: a node's RED carries the link that LEAVES it -- to the next surviving node of a forward path (so a
-            //      node is counted when its successor is known), to the previous one of a reverse path (REF:357-363)
-            {
-                uint32_t last_k = NONE32;                                   // last surviving step
-                for (uint32_t k = ns; k-- > 0u;)
-                    if (!(steps[s0 + k] & SE_DROPPED)) { last_k = k; break; }
-                uint32_t p_idx = NONE32, p_d01 = 0;                         // previous surviving node
-                for (uint32_t k = 0; k < ns && last_k != NONE32; k++) {
-                    const uint32_t s = s0 + k, pf = steps[s];
-                    if (pf & SE_DROPPED) continue;
-                    const uint32_t idx = sidx[s], pos = pf & SE_POS_MASK;
-                    const bool first = p_idx == NONE32, last = k == last_k; // among the surviving nodes (REF:276-353: i == 0, i == last)
-                    const uint64_t stamp = (uint64_t)(base_off + (int64_t)pos + 1) << 2;
-                    if (!first) {
-                        const uint32_t from = rev ? idx : p_idx, to = rev ? p_idx : idx;
-                        const int eslot = DevSink::inline_slot(rev ? sd01[s] : p_d01, from, to);
-                        sink.bump(from, eslot);                             // REF:263-269, 357-363
-                        if (eslot < 0) {
-                            // not inline: hash-table work, collected and done at the end of the tile with every lane busy.
-                            // Stamped like the reference's insertion: when the later of the two steps is reached
-                            const uint32_t f = atomicAdd(&s_nfar, 1u);
-                            if (f < (uint32_t)G::FAR_CAP) {
-                                far[3u * f] = from;
-                                far[3u * f + 1u] = to;
-                                far[3u * f + 2u] = pos;
-                            } else {
-                                sink.edge_far(from, to, stamp);
-                            }
-                        }
-                    } else if (rev) {
-                        sink.bump(idx, -1);                                 // the first node of a reverse path leaves by no link
-                    }
-                    if (!rev && last) sink.bump(idx, -1);                   // the last node of a forward path leaves by no link
-                    const int64_t n_count = (int64_t)(pf >> SE_NCNT_SHIFT);
-                    const bool il_cond = rev ? !last : !first, ol_cond = rev ? !first : !last;
-                    sink.dense_flagged(idx, il_cond ? n_count : 0, ol_cond ? n_count : 0, stamp | 1u, (pf & SE_NEED_IL) != 0u,
-                                       (pf & SE_NEED_OL) != 0u);            // REF:298-351
-                    p_idx = idx;
-                    p_d01 = sd01[s];
+            const uint32_t n_tot = R.n_tot;
+            if (Ak >= n_tot) {                                              // cs used up before the path ends: IndexError (REF:227)
+                R.stB = ST_DEFER;
+                R.whyB = WHY_WALK;
+                continue;
+            }
+            const uint32_t* op = ops + R.op_off;
+            const uint32_t nops = R.nops;
+            if (nops == 1u) {                                               // one op (a perfect match, mostly): its piece is the whole slice
+                const uint32_t kind = op[0] & 7u;
+                steps[s] = (kind == OP_DEL || kind == OP_INS) ? (se | SE_DROPPED)                       // REF:101-102
+                                                              : (se | ((kind != OP_SUB ? 1u : 0u) << SE_NCNT_SHIFT));
+                continue;
+            }
+            const uint32_t Bk = min(Ak + Lk, n_tot);
+            // pieces of the node = ops overlapping [Ak, Bk), clipped; compact_align as a running fold (REF:63-94)
+            uint32_t j = 0, o_start = 0, o_end = op[0] >> 3;
+            while (o_end <= Ak) {                                           // ends before the node starts (j < nops: Ak < n_tot)
+                j++;
+                o_start = o_end;
+                o_end += op[j] >> 3;
+            }
+            uint32_t nP = 0, nQ = 0, p0 = 0, qlast_op = 0, qlast_len = 0, first_op = 0, first_len = 0, n_count = 0;
+            for (;;) {
+                const uint32_t kind = op[j] & 7u;
+                const uint32_t take = min(o_end, Bk) - max(o_start, Ak);
+                bool push = false;
+                uint32_t push_len = take;
+                if (nP == 0u) { p0 = kind; push = kind != OP_SUB; }
+                else if (nQ == 0u) { push = true; push_len = take + 1u; }
+                else if (kind == qlast_op || kind == OP_SUB) qlast_len += take;
+                else push = true;
+                if (push) {
+                    if (nQ == 1u) { first_op = qlast_op; first_len = qlast_len; }
+                    qlast_op = kind;
+                    qlast_len = push_len;
+                    nQ++;
+                    if (kind != OP_DEL && kind != OP_SUB) n_count++;
+                }
+                nP++;
+                if (o_end >= Bk || j + 1u >= nops) break;
+                j++;
+                o_start = o_end;
+                o_end += op[j] >> 3;
+            }
+            if (nQ == 1u) { first_op = qlast_op; first_len = qlast_len; }
+            if (nP == 1u && (p0 == OP_DEL || p0 == OP_INS)) {               // clear_align drops the node (REF:101-102)
+                steps[s] = se | SE_DROPPED;
+                continue;
+            }
+            if (n_count > 3u) {                                             // more counting ops than the entry holds: slow path
+                R.stB = ST_DEFER;
+                R.whyB = WHY_WALK;
+                continue;
+            }
+            steps[s] = se | (n_count << SE_NCNT_SHIFT);
+            const bool first_del = nQ > 0u && first_op == OP_DEL, last_del = nQ > 0u && qlast_op == OP_DEL;
+            if (first_del || last_del) {                                    // deletion-derived IL/OL keys (REF:281-297,317-333)
+                const uint32_t k = atomicAdd(&s_ndel, 1u);
+                if (k < (uint32_t)G::DEL_CAP) {
+                    dels[3u * k] = s;
+                    dels[3u * k + 1u] = first_len | (first_del ? 0x80000000u : 0u);
+                    dels[3u * k + 2u] = qlast_len | (last_del ? 0x80000000u : 0u);
+                } else {
+                    R.stB = ST_DEFER;                                       // list full: slow path (nothing counted yet)
+                    R.whyB = WHY_WALK;
                 }
             }
         }
-        __syncthreads();                                                    // ---- far-link list, deletion list complete
+        __syncthreads();                                                    // ---- every hand-over decision is made; nothing counted so far
+        for (uint32_t l = tid; l < n_own; l += THREADS) {
+            const LineRecF& R = recs[l];
+            if (rec_status(R) == ST_DEFER) defer_line(T, t0 + R.ls - 16u, A.file_off, rec_why(R));
+        }
+
+        // surviving neighbours of step s inside its record (dropped nodes are skipped)
+        auto prev_survivor = [&](uint32_t s) -> uint32_t {                  // NONE32: s is the first survivor
+            uint32_t t = s;
+            while (!(steps[t] & SE_FIRST)) {
+                t--;
+                if (!(steps[t] & SE_DROPPED)) return t;
+            }
+            return NONE32;
+        };
+        auto next_survivor = [&](uint32_t s) -> uint32_t {                  // NONE32: s is the last survivor
+            uint32_t t = s;
+            while (!(steps[t] & SE_LAST)) {
+                t++;
+                if (!(steps[t] & SE_DROPPED)) return t;
+            }
+            return NONE32;
+        };
+
+        // ================= count: one thread per surviving step =================
+        // UB steps per thread and iteration: their node-record loads (one 16-byte LDG each, L2 hits
+        // thanks to the prefetch) are all in flight before the first one is used.
+        {
+            constexpr int UB = 2;
+            for (uint32_t s00 = 0; s00 < n_ent; s00 += THREADS * UB) {
+                uint32_t se_[UB], idx_[UB];
+                DevSink::Hot hot_[UB];
+#pragma unroll
+                for (int u = 0; u < UB; u++) {
+                    const uint32_t s = s00 + THREADS * u + tid;
+                    uint32_t se = s < n_ent ? steps[s] : SE_INVALID;
+                    if (se != SE_INVALID && ((se & (SE_SENT | SE_DROPPED)) || rec_status(recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK]) != ST_FAST))
+                        se = SE_INVALID;
+                    se_[u] = se;
+                    idx_[u] = 0;
+                    hot_[u].len = 0; hot_[u].il = 0; hot_[u].ol = 0; hot_[u].d01 = 0;
+                    if (se != SE_INVALID) {
+                        idx_[u] = sidx[s];
+                        hot_[u] = sink.load_hot(idx_[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UB; u++) {
+                    const uint32_t s = s00 + THREADS * u + tid;
+                    const uint32_t se = se_[u], idx = idx_[u];
+                    if (se == SE_INVALID) continue;
+                    const bool rev = (se & SE_REV) != 0u;
+                    const uint32_t ps = prev_survivor(s), nx = next_survivor(s);
+                    const bool first = ps == NONE32, last = nx == NONE32;   // among the surviving nodes (REF:276-353: i == 0, i == last)
+                    const int64_t n_count = (int64_t)(se >> SE_NCNT_SHIFT);
+                    const bool il_cond = rev ? !last : !first, ol_cond = rev ? !first : !last;
+                    const uint64_t stamp = (uint64_t)(base_off + (int64_t)(se & SE_POS_MASK) + 1) << 2;
+                    // this thread owns the link that LEAVES its node: to the next survivor forward, to the previous one reverse
+                    const bool have_edge = rev ? !first : !last;
+                    int eslot = -1;
+                    uint32_t other = 0;
+                    if (have_edge) {
+                        other = sidx[rev ? ps : nx];
+                        eslot = DevSink::inline_slot(hot_[u].d01, idx, other);
+                    }
+                    sink.bump(idx, eslot);                                              // REF:263-269, 357-363
+                    if (have_edge && eslot < 0) {
+                        // not inline: hash-table work, collected and done below with every lane busy.  Stamped like
+                        // the reference's insertion: when the later of the two steps is reached
+                        const uint32_t ep = rev ? (se & SE_POS_MASK) : (steps[nx] & SE_POS_MASK);
+                        const uint32_t j = atomicAdd(&s_nfar, 1u);
+                        if (j < (uint32_t)G::FAR_CAP) {
+                            far[3u * j] = idx;
+                            far[3u * j + 1u] = other;
+                            far[3u * j + 2u] = ep;
+                        } else {
+                            sink.edge_far(idx, other, (uint64_t)(base_off + (int64_t)ep + 1) << 2);
+                        }
+                    }
+                    DevSink::Stamps st;
+                    st.il = hot_[u].il;
+                    st.ol = hot_[u].ol;
+                    sink.dense(idx, il_cond ? n_count : 0, ol_cond ? n_count : 0, stamp | 1u, st);   // REF:298-351
+                }
+            }
+        }
+        __syncthreads();                                                    // ---- far-link list complete
         {
             const uint32_t n_far = min(s_nfar, (uint32_t)G::FAR_CAP);
             for (uint32_t j = tid; j < n_far; j += THREADS)
@@ -896,18 +959,16 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             // deletion-derived keys: position of the deletion inside the node, IL or OL by orientation
             const uint32_t n_del = min(s_ndel, (uint32_t)G::DEL_CAP);
             for (uint32_t j = tid; j < n_del; j += THREADS) {
-                const uint32_t s = dels[4u * j], f = dels[4u * j + 1u], g = dels[4u * j + 2u];
-                const LineRecF& R = recs[dels[4u * j + 3u]];
-                if (rec_status(R) != ST_FAST) continue;                     // handed over after the key was listed
-                const uint32_t pf = steps[s], idx = sidx[s];
-                const int64_t len = (int64_t)((pf >> SE_LEN_SHIFT) & SE_LEN_MASK);
-                const bool rev = R.rev != 0;
-                bool not_first = false, not_last = false;                   // among the surviving nodes of the record
-                for (uint32_t t = R.s0; t < s; t++) not_first |= !(steps[t] & SE_DROPPED);
-                for (uint32_t t = s + 1u; t < (uint32_t)R.s0 + R.ns; t++) not_last |= !(steps[t] & SE_DROPPED);
+                const uint32_t s = dels[3u * j], f = dels[3u * j + 1u], g = dels[3u * j + 2u];
+                const uint32_t se = steps[s];
+                if (rec_status(recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK]) != ST_FAST) continue;
+                const uint32_t idx = sidx[s];
+                const int64_t len = (int64_t)sink.load_len(idx);
+                const bool rev = (se & SE_REV) != 0u;
+                const bool not_first = prev_survivor(s) != NONE32, not_last = next_survivor(s) != NONE32;
                 const bool first_del = (f >> 31) != 0u, last_del = (g >> 31) != 0u;
                 const int64_t first_len = f & 0x7FFFFFFFu, last_len = g & 0x7FFFFFFFu;     // >= 1: no op is empty here
-                const uint64_t stamp = (uint64_t)(base_off + (int64_t)(pf & SE_POS_MASK) + 1) << 2;
+                const uint64_t stamp = (uint64_t)(base_off + (int64_t)(se & SE_POS_MASK) + 1) << 2;
                 if (!rev) {
                     if (first_del && not_first) sink.sparse(idx, 0, first_len, stamp | 0u);               // REF:282-289
                     if (last_del && not_last) sink.sparse(idx, 1, len - last_len - 1, stamp | 2u);         // REF:290-297
@@ -917,11 +978,9 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 }
             }
         }
-        __syncthreads();                                                    // ---- the lists are free again
-        if (tid == 0) {
-            s_nfar = 0;
-            s_ndel = 0;
-        }
+        // no barrier here: the next tile's scan writes the masks (= the two lists, nobody reads them any more
+        // once its first barrier is passed ... which every thread reaches only after finishing the loops above)
+        __syncthreads();
     }
 
     // rejected-record count: warp reduce, one RED per warp
