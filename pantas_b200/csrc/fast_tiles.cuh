@@ -450,25 +450,20 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         }
 
         // ================= scatter: one thread per vector: whitespace / separator bit -> flat lists at its ordinal =================
-        for (uint32_t v = tid; v < 4u * nwords; v += THREADS) {
-            const uint32_t w = v >> 2, sh = 16u * (v & 3u);
-            const unsigned long long wmw = wm64[w], smw = sm64[w];
-            uint32_t w16 = (uint32_t)(wmw >> sh) & 0xFFFFu, s16 = (uint32_t)(smw >> sh) & 0xFFFFu;
-            if ((w16 | s16) == 0u) continue;
-            const unsigned long long nlw = nl64[w], gp = gpre[w], below = ~(~0ull << sh);
-            const uint32_t n16 = (uint32_t)(nlw >> sh) & 0xFFFFu;
-            uint32_t ows = ((uint32_t)gp & 0xFFFFu) + (uint32_t)__popcll(wmw & below);
-            uint32_t osep = ((uint32_t)(gp >> 16) & 0xFFFFu) + (uint32_t)__popcll(smw & below);
-            uint32_t rec = ((uint32_t)(gp >> 32) & 0xFFFFu) + (uint32_t)__popcll(nlw & below);   // records started before the vector
-            while (s16) {
-                const uint32_t b = (uint32_t)(__ffs((int)s16) - 1);
-                s16 &= s16 - 1u;
-                const uint32_t k = rec + (uint32_t)__popc(n16 & ((1u << b) - 1u));      // records started before the byte
-                steps[osep++] = k == 0u ? SE_INVALID : ((16u * v + b) | ((k - 1u) << SE_SLOT_SHIFT));   // k == 0: tail of a record of the previous tile
-            }
-            while (w16) {
-                const uint32_t b = (uint32_t)(__ffs((int)w16) - 1);
-                w16 &= w16 - 1u;
+        // The first two whitespace bytes and the first two separators of a vector are handled without a loop (all lanes in
+        // step); vectors with more (the dense column zones, short ids) go to a per-warp list and are finished afterwards,
+        // dense vectors next to dense vectors.  The list borrows the (not yet used) sidx array.
+        {
+            constexpr uint32_t DL_CAP = (uint32_t)(4 * G::STEP_CAP) / (16u * NWARPS);
+            uint32_t* const dl = sidx + warp * (4u * DL_CAP);
+            uint32_t ndl = 0;
+            // separator at bit b of vector v (rec0 records started before the vector, n16 its newline bits)
+            auto put_sep = [&](uint32_t v, uint32_t b, uint32_t rec0, uint32_t n16, uint32_t osep) {
+                const uint32_t k = rec0 + (uint32_t)__popc(n16 & ((1u << b) - 1u));     // records started before the byte
+                steps[osep] = k == 0u ? SE_INVALID : ((16u * v + b) | ((k - 1u) << SE_SLOT_SHIFT));   // k == 0: tail of a record of the previous tile
+            };
+            // whitespace at bit b: a newline opens record `rec`
+            auto put_ws = [&](uint32_t v, uint32_t b, uint32_t n16, uint32_t& ows, uint32_t& rec) {
                 const uint32_t pos = 16u * v + b;
                 wslist[ows++] = (uint16_t)pos;
                 if ((n16 >> b) & 1u) {
@@ -476,6 +471,73 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                     recws[rec] = (uint16_t)ows;
                     rec++;
                 }
+            };
+            auto finish = [&](uint32_t v, uint32_t w16, uint32_t s16, uint32_t n16, uint32_t ows, uint32_t osep, uint32_t rec0) {
+                while (s16) {
+                    const uint32_t b = (uint32_t)(__ffs((int)s16) - 1);
+                    s16 &= s16 - 1u;
+                    put_sep(v, b, rec0, n16, osep++);
+                }
+                if (w16) {
+                    uint32_t rec = rec0 + (uint32_t)__popc(n16 & ((w16 & (0u - w16)) - 1u));     // newlines before the first byte left
+                    while (w16) {
+                        const uint32_t b = (uint32_t)(__ffs((int)w16) - 1);
+                        w16 &= w16 - 1u;
+                        put_ws(v, b, n16, ows, rec);
+                    }
+                }
+            };
+            for (uint32_t vb = 32u * warp; vb < 4u * nwords; vb += THREADS) {
+                const uint32_t v = vb + lane;
+                uint32_t w16 = 0, s16 = 0, n16 = 0, ows = 0, osep = 0, rec0 = 0;
+                if (v < 4u * nwords) {
+                    const uint32_t w = v >> 2, sh = 16u * (v & 3u);
+                    const unsigned long long wmw = wm64[w], smw = sm64[w];
+                    w16 = (uint32_t)(wmw >> sh) & 0xFFFFu;
+                    s16 = (uint32_t)(smw >> sh) & 0xFFFFu;
+                    if ((w16 | s16) != 0u) {
+                        const unsigned long long nlw = nl64[w], gp = gpre[w], below = ~(~0ull << sh);
+                        n16 = (uint32_t)(nlw >> sh) & 0xFFFFu;
+                        ows = ((uint32_t)gp & 0xFFFFu) + (uint32_t)__popcll(wmw & below);
+                        osep = ((uint32_t)(gp >> 16) & 0xFFFFu) + (uint32_t)__popcll(smw & below);
+                        rec0 = ((uint32_t)(gp >> 32) & 0xFFFFu) + (uint32_t)__popcll(nlw & below);   // records started before the vector
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 2; r++)
+                    if (s16) {
+                        const uint32_t b = (uint32_t)(__ffs((int)s16) - 1);
+                        s16 &= s16 - 1u;
+                        put_sep(v, b, rec0, n16, osep++);
+                    }
+                uint32_t rec = rec0;
+#pragma unroll
+                for (int r = 0; r < 2; r++)
+                    if (w16) {
+                        const uint32_t b = (uint32_t)(__ffs((int)w16) - 1);
+                        w16 &= w16 - 1u;
+                        put_ws(v, b, n16, ows, rec);
+                    }
+                const bool left = (w16 | s16) != 0u;
+                const uint32_t bm = __ballot_sync(0xffffffffu, left);
+                if (left) {
+                    const uint32_t slot = ndl + (uint32_t)__popc(bm & ((1u << lane) - 1u));
+                    if (slot < DL_CAP) {
+                        dl[4u * slot] = w16 | (s16 << 16);
+                        dl[4u * slot + 1u] = n16 | (v << 16);
+                        dl[4u * slot + 2u] = ows | (osep << 16);
+                        dl[4u * slot + 3u] = rec0;
+                    } else {
+                        finish(v, w16, s16, n16, ows, osep, rec0);          // list full: finish it here
+                    }
+                }
+                ndl += (uint32_t)__popc(bm);
+            }
+            __syncwarp();
+            ndl = min(ndl, DL_CAP);
+            for (uint32_t i = lane; i < ndl; i += 32u) {
+                const uint32_t d0 = dl[4u * i], d1 = dl[4u * i + 1u], d2 = dl[4u * i + 2u], d3 = dl[4u * i + 3u];
+                finish(d1 >> 16, d0 & 0xFFFFu, d0 >> 16, d1 & 0xFFFFu, d2 & 0xFFFFu, d2 >> 16, d3);
             }
         }
         __syncthreads();                                                    // ---- whitespace list, raw step list, record starts complete
