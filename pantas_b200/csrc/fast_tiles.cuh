@@ -548,8 +548,18 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         if (tid == 0) { my_lines += n_own; my_tiles++; }
 
         // ================= fields: A (tags), T0 (shape, filters, path shape), T1 (coordinates) =================
-        for (uint32_t item = tid; item < 3u * n_own; item += THREADS) {
-            if (item < n_own) {
+        // Whole warps per role (a warp that mixes roles runs them one after the other), and the records of a role dealt
+        // round-robin over its warps: the phase is as long as ONE role over n_own / warps records.
+        constexpr uint32_t WARPS_A = NWARPS >= 4u ? NWARPS / 2u : 1u, WARPS_T = NWARPS >= 4u ? NWARPS / 4u : 1u;
+        constexpr uint32_t ROLE_PASSES = NWARPS >= 4u ? 1u : (NWARPS == 2u ? 2u : 3u);   // few warps: a warp takes several roles in turn
+        for (uint32_t rp = 0; rp < ROLE_PASSES; rp++) {
+        const uint32_t vwarp = NWARPS >= 4u ? warp : (NWARPS == 2u ? (rp == 0u ? (warp == 0u ? 0u : 1u) : (warp == 0u ? 2u : 3u)) : rp);
+        // virtual role warps: [0, WARPS_A) role A, then WARPS_T of T0, then WARPS_T of T1
+        const uint32_t role = vwarp < WARPS_A ? 0u : (vwarp < WARPS_A + WARPS_T ? 1u : (vwarp < WARPS_A + 2u * WARPS_T ? 2u : 3u));
+        const uint32_t rwarps = role == 0u ? WARPS_A : WARPS_T;
+        const uint32_t rw0 = role == 0u ? vwarp : (role == 1u ? vwarp - WARPS_A : vwarp - WARPS_A - WARPS_T);
+        for (uint32_t item = rw0 + rwarps * lane; item < n_own && role < 3u; item += 32u * rwarps) {
+            if (role == 0u) {
                 // ---------------- role A: tags -> dv filter, cs ops
                 const uint32_t l = item;
                 LineRecF& R = recs[l];
@@ -670,9 +680,9 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 }
                 R.stA = (uint8_t)(slow ? ST_DEFER : (done ? ST_DONE : ST_FAST));
                 R.whyA = (uint8_t)why;
-            } else if (item < 2u * n_own) {
+            } else if (role == 1u) {
                 // ---------------- role T0: column shape, MAPQ and '*' filters, path column shape, sentinel
-                const uint32_t l = item - n_own;
+                const uint32_t l = item;
                 LineRecF& R = recs[l];
                 const uint32_t rw = recws[l];
                 const uint16_t* const e = wslist + rw - 1u;               // e[c]: end of column c (e[0]: the newline before the record)
@@ -725,7 +735,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 R.whyB = (uint8_t)why;
             } else {
                 // ---------------- role T1: the three coordinates (REF:151-153)
-                const uint32_t l = item - 2u * n_own;
+                const uint32_t l = item;
                 LineRecF& R = recs[l];
                 const uint32_t rw = recws[l];
                 const uint16_t* const e = wslist + rw - 1u;               // e[c]: end of column c (e[0]: the newline before the record)
@@ -744,6 +754,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 }
                 R.stC = (uint8_t)st;
             }
+        }
         }
         __syncthreads();                                                    // ---- records, ops complete
 
