@@ -1,36 +1,26 @@
-// fast_tiles.cuh -- the fast path of the augment kernel (included by aug_kernels.cuh after tables.cuh,
-// the TMA helpers, ChunkArgs and defer_line()).
+// fast_tiles.cuh -- the fast path of the augment kernel (included by pantas_aug.cu inside its
+// anonymous namespace, after tables.cuh, the TMA helpers, ChunkArgs and defer_line()).
 //
 // Reference loop body: /root/reference/scripts/alignments_augmentation_from_gaf.py:142-363 (REF:n).
 //
 // A persistent CTA takes tiles of the GAF chunk (TILE bytes + OV bytes of look-ahead, one 1-D TMA
-// bulk copy, UBLKCP) and runs data-parallel phases over the tile in shared memory.  Nothing in the
-// first half walks a record serially: every phase is "one thread per <small thing>", and where a
-// thing sits inside its record comes from prefix counts, not from a per-record loop.
+// bulk copy, UBLKCP) and runs data-parallel phases over the tile in shared memory:
 //
-//   scan     one thread per 16-byte vector (LDS.128, conflict free), branch-free SWAR: 16-bit pieces of
-//            three masks -- whitespace (<= 0x20), newline, path separator ('>' '<').  Lone '\r' and
-//            non-ASCII bytes are (fatal) errors; any whitespace other than tab / newline raises a
-//            tile flag that switches on the per-column tab check below.
-//   prefix   per 64-byte mask word: exclusive counts of whitespace, separators and record starts
-//            before the word, and the start of the record that is open there (block-wide scan).
-//   scatter  one thread per 16-byte vector (32-bit arithmetic on its 16-bit mask pieces): every whitespace
-//            position goes to a flat list at its ordinal (prefix count), every separator to the step list
-//            at its ordinal, tagged with its record; newlines open the next record (its first byte, its
-//            first whitespace ordinal).  Column c of record r ends at wslist[recws[r] + c - 1]: no table
-//            of column boundaries is ever built, nothing walks a record.
-//   fields   small independent items, one thread each:
-//              A   tags of a record: first cs token, first dv:f: token (REF:154-160,172-180), the dv
-//                  filter, the cs string parsed into the tile's op pool (REF:10-50, cigar_clipping)
-//              T0  column shape, MAPQ and '*' filters (REF:143-148), path column shape
-//              T1  the three coordinates (REF:151-153)
+//   scan     one thread per 64 bytes (4 x LDS.128), branch-free SWAR: a 64-bit whitespace mask and a
+//            64-bit path-separator ('>' '<') mask per group; record starts ('\n') go to a list;
+//            lone '\r' and non-ASCII bytes are (fatal) errors.
+//   records  TWO threads per record, both walking the whitespace mask from the record start:
+//              B  the 12 column boundaries (single tabs, no empty column), MAPQ and '*' filters
+//                 (REF:143-148), the three coordinates (REF:151-153), then the separator mask of
+//                 the path column -> one entry per path step (+ a sentinel) in the tile's step list;
+//              A  the tags: first cs token, first dv:f: token (REF:154-160,172-180), the dv filter,
+//                 and the cs string parsed into the tile's op pool (REF:10-50, incl. cigar_clipping).
 //            Anything unusual -- other whitespace in the columns, integers that are not plain
 //            digits, tags that could confuse the reference's regexes, '~' or zero-length or oddly
 //            spelled cs ops -- hands the record to the exact per-record path (line_core.cuh via
 //            augment_deferred_kernel).
-//   ids      one thread per separator of the step list: inside its record's path column?  first / last
-//            step?  then the SWAR decimal parse of the id out of shared memory, node index, node length
-//            (the load also pulls the node's sector into L2).  After this phase the bytes are dead and the
+//   ids      one thread per path step: SWAR decimal parse of the id out of shared memory, node
+//            index, L2 prefetch of the node record.  After this phase the bytes are dead and the
 //            next tile's TMA copy is issued: it overlaps the table traffic of the remaining phases.
 //   walk     one thread per path step.  The reference's merge walk (REF:205-255) gives node k the
 //            ops that overlap [A_k, A_k + L_k) in cs coordinates, where A is the prefix sum of the
@@ -54,24 +44,25 @@ constexpr int MAX_OPS = 48;                   // more cs ops: slow path
 constexpr uint32_t L_CLAMP = 1u << 23;        // step lengths are clamped here (> any cs length the fast path takes)
 constexpr int32_t MAX_NTOT = 1 << 22;
 
-enum : uint8_t { ST_FAST = 0, ST_DONE = 1, ST_DEFER = 2 };      // per role
+enum : uint8_t { ST_FAST = 0, ST_DONE = 1, ST_DEFER = 2 };      // per role; a record's status is the maximum
 enum : uint32_t { OP_MATCH = 0, OP_SUB = 1, OP_DEL = 2, OP_INS = 3, OP_EQ = 4 };   // ':' '*' '-' '+' '='  (op = kind | len << 3)
 
-struct __align__(8) LineRecF {
-    int32_t start;        // int(tokens[7])                                    (role T1)
-    int32_t end_rel1;     // int(tokens[6]) - int(tokens[8]) - 1               (role T1)
+struct __align__(4) LineRecF {
+    int32_t start;        // int(tokens[7])                                    (role B)
+    int32_t end_rel1;     // int(tokens[6]) - int(tokens[8]) - 1               (role B)
     int32_t start_add;    // cigar_clipping: start_pos += len of a leading '+' (role A, REF:46-47)
     uint32_t n_tot;       // sum of the cs op lengths                          (role A)
     uint32_t base;        // step-length prefix at the record's first step     (walk)
-    uint16_t ls;          // buffer position of the record's first byte        (role T0)
+    uint16_t s0;          // first entry of the record in the step list        (role B)
+    uint16_t nsteps;      //                                                   (role B)
+    uint16_t ls;          // buffer position of the record's first byte        (role B)
     uint16_t op_off;      // first op of the record in the op pool             (role A)
     uint8_t nops;         //                                                   (role A)
-    uint8_t stA, stB, stC;   // ST_* per role; walk raises stB
-    uint16_t a5, b5;      // the path column [a5, b5) (0xFFFF, 0xFFFF: the record has none)   (role T0)
-    uint8_t whyA, whyB;   // WHY_* when the role says ST_DEFER (T1: always WHY_INTS)
-    uint8_t pad[6];
+    uint8_t stA, stB;     // ST_* per role; walk raises stB
+    uint8_t whyA, whyB;   // WHY_* when the role says ST_DEFER
+    uint8_t pad[3];
 };
-static_assert(sizeof(LineRecF) == 40, "record layout");
+static_assert(sizeof(LineRecF) == 36 && offsetof(LineRecF, nops) == 28, "rec_status reads nops / stA / stB as one word");
 
 // step list entry
 constexpr uint32_t SE_POS_MASK = 0xFFFFu;     // bits 0..15  buffer position of the separator (sentinel: end of the path column)
@@ -81,10 +72,6 @@ constexpr uint32_t SE_FIRST = 1u << 25, SE_LAST = 1u << 26, SE_REV = 1u << 27, S
 constexpr int SE_NCNT_SHIFT = 30;             // bits 30..31 counting ops of the compacted slice (0..3)
 constexpr uint32_t SE_INVALID = 0xFFFFFFFFu;
 
-// per mask word: counts before the word, packed
-constexpr unsigned long long PRE_SUMS = 0xFFFFFFFFFFFFull;    // bits 0..15 whitespace, 16..31 separators, 32..47 record starts
-constexpr int PRE_LS_SHIFT = 48;                              // bits 48..63 first byte of the record open at the word (0: none)
-
 template <int TILE_, int OV_, int THREADS_>
 struct Geo {
     static constexpr int TILE = TILE_;
@@ -92,39 +79,30 @@ struct Geo {
     static constexpr int THREADS = THREADS_;
     static constexpr int BUF = 16 + TILE + OV + 16;               // [pre 16][tile][look-ahead][pad 16]
     static constexpr int NV = ((16 + TILE + OV) / 16 + 3) & ~3;   // 16-byte vectors, padded to whole 64-bit mask words
-    static constexpr int NW = NV / 4;                             // 64-bit mask words
-    static constexpr int LINE_CAP = ((TILE + OV + 111) / 112 + 7) & ~7;   // typical: one record per 300 bytes
-    static constexpr int STEP_CAP = (((TILE + OV) / 12) + 63) & ~63;  // separators; typical: 14 steps per 300 bytes
-    static constexpr int WS_CAP = (((TILE + OV) / 8) + 63) & ~63;     // whitespace bytes; typical: 17 per 300 bytes
+    static constexpr int LINE_CAP = ((TILE + 111) / 112 + 7) & ~7;   // typical: one record per 300 bytes
+    static constexpr int STEP_CAP = (((TILE + OV) / 12 + LINE_CAP) + 63) & ~63;   // typical: 14 steps per 300 bytes, + sentinels
     static constexpr int OPS_CAP = (LINE_CAP * 4 + 63) & ~63;
     static constexpr int FAR_CAP = (STEP_CAP / 8 + 31) & ~31;     // links that are not inline: typically 1-2 per record
     static constexpr int DEL_CAP = (LINE_CAP / 2 + 31) & ~31;     // steps with deletion-derived keys
-    // region X, first life (scan .. fields): three masks, the per-word prefix, whitespace list, record starts
+    static constexpr int MASK_BYTES = 4 * NV;                     // whitespace + separator masks; dead after `records`:
+    static constexpr int LIST_BYTES = 12 * FAR_CAP + 12 * DEL_CAP;    // ... the two end-of-tile lists reuse the space
     static constexpr int OFF_WM = (BUF + 127) & ~127;
-    static constexpr int OFF_NL = OFF_WM + 8 * NW;
-    static constexpr int OFF_SM = OFF_NL + 8 * NW;
-    static constexpr int OFF_PRE = OFF_SM + 8 * NW;
-    static constexpr int OFF_WSL = OFF_PRE + 8 * (NW + 1);        // + one word of totals (a position may be the end of the data)
-    static constexpr int OFF_LINES = OFF_WSL + 2 * WS_CAP;
-    static constexpr int OFF_RECWS = OFF_LINES + 2 * LINE_CAP;
-    static constexpr int X_END1 = OFF_RECWS + 2 * LINE_CAP;
-    // region X, second life (walk .. count): step-length prefix and the two end-of-tile lists
-    static constexpr int OFF_SINFO = OFF_WM;
-    static constexpr int OFF_FAR = OFF_SINFO + 4 * (STEP_CAP + 4);
-    static constexpr int OFF_DEL = OFF_FAR + 12 * FAR_CAP;
-    static constexpr int X_END2 = OFF_DEL + 12 * DEL_CAP;
-    static constexpr int OFF_STEP = ((X_END1 > X_END2 ? X_END1 : X_END2) + 15) & ~15;
+    static constexpr int OFF_SM = OFF_WM + 2 * NV;
+    static constexpr int OFF_FAR = OFF_WM;
+    static constexpr int OFF_DEL = OFF_WM + 12 * FAR_CAP;
+    static constexpr int OFF_STEP = (OFF_WM + (MASK_BYTES > LIST_BYTES ? MASK_BYTES : LIST_BYTES) + 15) & ~15;
     static constexpr int OFF_SIDX = OFF_STEP + 4 * STEP_CAP;
-    static constexpr int OFF_OPS = OFF_SIDX + 4 * STEP_CAP;
-    static constexpr int OFF_REC = (OFF_OPS + 4 * OPS_CAP + 7) & ~7;
+    static constexpr int OFF_SINFO = OFF_SIDX + 4 * STEP_CAP;
+    static constexpr int OFF_OPS = OFF_SINFO + 4 * (STEP_CAP + 4);
+    static constexpr int OFF_LINES = OFF_OPS + 4 * OPS_CAP;
+    static constexpr int OFF_REC = (OFF_LINES + 2 * LINE_CAP + 7) & ~7;
     static constexpr int SMEM_BYTES = (OFF_REC + (int)sizeof(LineRecF) * LINE_CAP + 127) & ~127;
     static constexpr int FIT = (227 * 1024) / (SMEM_BYTES + 1024);                    // CTAs per SM by shared memory
     static constexpr int REG = 1024 / THREADS < 1 ? 1 : 1024 / THREADS;               // ... leaving >= 64 registers per thread
     static constexpr int MIN_CTAS = FIT < 1 ? 1 : (FIT < REG ? FIT : REG);
-    static_assert(BUF < 65536, "step entries and prefix words hold 16-bit positions");
+    static_assert(BUF <= 65536, "step entries hold 16-bit positions");
     static_assert(LINE_CAP <= 512, "step entries hold 9-bit record slots");
     static_assert(STEP_CAP < 65536 && OPS_CAP < 65536, "records hold 16-bit list offsets");
-    static_assert(OFF_SINFO + 4 * (STEP_CAP + 4) <= OFF_WSL, "ids writes node lengths while the whitespace list is still read");
 };
 
 // 0x80 flags at bits 7/15/23/31 -> 4-bit mask in the top nibble (no carries: the partial products
@@ -237,17 +215,10 @@ __device__ __forceinline__ unsigned long long sep_word(const unsigned long long*
 
 __device__ __forceinline__ bool is_lower(uint32_t c) { return c - 'a' <= 25u; }
 
-__device__ __forceinline__ uint32_t flag_nl(uint32_t x) { return flag_eq7(x ^ 0x0A0A0A0Au); }
-
-// status of a record: T0's verdict (shape, MAPQ, '*') comes first -- the reference `continue`s there
-// before it looks at anything else (REF:143-148); otherwise the worse of the other two roles
+// status of a record = the worse of its two roles
 __device__ __forceinline__ uint32_t rec_status(const LineRecF& R) {
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(&R.nops);        // nops | stA << 8 | stB << 16 | stC << 24: one LDS
-    const uint32_t a = (w >> 8) & 0xFFu, b = (w >> 16) & 0xFFu, c = w >> 24;
-    return b != ST_FAST ? b : max(a, c);
-}
-__device__ __forceinline__ int rec_why(const LineRecF& R) {
-    return R.stB == ST_DEFER ? (int)R.whyB : (R.stC == ST_DEFER ? (int)WHY_INTS : (int)R.whyA);
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(&R.nops);        // nops | stA << 8 | stB << 16 | whyA << 24: one LDS
+    return max((w >> 8) & 0xFFu, (w >> 16) & 0xFFu);
 }
 
 template <class G>
@@ -256,34 +227,29 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
     constexpr uint32_t NWARPS = THREADS / 32;
     PT_DYNAMIC_SMEM(smem);
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t s_nops, s_nfar, s_ndel, s_oth;
-    __shared__ unsigned long long s_wsum64[NWARPS];
-    __shared__ uint32_t s_wmax[NWARPS];
+    __shared__ uint32_t s_nlines, s_nsteps, s_nops, s_nfar, s_ndel;
     __shared__ uint32_t s_wsum[NWARPS];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint8_t* const buf = smem;
     unsigned long long* const wm64 = reinterpret_cast<unsigned long long*>(smem + G::OFF_WM);
-    unsigned long long* const nl64 = reinterpret_cast<unsigned long long*>(smem + G::OFF_NL);
     unsigned long long* const sm64 = reinterpret_cast<unsigned long long*>(smem + G::OFF_SM);
-    unsigned long long* const gpre = reinterpret_cast<unsigned long long*>(smem + G::OFF_PRE);
-    uint16_t* const wslist = reinterpret_cast<uint16_t*>(smem + G::OFF_WSL);   // positions of the whitespace bytes, in order
-    uint16_t* const lines = reinterpret_cast<uint16_t*>(smem + G::OFF_LINES);  // first byte of record r
-    uint16_t* const recws = reinterpret_cast<uint16_t*>(smem + G::OFF_RECWS);  // whitespace ordinal at the start of record r
-    uint32_t* const sinfo = reinterpret_cast<uint32_t*>(smem + G::OFF_SINFO);  // step-length prefix           (second life of region X)
-    uint32_t* const far = reinterpret_cast<uint32_t*>(smem + G::OFF_FAR);      // {from, to, separator position}
-    uint32_t* const dels = reinterpret_cast<uint32_t*>(smem + G::OFF_DEL);     // {step, first del, last del}
+    uint32_t* const far = reinterpret_cast<uint32_t*>(smem + G::OFF_FAR);      // {from, to, separator position} (reuses the masks)
+    uint32_t* const dels = reinterpret_cast<uint32_t*>(smem + G::OFF_DEL);     // {step, first del, last del}     (reuses the masks)
     uint32_t* const steps = reinterpret_cast<uint32_t*>(smem + G::OFF_STEP);
     uint32_t* const sidx = reinterpret_cast<uint32_t*>(smem + G::OFF_SIDX);
+    uint32_t* const sinfo = reinterpret_cast<uint32_t*>(smem + G::OFF_SINFO);  // step-length prefix
     uint32_t* const ops = reinterpret_cast<uint32_t*>(smem + G::OFF_OPS);
+    uint16_t* const lines = reinterpret_cast<uint16_t*>(smem + G::OFF_LINES);
     LineRecF* const recs = reinterpret_cast<LineRecF*>(smem + G::OFF_REC);
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
+        s_nlines = 0;
+        s_nsteps = 0;
         s_nops = 0;
         s_nfar = 0;
         s_ndel = 0;
-        s_oth = 0;
     }
     __syncthreads();
 
@@ -301,21 +267,6 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         mbar_expect_tx(&mbar, bytes);
         tma_load_1d(buf + (tile ? 0u : 16u), A.gaf + lo, bytes, &mbar);
     };
-    // counts strictly below buffer position pos (< 64 * nwords): whitespace | separators << 16 | record starts << 32
-    auto pre_at = [&](uint32_t pos) -> unsigned long long {
-        const uint32_t w = pos >> 6;
-        const unsigned long long below = ~(~0ull << (pos & 63u));
-        return (gpre[w] & PRE_SUMS) + ((unsigned long long)__popcll(wm64[w] & below) | ((unsigned long long)__popcll(sm64[w] & below) << 16) |
-                                       ((unsigned long long)__popcll(nl64[w] & below) << 32));
-    };
-    auto ws_at = [&](uint32_t pos) -> uint32_t {
-        const uint32_t w = pos >> 6;
-        return ((uint32_t)gpre[w] & 0xFFFFu) + (uint32_t)__popcll(wm64[w] & ~(~0ull << (pos & 63u)));
-    };
-    auto sep_at = [&](uint32_t pos) -> uint32_t {
-        const uint32_t w = pos >> 6;
-        return ((uint32_t)(gpre[w] >> 16) & 0xFFFFu) + (uint32_t)__popcll(sm64[w] & ~(~0ull << (pos & 63u)));
-    };
 
     uint32_t tile = blockIdx.x;
     if (tile < A.n_tiles && tid == 0) issue_load(tile);
@@ -331,248 +282,197 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         mbar_wait(&mbar, parity);
         parity ^= 1;
 
-        // ================= scan: one thread per 16-byte vector -> 16-bit pieces of the three masks =================
-        {
-            uint16_t* const wm16 = reinterpret_cast<uint16_t*>(wm64);
-            uint16_t* const nl16 = reinterpret_cast<uint16_t*>(nl64);
-            uint16_t* const sm16 = reinterpret_cast<uint16_t*>(sm64);
-            for (uint32_t v = tid; v < 4u * nwords; v += THREADS) {
-                const uint4 q = *reinterpret_cast<const uint4*>(buf + 16u * v);
-                const uint32_t w0 = flag_ws(q.x), w1 = flag_ws(q.y), w2 = flag_ws(q.z), w3 = flag_ws(q.w);
-                const uint32_t n0 = flag_nl(q.x), n1 = flag_nl(q.y), n2 = flag_nl(q.z), n3 = flag_nl(q.w);
-                // whitespace that is neither tab nor newline ('\r', ' ', ...): rare, see below
-                const uint32_t o0 = w0 ^ (flag_tab(q.x) | n0), o1 = w1 ^ (flag_tab(q.y) | n1), o2 = w2 ^ (flag_tab(q.z) | n2),
-                               o3 = w3 ^ (flag_tab(q.w) | n3);
-                uint32_t w16 = mask16(w0, w1, w2, w3), n16 = mask16(n0, n1, n2, n3);
-                uint32_t s16 = mask16(flag_sep(q.x), flag_sep(q.y), flag_sep(q.z), flag_sep(q.w));
-                uint32_t oth = o0 | o1 | o2 | o3, hib = (q.x | q.y | q.z | q.w) & 0x80808080u;
-                const uint32_t room = lim > 16u * v ? lim - 16u * v : 0u;   // loaded bytes in this vector
-                const uint32_t keep = room >= 16u ? 0xFFFFu : ((1u << room) - 1u);
-                if (v == 0u) {
-                    // positions 0..15 are before the tile: all that matters is whether a record starts at 16
-                    // (the chunk starts at a record start; otherwise: is the byte before the tile a newline?)
-                    n16 = tile == 0u ? 0x8000u : (n16 & 0x8000u);
-                    w16 = n16;
-                    s16 = 0u;
-                    oth = 0u;
-                    hib = 0u;
-                } else {
-                    w16 &= keep;
-                    n16 &= keep;
-                    s16 &= keep;
-                }
-                wm16[v] = (uint16_t)w16;
-                nl16[v] = (uint16_t)n16;
-                sm16[v] = (uint16_t)s16;
-                if (oth != 0u) {
-                    uint32_t om = mask16(o0, o1, o2, o3) & keep;
-                    if (om) s_oth = 1u;                                     // fields: check every column boundary byte
-                    while (om) {
-                        const uint32_t p = 16u * v + (uint32_t)(__ffs((int)om) - 1);
-                        om &= om - 1u;
-                        if (buf[p] == '\r' && p < own_end) {
-                            const uint64_t abs_pos = t0 + p - 16u;
-                            if (abs_pos + 1 < A.nbytes && buf[p + 1] != '\n') report_error(T, pt::PT_U_BARE_CR, base_off + (int64_t)p);
+        // ================= scan: whitespace / separator masks, record starts =================
+        for (uint32_t g = tid; g < nwords; g += THREADS) {
+            unsigned long long wm = 0, sm = 0;
+            uint32_t oth = 0, hib = 0;
+            uint4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) q[u] = *reinterpret_cast<const uint4*>(buf + 64u * g + 16u * u);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t w0 = flag_ws(q[u].x), w1 = flag_ws(q[u].y), w2 = flag_ws(q[u].z), w3 = flag_ws(q[u].w);
+                wm |= (unsigned long long)mask16(w0, w1, w2, w3) << (16 * u);
+                sm |= (unsigned long long)mask16(flag_sep(q[u].x), flag_sep(q[u].y), flag_sep(q[u].z), flag_sep(q[u].w)) << (16 * u);
+                // whitespace that is not a tab: '\n' (record start), '\r' (lone: error); the rest only matters to the walkers
+                oth |= (w0 & ~flag_tab(q[u].x)) | (w1 & ~flag_tab(q[u].y)) | (w2 & ~flag_tab(q[u].z)) | (w3 & ~flag_tab(q[u].w));
+                hib |= q[u].x | q[u].y | q[u].z | q[u].w;
+            }
+            const uint32_t room = lim > 64u * g ? lim - 64u * g : 0u;       // loaded bytes in this group
+            unsigned long long keep = room < 64u ? ~(~0ull << room) : ~0ull;
+            if (g == 0) keep &= ~0xFFFFull;                                 // positions 0..15 are before the tile
+            wm &= keep;
+            sm &= keep;
+            wm64[g] = wm;
+            sm64[g] = sm;
+            if (g == 0 && tile == 0 && owned > 0u) {                        // the chunk starts at a record start
+                const uint32_t j = atomicAdd(&s_nlines, 1u);
+                if (j < (uint32_t)G::LINE_CAP) lines[j] = 16;
+            }
+            if (oth != 0u) {
+                unsigned long long om = 0;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    om |= (unsigned long long)mask16(flag_ws(q[u].x) & ~flag_tab(q[u].x), flag_ws(q[u].y) & ~flag_tab(q[u].y),
+                                                     flag_ws(q[u].z) & ~flag_tab(q[u].z), flag_ws(q[u].w) & ~flag_tab(q[u].w)) << (16 * u);
+                if (g == 0 && tile != 0) keep |= 0x8000ull;                 // is the byte before the tile a newline?
+                om &= keep;
+                while (om) {
+                    const uint32_t p = 64u * g + (uint32_t)(__ffsll((long long)om) - 1);
+                    om &= om - 1ull;
+                    const uint32_t c = buf[p];
+                    if (c == '\n') {
+                        if (p + 1u < own_end) {
+                            const uint32_t j = atomicAdd(&s_nlines, 1u);
+                            if (j < (uint32_t)G::LINE_CAP) lines[j] = (uint16_t)(p + 1u);
                         }
+                    } else if (c == '\r' && p >= 16u && p < own_end) {
+                        const uint64_t abs_pos = t0 + p - 16u;
+                        if (abs_pos + 1 < A.nbytes && buf[p + 1] != '\n')
+                            report_error(T, pt::PT_U_BARE_CR, base_off + (int64_t)p);
                     }
                 }
-                if (hib != 0u) {                                            // non-ASCII byte: not modelled
-                    for (uint32_t p = 16u * v; p < min(16u * v + 16u, min(lim, own_end)); p++)
-                        if (buf[p] >= 0x80u) { report_error(T, pt::PT_U_NON_ASCII, base_off + (int64_t)p); break; }
-                }
+            }
+            if ((hib & 0x80808080u) != 0u) {                                // non-ASCII byte: not modelled
+                for (uint32_t p = max(64u * g, 16u); p < min(64u * g + 64u, min(lim, own_end)); p++)
+                    if (buf[p] >= 0x80u) { report_error(T, pt::PT_U_NON_ASCII, base_off + (int64_t)p); break; }
             }
         }
-        __syncthreads();                                                    // ---- masks complete
+        __syncthreads();                                                    // ---- masks + record list complete
+        const uint32_t n_lines_all = s_nlines;
+        if (tid == 0) { my_lines += n_lines_all; my_tiles++; }
 
-        // ================= prefix: counts before every mask word, start of the record open there =================
-        const uint32_t per_w = (nwords + THREADS - 1u) / THREADS;          // consecutive words per thread
-        const uint32_t wa = min(tid * per_w, nwords), wb = min(wa + per_w, nwords);
-        unsigned long long tot = 0;
-        {
-            unsigned long long local = 0;
-            uint32_t lmax = 0;
-            for (uint32_t w = wa; w < wb; w++) {
-                const unsigned long long nlv = nl64[w];
-                gpre[w] = local | ((unsigned long long)lmax << PRE_LS_SHIFT);
-                local += (unsigned long long)__popcll(wm64[w]) | ((unsigned long long)__popcll(sm64[w]) << 16) |
-                         ((unsigned long long)__popcll(nlv) << 32);
-                if (nlv) lmax = 64u * w + 64u - (uint32_t)__clzll((long long)nlv);      // last newline + 1
+        if (n_lines_all > (uint32_t)G::LINE_CAP) {
+            // more records than the list holds (pathological input): all of them take the slow path
+            for (uint32_t p = 15u + tid; p + 1u < own_end; p += THREADS) {
+                const bool nl = p == 15u ? (tile == 0 || buf[p] == '\n') : buf[p] == '\n';
+                if (nl) defer_line(T, t0 + p + 1u - 16u, A.file_off, WHY_LINES_FULL);
             }
-            unsigned long long incl = local;
-            uint32_t imax = lmax;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o);
-                const uint32_t m = __shfl_up_sync(0xffffffffu, imax, o);
-                if (lane >= (uint32_t)o) { incl += y; imax = max(imax, m); }
-            }
-            if (lane == 31u) { s_wsum64[warp] = incl; s_wmax[warp] = imax; }
-            unsigned long long basev = incl - local;
-            uint32_t bmax = __shfl_up_sync(0xffffffffu, imax, 1);
-            if (lane == 0u) bmax = 0u;
-            __syncthreads();
-#pragma unroll
-            for (uint32_t w = 0; w < NWARPS; w++) {
-                const unsigned long long sw = s_wsum64[w];
-                if (w < warp) { basev += sw; bmax = max(bmax, s_wmax[w]); }
-                tot += sw;
-            }
-            for (uint32_t w = wa; w < wb; w++) {
-                const unsigned long long g = gpre[w];
-                gpre[w] = ((g & PRE_SUMS) + basev) | ((unsigned long long)max((uint32_t)(g >> PRE_LS_SHIFT), bmax) << PRE_LS_SHIFT);
-            }
-            if (tid == 0) gpre[nwords] = tot & PRE_SUMS;                    // counts before a position just past the last word
-        }
-        const uint32_t n_ws_all = (uint32_t)tot & 0xFFFFu;                  // whitespace bytes in the loaded bytes
-        const uint32_t n_sep_all = (uint32_t)(tot >> 16) & 0xFFFFu;         // separators in the loaded bytes
-        const uint32_t n_rec_all = (uint32_t)(tot >> 32) & 0xFFFFu;         // records starting in the loaded bytes (ours + look-ahead)
-        __syncthreads();                                                    // ---- prefix complete
-
-        if (n_rec_all > (uint32_t)G::LINE_CAP || n_sep_all > (uint32_t)G::STEP_CAP || n_ws_all > (uint32_t)G::WS_CAP) {
-            // more records / separators than the lists hold (pathological input): the whole tile takes the slow path
-            for (uint32_t w = tid; w < nwords; w += THREADS) {
-                unsigned long long m = nl64[w];
-                while (m) {
-                    const uint32_t p = 64u * w + (uint32_t)(__ffsll((long long)m) - 1);
-                    m &= m - 1ull;
-                    if (p + 1u < own_end) defer_line(T, t0 + p + 1u - 16u, A.file_off, WHY_LINES_FULL);
-                }
-            }
-            if (tid == 0) my_tiles++;
             __syncthreads();
             if (tid == 0) {
-                s_oth = 0;
+                s_nlines = 0;
                 const uint32_t nxt = tile + gridDim.x;
                 if (nxt < A.n_tiles) issue_load(nxt);
             }
             __syncthreads();
             continue;
         }
+        const uint32_t n_lines = n_lines_all;
 
-        // ================= scatter: one thread per vector: whitespace / separator bit -> flat lists at its ordinal =================
-        // The first two whitespace bytes and the first two separators of a vector are handled without a loop (all lanes in
-        // step); vectors with more (the dense column zones, short ids) go to a per-warp list and are finished afterwards,
-        // dense vectors next to dense vectors.  The list borrows the (not yet used) sidx array.
-        {
-            constexpr uint32_t DL_CAP = (uint32_t)(4 * G::STEP_CAP) / (16u * NWARPS);
-            uint32_t* const dl = sidx + warp * (4u * DL_CAP);
-            uint32_t ndl = 0;
-            // separator at bit b of vector v (rec0 records started before the vector, n16 its newline bits)
-            auto put_sep = [&](uint32_t v, uint32_t b, uint32_t rec0, uint32_t n16, uint32_t osep) {
-                const uint32_t k = rec0 + (uint32_t)__popc(n16 & ((1u << b) - 1u));     // records started before the byte
-                steps[osep] = k == 0u ? SE_INVALID : ((16u * v + b) | ((k - 1u) << SE_SLOT_SHIFT));   // k == 0: tail of a record of the previous tile
-            };
-            // whitespace at bit b: a newline opens record `rec`
-            auto put_ws = [&](uint32_t v, uint32_t b, uint32_t n16, uint32_t& ows, uint32_t& rec) {
-                const uint32_t pos = 16u * v + b;
-                wslist[ows++] = (uint16_t)pos;
-                if ((n16 >> b) & 1u) {
-                    lines[rec] = (uint16_t)(pos + 1u);
-                    recws[rec] = (uint16_t)ows;
-                    rec++;
-                }
-            };
-            auto finish = [&](uint32_t v, uint32_t w16, uint32_t s16, uint32_t n16, uint32_t ows, uint32_t osep, uint32_t rec0) {
-                while (s16) {
-                    const uint32_t b = (uint32_t)(__ffs((int)s16) - 1);
-                    s16 &= s16 - 1u;
-                    put_sep(v, b, rec0, n16, osep++);
-                }
-                if (w16) {
-                    uint32_t rec = rec0 + (uint32_t)__popc(n16 & ((w16 & (0u - w16)) - 1u));     // newlines before the first byte left
-                    while (w16) {
-                        const uint32_t b = (uint32_t)(__ffs((int)w16) - 1);
-                        w16 &= w16 - 1u;
-                        put_ws(v, b, n16, ows, rec);
-                    }
-                }
-            };
-            for (uint32_t vb = 32u * warp; vb < 4u * nwords; vb += THREADS) {
-                const uint32_t v = vb + lane;
-                uint32_t w16 = 0, s16 = 0, n16 = 0, ows = 0, osep = 0, rec0 = 0;
-                if (v < 4u * nwords) {
-                    const uint32_t w = v >> 2, sh = 16u * (v & 3u);
-                    const unsigned long long wmw = wm64[w], smw = sm64[w];
-                    w16 = (uint32_t)(wmw >> sh) & 0xFFFFu;
-                    s16 = (uint32_t)(smw >> sh) & 0xFFFFu;
-                    if ((w16 | s16) != 0u) {
-                        const unsigned long long nlw = nl64[w], gp = gpre[w], below = ~(~0ull << sh);
-                        n16 = (uint32_t)(nlw >> sh) & 0xFFFFu;
-                        ows = ((uint32_t)gp & 0xFFFFu) + (uint32_t)__popcll(wmw & below);
-                        osep = ((uint32_t)(gp >> 16) & 0xFFFFu) + (uint32_t)__popcll(smw & below);
-                        rec0 = ((uint32_t)(gp >> 32) & 0xFFFFu) + (uint32_t)__popcll(nlw & below);   // records started before the vector
-                    }
-                }
+        // ================= records: two threads per record =================
+        // Whole warps per role (a warp that mixes the roles runs them one after the other), and the records dealt
+        // round-robin over a role's warps: every warp of the CTA gets n_lines / (NWARPS / 2) records of ONE role.
+        static_assert(NWARPS >= 2u && NWARPS % 2u == 0u, "half of the warps per role");
+        constexpr uint32_t RW = NWARPS / 2u;
+        const bool roleA = warp >= RW;
+        for (uint32_t l = (roleA ? warp - RW : warp) + RW * lane; l < n_lines; l += 32u * RW) {
+            LineRecF& R = recs[l];
+            const uint32_t ls = lines[l];
+            uint32_t wi = ls >> 6;
+            unsigned long long wmk = wm64[wi] & (~0ull << (ls & 63u));
+            uint32_t st = ST_FAST;
+            int why = WHY_LONG;
+            if (!roleA) {
+                // ---------------- role B: columns, filters, coordinates, path steps
+                uint32_t e[13];
+                e[0] = ls - 1u;
+                bool ran_off = false, gaps_ok = true;
+                uint32_t tabs = 0xFFFFFFFFu;                  // AND of (byte == '\t') over the first 11 boundaries
 #pragma unroll
-                for (int r = 0; r < 2; r++)
-                    if (s16) {
-                        const uint32_t b = (uint32_t)(__ffs((int)s16) - 1);
-                        s16 &= s16 - 1u;
-                        put_sep(v, b, rec0, n16, osep++);
-                    }
-                uint32_t rec = rec0;
-#pragma unroll
-                for (int r = 0; r < 2; r++)
-                    if (w16) {
-                        const uint32_t b = (uint32_t)(__ffs((int)w16) - 1);
-                        w16 &= w16 - 1u;
-                        put_ws(v, b, n16, ows, rec);
-                    }
-                const bool left = (w16 | s16) != 0u;
-                const uint32_t bm = __ballot_sync(0xffffffffu, left);
-                if (left) {
-                    const uint32_t slot = ndl + (uint32_t)__popc(bm & ((1u << lane) - 1u));
-                    if (slot < DL_CAP) {
-                        dl[4u * slot] = w16 | (s16 << 16);
-                        dl[4u * slot + 1u] = n16 | (v << 16);
-                        dl[4u * slot + 2u] = ows | (osep << 16);
-                        dl[4u * slot + 3u] = rec0;
-                    } else {
-                        finish(v, w16, s16, n16, ows, osep, rec0);          // list full: finish it here
+                for (int j = 1; j <= 12; j++) {
+                    e[j] = 0;
+                    if (!ran_off) {
+                        if (!next_ws(wm64, nwords, wi, wmk, e[j])) ran_off = true;   // record runs past the look-ahead
+                        else {
+                            gaps_ok &= e[j] - e[j - 1] >= 2u;                        // no empty column
+                            if (j < 12) tabs &= buf[e[j]] == '\t' ? 0xFFFFFFFFu : 0u;
+                        }
                     }
                 }
-                ndl += (uint32_t)__popc(bm);
-            }
-            __syncwarp();
-            ndl = min(ndl, DL_CAP);
-            for (uint32_t i = lane; i < ndl; i += 32u) {
-                const uint32_t d0 = dl[4u * i], d1 = dl[4u * i + 1u], d2 = dl[4u * i + 2u], d3 = dl[4u * i + 3u];
-                finish(d1 >> 16, d0 & 0xFFFFu, d0 >> 16, d1 & 0xFFFFu, d2 & 0xFFFFu, d2 >> 16, d3);
-            }
-        }
-        __syncthreads();                                                    // ---- whitespace list, raw step list, record starts complete
-
-        // records that start in the owned bytes; their separators = the step-list entries that matter
-        const uint32_t n_own = (uint32_t)(pre_at(own_end - 1u) >> 32) & 0xFFFFu;
-        const uint32_t n_ent = n_own == 0u ? 0u : (n_own < n_rec_all ? sep_at(lines[n_own]) : n_sep_all);
-        if (tid == 0) { my_lines += n_own; my_tiles++; }
-
-        // ================= fields: A (tags), T0 (shape, filters, path shape), T1 (coordinates) =================
-        // Whole warps per role (a warp that mixes roles runs them one after the other), and the records of a role dealt
-        // round-robin over its warps: the phase is as long as ONE role over n_own / warps records.
-        constexpr uint32_t WARPS_A = NWARPS >= 4u ? NWARPS / 2u : 1u, WARPS_T = NWARPS >= 4u ? NWARPS / 4u : 1u;
-        constexpr uint32_t ROLE_PASSES = NWARPS >= 4u ? 1u : (NWARPS == 2u ? 2u : 3u);   // few warps: a warp takes several roles in turn
-        for (uint32_t rp = 0; rp < ROLE_PASSES; rp++) {
-        const uint32_t vwarp = NWARPS >= 4u ? warp : (NWARPS == 2u ? (rp == 0u ? (warp == 0u ? 0u : 1u) : (warp == 0u ? 2u : 3u)) : rp);
-        // virtual role warps: [0, WARPS_A) role A, then WARPS_T of T0, then WARPS_T of T1
-        const uint32_t role = vwarp < WARPS_A ? 0u : (vwarp < WARPS_A + WARPS_T ? 1u : (vwarp < WARPS_A + 2u * WARPS_T ? 2u : 3u));
-        const uint32_t rwarps = role == 0u ? WARPS_A : WARPS_T;
-        const uint32_t rw0 = role == 0u ? vwarp : (role == 1u ? vwarp - WARPS_A : vwarp - WARPS_A - WARPS_T);
-        for (uint32_t item = rw0 + rwarps * lane; item < n_own && role < 3u; item += 32u * rwarps) {
-            if (role == 0u) {
-                // ---------------- role A: tags -> dv filter, cs ops
-                const uint32_t l = item;
-                LineRecF& R = recs[l];
-                const uint32_t rw = recws[l];
-                const uint16_t* const e = wslist + rw - 1u;               // e[c]: end of column c (e[0]: the newline before the record)
-                const uint32_t nc = l + 1u < n_rec_all ? (uint32_t)recws[l + 1u] - rw : 0u;   // whitespace bytes incl. the newline; 0: not terminated
-                int why = WHY_TAGS;
-                bool slow = nc < 13u, done = false;                          // no tags: no dv, ValueError (REF:179); the slow path reports
-                uint32_t cs_a = 0, cs_b = 0, dv_a = 0, dv_b = 0;
+                bool slow = ran_off, done = false, no_tags = false;
+                int32_t mapq = 0, plen = 0, start = 0, pend = 0;
                 if (!slow) {
-                    // ---- tags: [inert]* cs [inert]* dv in any order, within the first six tags
-                    uint32_t a = (uint32_t)e[12] + 1u, b = e[13];
-                    for (uint32_t t = 0;; t++) {
+                    // 11 single tabs, then a tab (tags follow) or the end of a 12-column record
+                    const uint32_t c12 = buf[e[12]];
+                    no_tags = c12 == '\n';
+                    if (!gaps_ok || tabs == 0u || (c12 != '\t' && !no_tags)) { slow = true; why = WHY_COLUMNS; }
+                }
+                if (!slow) {
+                    why = WHY_INTS;
+                    slow = !small_uint(buf, e[11] + 1u, e[12], mapq);
+                    if (!slow) {
+                        if ((int64_t)mapq < A.thr) { sink.reject(); done = true; }                   // REF:143-146
+                        else if (e[6] - e[5] == 2u && buf[e[5] + 1u] == '*') done = true;             // REF:147-148
+                    }
+                }
+                if (!slow && !done)
+                    slow = !small_uint(buf, e[6] + 1u, e[7], plen) || !small_uint(buf, e[7] + 1u, e[8], start) ||
+                           !small_uint(buf, e[8] + 1u, e[9], pend);
+                if (!slow && !done && no_tags) { slow = true; why = WHY_TAGS; }   // no dv tag: ValueError (REF:179), slow path reports
+                // ---- path column (REF:185-197): it must start with a separator; count the steps
+                uint32_t ns = 0, off = 0, a5 = 0, b5 = 0;
+                if (!slow && !done) {
+                    why = WHY_PATH;
+                    a5 = e[5] + 1u;
+                    b5 = e[6];
+                    for (uint32_t w = a5 >> 6; w <= ((b5 - 1u) >> 6); w++) ns += (uint32_t)__popcll(sep_word(sm64, w, a5, b5));
+                    if (ns == 0u || ns > (uint32_t)MAX_STEPS || !((sm64[a5 >> 6] >> (a5 & 63u)) & 1ull)) {
+                        slow = true;
+                    } else {
+                        off = atomicAdd(&s_nsteps, ns + 1u);                      // any order: a record only needs a contiguous range
+                        if (off + ns + 1u > (uint32_t)G::STEP_CAP) {              // list full: slow path
+                            slow = true;
+                            why = WHY_STEPS_FULL;
+                            for (uint32_t i = off; i < (uint32_t)G::STEP_CAP; i++) steps[i] = SE_INVALID;
+                        }
+                    }
+                }
+                st = slow ? ST_DEFER : (done ? ST_DONE : ST_FAST);
+                R.ls = (uint16_t)ls;
+                R.stB = (uint8_t)st;
+                R.whyB = (uint8_t)why;
+                R.nsteps = 0;
+                R.s0 = 0;
+                if (st == ST_FAST) {
+                    R.start = start;
+                    R.end_rel1 = plen - pend - 1;
+                    R.s0 = (uint16_t)off;
+                    R.nsteps = (uint16_t)ns;
+                    // ---- one entry per path step, then the sentinel (end of the column)
+                    const uint32_t common = (l << SE_SLOT_SHIFT) | (buf[a5] == '<' ? SE_REV : 0u);
+                    uint32_t i = off;
+                    for (uint32_t w = a5 >> 6; w <= ((b5 - 1u) >> 6); w++) {
+                        unsigned long long m = sep_word(sm64, w, a5, b5);
+                        while (m) {
+                            const uint32_t q = 64u * w + (uint32_t)(__ffsll((long long)m) - 1);
+                            m &= m - 1ull;
+                            steps[i] = q | common | (i == off ? SE_FIRST : 0u) | (i + 1u == off + ns ? SE_LAST : 0u);
+                            i++;
+                        }
+                    }
+                    steps[off + ns] = b5 | (l << SE_SLOT_SHIFT) | SE_SENT;
+                }
+            } else {
+                // ---------------- role A: tags -> dv filter, cs ops
+                uint32_t e11 = 0, e12 = 0, pos = 0;
+                bool ran_off = false;
+#pragma unroll 1
+                for (int j = 1; j <= 12 && !ran_off; j++) {
+                    if (!next_ws(wm64, nwords, wi, wmk, pos)) ran_off = true;
+                    e11 = e12;
+                    e12 = pos;
+                }
+                // role B decides about everything up to column 12; here: is there anything left to do?
+                int32_t mapq = 0;
+                bool idle = ran_off || buf[e12] != '\t' || !small_uint(buf, e11 + 1u, e12, mapq) || (int64_t)mapq < A.thr;
+                bool slow = false, done = false;
+                uint32_t cs_a = 0, cs_b = 0, dv_a = 0, dv_b = 0;
+                if (!idle) {
+                    // ---- tags: [inert]* cs [inert]* dv in any order, within the first few tags
+                    why = WHY_TAGS;
+                    uint32_t a = e12 + 1u, b = 0;
+                    if (!next_ws(wm64, nwords, wi, wmk, b)) slow = true;
+                    for (int j = 13; !slow; j++) {
                         if (!cs_b && b - a >= 3u && buf[a] == 'c' && buf[a + 1] == 's' && buf[a + 2] == ':') {
                             cs_a = a;
                             cs_b = b;
@@ -586,208 +486,128 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                             break;
                         }
                         if (cs_b && dv_b) break;
-                        if (13u + t == nc || t == 5u) { slow = true; break; }   // end of the record: a tag is missing
+                        if (buf[b] == '\n' || j >= 18) { slow = true; break; }      // end of the record: a tag is missing
                         a = b + 1u;
-                        b = e[14u + t];
+                        if (!next_ws(wm64, nwords, wi, wmk, b)) { slow = true; break; }
                     }
-                }
-                // ---- dv filter (REF:172-180).  The reference parses cs first, but that has no side effects and
-                //      cannot raise, so a record that dv filters out needs no cs class
-                if (!slow) {
-                    const uint32_t f = buf[dv_a], g = dv_a + 1u < dv_b ? buf[dv_a + 1u] : 0u, h = dv_a + 2u < dv_b ? buf[dv_a + 2u] : 0u;
-                    if (f == '0' && g == '.' && h == '0') {
-                        // 0.0xxx: never greater
-                    } else if (pt::dv_token_greater(buf, (int)dv_a, (int)dv_b)) {
-                        done = true;
-                    }
-                }
-                // ---- cs string (REF:10-37): "cs:Z:" then ops spelled the way an aligner spells them:
-                //      ':'<digits>  '*'<2 letters>  '-'<letters>  '+'<letters>  '='<LETTERS>, every length >= 1
-                if (!slow && !done) {
-                    why = WHY_CS;
-                    uint32_t n_tot = 0, nops = 0, op_off = 0;
-                    int32_t start_add = 0;
-                    if (cs_b - cs_a < 7u || buf[cs_a + 3] != 'Z' || buf[cs_a + 4] != ':') slow = true;
-                    uint32_t q = cs_a + 5u;
-                    uint64_t one;
-                    if (!slow && buf[q] == ':' && cs_b - q - 1u <= 7u && step_id(buf, q + 1u, cs_b - q - 1u, one) && one != 0u) {
-                        // cs:Z::<n> -- a perfect match
-                        op_off = atomicAdd(&s_nops, 1u);
-                        if (op_off < (uint32_t)G::OPS_CAP) ops[op_off] = OP_MATCH | ((uint32_t)one << 3);
-                        else slow = true;
-                        nops = 1;
-                        n_tot = (uint32_t)one;
-                    } else if (!slow) {
-                        // every op takes at least two bytes: room for (bytes / 2) ops is enough
-                        const uint32_t room = min((cs_b - q) >> 1, (uint32_t)MAX_OPS);
-                        op_off = atomicAdd(&s_nops, room);
-                        if (op_off + room > (uint32_t)G::OPS_CAP) slow = true;
-                        while (!slow && q < cs_b) {
-                            const uint32_t c = buf[q++];
-                            uint32_t kind, len = 0;
-                            if (c == ':') {
-                                kind = OP_MATCH;
-                                uint32_t nd = 0;
-                                while (q < cs_b && pt::is_digit(buf[q])) { len = len * 10u + (buf[q] - '0'); q++; nd++; }
-                                if (nd == 0u || nd > 7u) slow = true;
-                            } else if (c == '*') {
-                                kind = OP_SUB;
-                                if (q + 2u > cs_b || !is_lower(buf[q]) || !is_lower(buf[q + 1])) slow = true;
-                                q += 2u;
-                                len = 1;
-                            } else if (c == '-' || c == '+') {
-                                kind = c == '-' ? OP_DEL : OP_INS;
-                                while (q < cs_b && is_lower(buf[q])) { q++; len++; }
-                            } else if (c == '=') {
-                                kind = OP_EQ;
-                                while (q < cs_b && buf[q] - 'A' <= 24u) { q++; len++; }      // 'A'..'Y': "cs:Z:" cannot hide in here
-                            } else {
-                                slow = true;
-                                kind = 0;
-                            }
-                            // the text must end where the next op starts
-                            if (q < cs_b) {
-                                const uint32_t d = buf[q];
-                                if (d != ':' && d != '*' && d != '-' && d != '+' && d != '=') slow = true;
-                            }
-                            if (len == 0u || len > (uint32_t)MAX_NTOT || nops >= room) slow = true;
-                            if (!slow) {
-                                ops[op_off + nops] = kind | (len << 3);
-                                nops++;
-                                n_tot += len;
-                                if (n_tot > (uint32_t)MAX_NTOT) slow = true;
-                            }
-                        }
-                        if (nops == 0u) slow = true;
-                        // cigar_clipping (REF:40-50): only when there are exactly two ops
-                        if (!slow && nops == 2u) {
-                            const uint32_t o0 = ops[op_off], o1 = ops[op_off + 1u];
-                            if ((o0 & 7u) == OP_INS && (o1 & 7u) == OP_MATCH) {
-                                start_add = (int32_t)(o0 >> 3);
-                                ops[op_off] = o1;
-                                nops = 1;
-                                n_tot = o1 >> 3;
-                            } else if ((o0 & 7u) == OP_MATCH && (o1 & 7u) == OP_INS) {
-                                nops = 1;
-                                n_tot = o0 >> 3;
-                            }
-                        }
-                    }
-                    R.n_tot = n_tot;
-                    R.op_off = (uint16_t)op_off;
-                    R.nops = (uint8_t)nops;
-                    R.start_add = start_add;
-                }
-                R.stA = (uint8_t)(slow ? ST_DEFER : (done ? ST_DONE : ST_FAST));
-                R.whyA = (uint8_t)why;
-            } else if (role == 1u) {
-                // ---------------- role T0: column shape, MAPQ and '*' filters, path column shape, sentinel
-                const uint32_t l = item;
-                LineRecF& R = recs[l];
-                const uint32_t rw = recws[l];
-                const uint16_t* const e = wslist + rw - 1u;               // e[c]: end of column c (e[0]: the newline before the record)
-                const uint32_t nc = l + 1u < n_rec_all ? (uint32_t)recws[l + 1u] - rw : 0u;   // whitespace bytes incl. the newline; 0: not terminated
-                int why = WHY_LONG;                                         // nc == 0: the record runs past the look-ahead
-                bool slow = nc < 12u, done = false;
-                uint32_t e6 = 0;
-                if (nc != 0u && nc < 12u) why = WHY_COLUMNS;                // fewer than 12 columns: IndexError (REF:143), slow path reports
-                if (nc >= 6u) e6 = e[6];
-                if (!slow) {
-                    // 11 single tabs, then a tab (tags follow) or the end of a 12-column record; no empty column
-                    why = WHY_COLUMNS;
-                    uint32_t prev = e[0];
-                    bool ok = true;
-#pragma unroll
-                    for (int j = 1; j <= 12; j++) {
-                        const uint32_t cur = e[j];
-                        ok &= cur - prev >= 2u;
-                        prev = cur;
-                    }
-                    if (s_oth != 0u) {                                      // the tile holds whitespace other than tab / newline
-#pragma unroll
-                        for (int j = 1; j <= 11; j++) ok &= buf[e[j]] == '\t';
-                        const uint32_t c12 = buf[e[12]];
-                        ok &= c12 == '\t' || c12 == '\n';
-                    }
-                    slow = !ok;
-                }
-                if (!slow) {
-                    why = WHY_INTS;
-                    int32_t mapq = 0;
-                    const uint32_t e5 = e[5];
-                    slow = !small_uint(buf, (uint32_t)e[11] + 1u, e[12], mapq);
+                    // ---- dv filter (REF:172-180).  The reference parses cs first, but that has no side effects and
+                    //      cannot raise, so a record that dv filters out needs no cs class
                     if (!slow) {
-                        if ((int64_t)mapq < A.thr) { sink.reject(); done = true; }               // REF:143-146
-                        else if (e6 - e5 == 2u && buf[e5 + 1u] == '*') done = true;               // REF:147-148
+                        const uint32_t f = buf[dv_a], g = dv_a + 1u < dv_b ? buf[dv_a + 1u] : 0u, h = dv_a + 2u < dv_b ? buf[dv_a + 2u] : 0u;
+                        if (f == '0' && g == '.' && h == '0') {
+                            // 0.0xxx: never greater
+                        } else if (pt::dv_token_greater(buf, (int)dv_a, (int)dv_b)) {
+                            done = true;
+                        }
                     }
+                    // ---- cs string (REF:10-37): "cs:Z:" then ops spelled the way an aligner spells them:
+                    //      ':'<digits>  '*'<2 letters>  '-'<letters>  '+'<letters>  '='<LETTERS>, every length >= 1
                     if (!slow && !done) {
-                        // ---- path column (REF:185-197): it must start with a separator; count the steps
-                        why = WHY_PATH;
-                        const uint32_t a5 = e5 + 1u;
-                        const uint32_t ns = sep_at(e6) - sep_at(a5);
-                        if (ns == 0u || ns > (uint32_t)MAX_STEPS || !((sm64[a5 >> 6] >> (a5 & 63u)) & 1ull)) slow = true;
+                        why = WHY_CS;
+                        uint32_t n_tot = 0, nops = 0, op_off = 0;
+                        int32_t start_add = 0;
+                        if (cs_b - cs_a < 7u || buf[cs_a + 3] != 'Z' || buf[cs_a + 4] != ':') slow = true;
+                        uint32_t q = cs_a + 5u;
+                        uint64_t one;
+                        if (!slow && buf[q] == ':' && cs_b - q - 1u <= 7u && step_id(buf, q + 1u, cs_b - q - 1u, one) && one != 0u) {
+                            // cs:Z::<n> -- a perfect match
+                            op_off = atomicAdd(&s_nops, 1u);
+                            if (op_off < (uint32_t)G::OPS_CAP) ops[op_off] = OP_MATCH | ((uint32_t)one << 3);
+                            else slow = true;
+                            nops = 1;
+                            n_tot = (uint32_t)one;
+                        } else if (!slow) {
+                            // every op takes at least two bytes: room for (bytes / 2) ops is enough
+                            const uint32_t room = min((cs_b - q) >> 1, (uint32_t)MAX_OPS);
+                            op_off = atomicAdd(&s_nops, room);
+                            if (op_off + room > (uint32_t)G::OPS_CAP) slow = true;
+                            while (!slow && q < cs_b) {
+                                const uint32_t c = buf[q++];
+                                uint32_t kind, len = 0;
+                                if (c == ':') {
+                                    kind = OP_MATCH;
+                                    uint32_t nd = 0;
+                                    while (q < cs_b && pt::is_digit(buf[q])) { len = len * 10u + (buf[q] - '0'); q++; nd++; }
+                                    if (nd == 0u || nd > 7u) slow = true;
+                                } else if (c == '*') {
+                                    kind = OP_SUB;
+                                    if (q + 2u > cs_b || !is_lower(buf[q]) || !is_lower(buf[q + 1])) slow = true;
+                                    q += 2u;
+                                    len = 1;
+                                } else if (c == '-' || c == '+') {
+                                    kind = c == '-' ? OP_DEL : OP_INS;
+                                    while (q < cs_b && is_lower(buf[q])) { q++; len++; }
+                                } else if (c == '=') {
+                                    kind = OP_EQ;
+                                    while (q < cs_b && buf[q] - 'A' <= 24u) { q++; len++; }      // 'A'..'Y': "cs:Z:" cannot hide in here
+                                } else {
+                                    slow = true;
+                                    kind = 0;
+                                }
+                                // the text must end where the next op starts
+                                if (q < cs_b) {
+                                    const uint32_t d = buf[q];
+                                    if (d != ':' && d != '*' && d != '-' && d != '+' && d != '=') slow = true;
+                                }
+                                if (len == 0u || len > (uint32_t)MAX_NTOT || nops >= room) slow = true;
+                                if (!slow) {
+                                    ops[op_off + nops] = kind | (len << 3);
+                                    nops++;
+                                    n_tot += len;
+                                    if (n_tot > (uint32_t)MAX_NTOT) slow = true;
+                                }
+                            }
+                            if (nops == 0u) slow = true;
+                            // cigar_clipping (REF:40-50): only when there are exactly two ops
+                            if (!slow && nops == 2u) {
+                                const uint32_t o0 = ops[op_off], o1 = ops[op_off + 1u];
+                                if ((o0 & 7u) == OP_INS && (o1 & 7u) == OP_MATCH) {
+                                    start_add = (int32_t)(o0 >> 3);
+                                    ops[op_off] = o1;
+                                    nops = 1;
+                                    n_tot = o1 >> 3;
+                                } else if ((o0 & 7u) == OP_MATCH && (o1 & 7u) == OP_INS) {
+                                    nops = 1;
+                                    n_tot = o0 >> 3;
+                                }
+                            }
+                        }
+                        R.n_tot = n_tot;
+                        R.op_off = (uint16_t)op_off;
+                        R.nops = (uint8_t)nops;
+                        R.start_add = start_add;
                     }
                 }
-                R.a5 = (uint16_t)(nc >= 6u ? (uint32_t)e[5] + 1u : 0xFFFFu);            // `ids`: which separators are path steps
-                R.b5 = (uint16_t)(nc >= 6u ? e6 : 0xFFFFu);
-                R.ls = lines[l];
-                R.stB = (uint8_t)(slow ? ST_DEFER : (done ? ST_DONE : ST_FAST));
-                R.whyB = (uint8_t)why;
-            } else {
-                // ---------------- role T1: the three coordinates (REF:151-153)
-                const uint32_t l = item;
-                LineRecF& R = recs[l];
-                const uint32_t rw = recws[l];
-                const uint16_t* const e = wslist + rw - 1u;               // e[c]: end of column c (e[0]: the newline before the record)
-                const uint32_t nc = l + 1u < n_rec_all ? (uint32_t)recws[l + 1u] - rw : 0u;   // whitespace bytes incl. the newline; 0: not terminated
-                uint32_t st = ST_FAST;
-                if (nc >= 12u) {
-                    int32_t plen = 0, start = 0, pend = 0;
-                    const uint32_t e7 = e[7], e8 = e[8];
-                    if (small_uint(buf, (uint32_t)e[6] + 1u, e7, plen) && small_uint(buf, e7 + 1u, e8, start) &&
-                        small_uint(buf, e8 + 1u, e[9], pend)) {
-                        R.start = start;
-                        R.end_rel1 = plen - pend - 1;
-                    } else {
-                        st = ST_DEFER;
-                    }
-                }
-                R.stC = (uint8_t)st;
+                st = slow ? ST_DEFER : (done ? ST_DONE : ST_FAST);
+                R.stA = (uint8_t)st;
+                R.whyA = (uint8_t)why;
             }
         }
-        }
-        __syncthreads();                                                    // ---- records, ops complete
+        __syncthreads();                                                    // ---- records, ops, step list complete
+        const uint32_t n_ent = min(s_nsteps, (uint32_t)G::STEP_CAP);       // step entries incl. sentinels
+        if (tid == 0) s_nlines = 0;                                         // everyone has read it
 
-        // ================= ids: one thread per separator: path step or not, first / last, id -> node index, node length =================
-        // UI entries per thread and iteration: their node-record loads are all in flight before the first is stored
+        // ================= ids: one thread per path step: id -> node index, node length =================
+        // UI steps per thread and iteration: their node-record loads are all in flight before the first is stored
         // (the load also brings the node's sector into L2 for the count phase).  `sinfo` holds the lengths until walk 1.
         {
             constexpr int UI = 4;
             for (uint32_t s00 = 0; s00 < n_ent; s00 += THREADS * UI) {
-                uint32_t idx_[UI], len_[UI], se_[UI];
+                uint32_t idx_[UI], len_[UI];
 #pragma unroll
                 for (int u = 0; u < UI; u++) {
                     const uint32_t s = s00 + THREADS * u + tid;
-                    uint32_t idx = NONE32, se = SE_INVALID;
+                    uint32_t idx = NONE32;
                     if (s < n_ent) {
-                        const uint32_t raw = steps[s];                      // position | record << 16, from `scatter`
-                        if (raw != SE_INVALID) {
-                            const uint32_t p = raw & SE_POS_MASK;
-                            const LineRecF& R = recs[raw >> SE_SLOT_SHIFT];
-                            const uint32_t ab = *reinterpret_cast<const uint32_t*>(&R.a5), a5 = ab & 0xFFFFu, b5 = ab >> 16;
-                            if (p >= a5 && p < b5) {                        // inside the path column (not: read names, tags ...)
-                                // the next entry is the next separator of the record, or something at / past the end of the column
-                                const uint32_t nxt = s + 1u < n_sep_all ? (steps[s + 1u] & SE_POS_MASK) : SE_POS_MASK;
-                                const uint32_t end = min(nxt, b5);
-                                const bool rev = buf[a5] == '<';
-                                se = raw | (rev ? SE_REV : 0u) | (p == a5 ? SE_FIRST : 0u) | (nxt >= b5 ? SE_LAST : 0u);
-                                uint64_t id;
-                                uint32_t ix;
-                                if (buf[p] == (rev ? '<' : '>') && step_id(buf, p + 1u, end - p - 1u, id) && sink.id_to_idx(id, ix)) idx = ix;
-                            }
+                        const uint32_t se = steps[s];
+                        if (se != SE_INVALID && !(se & SE_SENT)) {
+                            const uint32_t p = se & SE_POS_MASK;
+                            const uint32_t end = steps[s + 1u] & SE_POS_MASK;       // next separator, or the sentinel
+                            uint64_t id;
+                            uint32_t ix;
+                            if (buf[p] == ((se & SE_REV) ? '<' : '>') && step_id(buf, p + 1u, end - p - 1u, id) && sink.id_to_idx(id, ix)) idx = ix;
                         }
                     }
-                    se_[u] = se;
                     idx_[u] = idx;                                          // NONE32: KeyError in the reference, `walk` hands the record over
                 }
 #pragma unroll
@@ -795,28 +615,27 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
 #pragma unroll
                 for (int u = 0; u < UI; u++) {
                     const uint32_t s = s00 + THREADS * u + tid;
-                    if (s < n_ent) { steps[s] = se_[u]; sidx[s] = idx_[u]; sinfo[s] = len_[u]; }
+                    if (s < n_ent) { sidx[s] = idx_[u]; sinfo[s] = len_[u]; }
                 }
             }
         }
         __syncthreads();                                                    // ---- node indices complete; the bytes and the masks are dead
         if (tid == 0) {
+            s_nsteps = 0;
             s_nops = 0;
             s_nfar = 0;
             s_ndel = 0;
-            s_oth = 0;
             const uint32_t nxt = tile + gridDim.x;
             if (nxt < A.n_tiles) issue_load(nxt);                           // overlaps walk + count
         }
 
         // ================= walk 1: step lengths and their block-wide prefix sum =================
-        // (one entry more than the list holds: walk 2 closes the last step with sinfo[s + 1])
-        const uint32_t per = (n_ent + THREADS) / THREADS;                   // consecutive entries per thread
-        const uint32_t sa = min(tid * per, n_ent + 1u), sb = min(sa + per, n_ent + 1u);
+        const uint32_t per = (n_ent + THREADS - 1u) / THREADS;              // consecutive entries per thread
+        const uint32_t sa = min(tid * per, n_ent), sb = min(sa + per, n_ent);
         {
             uint32_t local = 0;
             for (uint32_t s = sa; s < sb; s++) {
-                const uint32_t se = s < n_ent ? steps[s] : SE_INVALID;
+                const uint32_t se = steps[s];
                 uint32_t Lc = 0;
                 if (se != SE_INVALID && !(se & SE_SENT)) {
                     LineRecF& R = recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK];
@@ -851,7 +670,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             for (uint32_t s = sa; s < sb; s++) {
                 const uint32_t g = sinfo[s] + basev;
                 sinfo[s] = g;
-                const uint32_t se = s < n_ent ? steps[s] : SE_INVALID;
+                const uint32_t se = steps[s];
                 if (se != SE_INVALID && (se & SE_FIRST)) recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK].base = g;
             }
         }
@@ -939,9 +758,9 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             }
         }
         __syncthreads();                                                    // ---- every hand-over decision is made; nothing counted so far
-        for (uint32_t l = tid; l < n_own; l += THREADS) {
+        for (uint32_t l = tid; l < n_lines; l += THREADS) {
             const LineRecF& R = recs[l];
-            if (rec_status(R) == ST_DEFER) defer_line(T, t0 + R.ls - 16u, A.file_off, rec_why(R));
+            if (rec_status(R) == ST_DEFER) defer_line(T, t0 + R.ls - 16u, A.file_off, R.stB == ST_DEFER ? R.whyB : R.whyA);
         }
 
         // surviving neighbours of step s inside its record (dropped nodes are skipped)
