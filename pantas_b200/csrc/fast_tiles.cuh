@@ -192,24 +192,24 @@ __device__ __forceinline__ bool small_uint(const uint8_t* s, uint32_t a, uint32_
     return true;
 }
 
-// next whitespace bit at or after the walker's position (64 bytes of the tile per mask word);
+// The walkers read the 64-bit mask words as 32-bit halves (one FLO / POPC per step instead of two).
+// next whitespace bit at or after the walker's position (32 bytes of the tile per half word);
 // false: ran off the end of the loaded bytes
-__device__ __forceinline__ bool next_ws(const unsigned long long* wm64, uint32_t nwords, uint32_t& wi, unsigned long long& m,
-                                        uint32_t& pos) {
-    while (m == 0ull) {
-        if (++wi >= nwords) return false;
-        m = wm64[wi];
+__device__ __forceinline__ bool next_ws(const uint32_t* wm32, uint32_t nhalf, uint32_t& wi, uint32_t& m, uint32_t& pos) {
+    while (m == 0u) {
+        if (++wi >= nhalf) return false;
+        m = wm32[wi];
     }
-    pos = 64u * wi + (uint32_t)(__ffsll((long long)m) - 1);
-    m &= m - 1ull;
+    pos = 32u * wi + (uint32_t)(__ffs((int)m) - 1);
+    m &= m - 1u;
     return true;
 }
 
-// separator bits of mask word w that lie in buffer positions [a, b)
-__device__ __forceinline__ unsigned long long sep_word(const unsigned long long* sm64, uint32_t w, uint32_t a, uint32_t b) {
-    unsigned long long m = sm64[w];
-    if (w == (a >> 6)) m &= ~0ull << (a & 63u);
-    if (w == (b >> 6)) m &= ~(~0ull << (b & 63u));           // b & 63 == 0: nothing of this word is below b
+// separator bits of half word w that lie in buffer positions [a, b)
+__device__ __forceinline__ uint32_t sep_word(const uint32_t* sm32, uint32_t w, uint32_t a, uint32_t b) {
+    uint32_t m = sm32[w];
+    if (w == (a >> 5)) m &= ~0u << (a & 31u);
+    if (w == (b >> 5)) m &= ~(~0u << (b & 31u));             // b & 31 == 0: nothing of this half word is below b
     return m;
 }
 
@@ -234,6 +234,8 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
     uint8_t* const buf = smem;
     unsigned long long* const wm64 = reinterpret_cast<unsigned long long*>(smem + G::OFF_WM);
     unsigned long long* const sm64 = reinterpret_cast<unsigned long long*>(smem + G::OFF_SM);
+    const uint32_t* const wm32 = reinterpret_cast<const uint32_t*>(smem + G::OFF_WM);   // the same masks, as half words
+    const uint32_t* const sm32 = reinterpret_cast<const uint32_t*>(smem + G::OFF_SM);
     uint32_t* const far = reinterpret_cast<uint32_t*>(smem + G::OFF_FAR);      // {from, to, separator position} (reuses the masks)
     uint32_t* const dels = reinterpret_cast<uint32_t*>(smem + G::OFF_DEL);     // {step, first del, last del}     (reuses the masks)
     uint32_t* const steps = reinterpret_cast<uint32_t*>(smem + G::OFF_STEP);
@@ -368,8 +370,8 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         for (uint32_t l = (roleA ? warp - RW : warp) + RW * lane; l < n_lines; l += 32u * RW) {
             LineRecF& R = recs[l];
             const uint32_t ls = lines[l];
-            uint32_t wi = ls >> 6;
-            unsigned long long wmk = wm64[wi] & (~0ull << (ls & 63u));
+            uint32_t wi = ls >> 5;
+            uint32_t wmk = wm32[wi] & (~0u << (ls & 31u));
             uint32_t st = ST_FAST;
             int why = WHY_LONG;
             if (!roleA) {
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 for (int j = 1; j <= 12; j++) {
                     e[j] = 0;
                     if (!ran_off) {
-                        if (!next_ws(wm64, nwords, wi, wmk, e[j])) ran_off = true;   // record runs past the look-ahead
+                        if (!next_ws(wm32, 2u * nwords, wi, wmk, e[j])) ran_off = true;   // record runs past the look-ahead
                         else {
                             gaps_ok &= e[j] - e[j - 1] >= 2u;                        // no empty column
                             if (j < 12) tabs &= buf[e[j]] == '\t' ? 0xFFFFFFFFu : 0u;
@@ -415,8 +417,8 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                     why = WHY_PATH;
                     a5 = e[5] + 1u;
                     b5 = e[6];
-                    for (uint32_t w = a5 >> 6; w <= ((b5 - 1u) >> 6); w++) ns += (uint32_t)__popcll(sep_word(sm64, w, a5, b5));
-                    if (ns == 0u || ns > (uint32_t)MAX_STEPS || !((sm64[a5 >> 6] >> (a5 & 63u)) & 1ull)) {
+                    for (uint32_t w = a5 >> 5; w <= ((b5 - 1u) >> 5); w++) ns += (uint32_t)__popc(sep_word(sm32, w, a5, b5));
+                    if (ns == 0u || ns > (uint32_t)MAX_STEPS || !((sm32[a5 >> 5] >> (a5 & 31u)) & 1u)) {
                         slow = true;
                     } else {
                         off = atomicAdd(&s_nsteps, ns + 1u);                      // any order: a record only needs a contiguous range
@@ -441,11 +443,11 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                     // ---- one entry per path step, then the sentinel (end of the column)
                     const uint32_t common = (l << SE_SLOT_SHIFT) | (buf[a5] == '<' ? SE_REV : 0u);
                     uint32_t i = off;
-                    for (uint32_t w = a5 >> 6; w <= ((b5 - 1u) >> 6); w++) {
-                        unsigned long long m = sep_word(sm64, w, a5, b5);
+                    for (uint32_t w = a5 >> 5; w <= ((b5 - 1u) >> 5); w++) {
+                        uint32_t m = sep_word(sm32, w, a5, b5);
                         while (m) {
-                            const uint32_t q = 64u * w + (uint32_t)(__ffsll((long long)m) - 1);
-                            m &= m - 1ull;
+                            const uint32_t q = 32u * w + (uint32_t)(__ffs((int)m) - 1);
+                            m &= m - 1u;
                             steps[i] = q | common | (i == off ? SE_FIRST : 0u) | (i + 1u == off + ns ? SE_LAST : 0u);
                             i++;
                         }
@@ -454,14 +456,20 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 }
             } else {
                 // ---------------- role A: tags -> dv filter, cs ops
-                uint32_t e11 = 0, e12 = 0, pos = 0;
+                uint32_t e11 = 0, e12 = 0;
                 bool ran_off = false;
-#pragma unroll 1
-                for (int j = 1; j <= 12 && !ran_off; j++) {
-                    if (!next_ws(wm64, nwords, wi, wmk, pos)) ran_off = true;
-                    e11 = e12;
-                    e12 = pos;
+                // the first ten column boundaries are role B's business: skip them a half word at a time
+                uint32_t skip = 10;
+                for (;;) {
+                    const uint32_t c = (uint32_t)__popc(wmk);
+                    if (c > skip) break;
+                    skip -= c;
+                    if (++wi >= 2u * nwords) { ran_off = true; break; }
+                    wmk = wm32[wi];
                 }
+                for (; skip != 0u && !ran_off; skip--) wmk &= wmk - 1u;
+                if (!ran_off && !next_ws(wm32, 2u * nwords, wi, wmk, e11)) ran_off = true;
+                if (!ran_off && !next_ws(wm32, 2u * nwords, wi, wmk, e12)) ran_off = true;
                 // role B decides about everything up to column 12; here: is there anything left to do?
                 int32_t mapq = 0;
                 bool idle = ran_off || buf[e12] != '\t' || !small_uint(buf, e11 + 1u, e12, mapq) || (int64_t)mapq < A.thr;
@@ -471,7 +479,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                     // ---- tags: [inert]* cs [inert]* dv in any order, within the first few tags
                     why = WHY_TAGS;
                     uint32_t a = e12 + 1u, b = 0;
-                    if (!next_ws(wm64, nwords, wi, wmk, b)) slow = true;
+                    if (!next_ws(wm32, 2u * nwords, wi, wmk, b)) slow = true;
                     for (int j = 13; !slow; j++) {
                         if (!cs_b && b - a >= 3u && buf[a] == 'c' && buf[a + 1] == 's' && buf[a + 2] == ':') {
                             cs_a = a;
@@ -488,7 +496,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                         if (cs_b && dv_b) break;
                         if (buf[b] == '\n' || j >= 18) { slow = true; break; }      // end of the record: a tag is missing
                         a = b + 1u;
-                        if (!next_ws(wm64, nwords, wi, wmk, b)) { slow = true; break; }
+                        if (!next_ws(wm32, 2u * nwords, wi, wmk, b)) { slow = true; break; }
                     }
                     // ---- dv filter (REF:172-180).  The reference parses cs first, but that has no side effects and
                     //      cannot raise, so a record that dv filters out needs no cs class

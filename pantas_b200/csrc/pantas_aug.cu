@@ -552,6 +552,9 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
         typedef fastp::Geo<20480, 1024, 256> GG;
         typedef fastp::Geo<8192, 1024, 128> GH;
         typedef fastp::Geo<8192, 1024, 256> GI;
+        typedef fastp::Geo<49152, 1024, 768> GJ;
+        typedef fastp::Geo<40960, 1024, 512> GK;
+        typedef fastp::Geo<49152, 1024, 1024> GL;
         typedef fastp::Geo<1024, 256, 64> GT;    // tests: many tile boundaries, records longer than the look-ahead
         uint32_t ft;
 #define PT_PICK(Gx) { fkern = fastp::augment_fast_kernel<Gx>; fsmem = (size_t)Gx::SMEM_BYTES; ft = Gx::TILE; f_threads = Gx::THREADS; }
@@ -564,8 +567,11 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
         else if (ctx->fast_geo == 20480) PT_PICK(GG)
         else if (ctx->fast_geo == 8192) PT_PICK(GH)
         else if (ctx->fast_geo == 8193) PT_PICK(GI)
+        else if (ctx->fast_geo == 49152) PT_PICK(GJ)
+        else if (ctx->fast_geo == 40960) PT_PICK(GK)
+        else if (ctx->fast_geo == 49153) PT_PICK(GL)
         else if (ctx->fast_geo == 24576) PT_PICK(GA)
-        else PT_PICK(GC)
+        else PT_PICK(GA)
 #undef PT_PICK
         if (ctx->fast_ctas_per_sm == 0) {
             CK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
