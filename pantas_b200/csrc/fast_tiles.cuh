@@ -288,14 +288,18 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         for (uint32_t g = tid; g < nwords; g += THREADS) {
             unsigned long long wm = 0, sm = 0;
             uint32_t oth = 0, hib = 0;
+            // the four vectors of the group in a lane-dependent order: a quarter warp's eight LDS.128 then fall into
+            // eight different 16-byte bank groups (lane stride 64 bytes alone would put them into two)
+            const uint32_t rot = (lane >> 1) & 3u;
             uint4 q[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) q[u] = *reinterpret_cast<const uint4*>(buf + 64u * g + 16u * u);
+            for (int u = 0; u < 4; u++) q[u] = *reinterpret_cast<const uint4*>(buf + 64u * g + 16u * ((u + rot) & 3u));
 #pragma unroll
             for (int u = 0; u < 4; u++) {
+                const uint32_t sh = 16u * ((u + rot) & 3u);
                 const uint32_t w0 = flag_ws(q[u].x), w1 = flag_ws(q[u].y), w2 = flag_ws(q[u].z), w3 = flag_ws(q[u].w);
-                wm |= (unsigned long long)mask16(w0, w1, w2, w3) << (16 * u);
-                sm |= (unsigned long long)mask16(flag_sep(q[u].x), flag_sep(q[u].y), flag_sep(q[u].z), flag_sep(q[u].w)) << (16 * u);
+                wm |= (unsigned long long)mask16(w0, w1, w2, w3) << sh;
+                sm |= (unsigned long long)mask16(flag_sep(q[u].x), flag_sep(q[u].y), flag_sep(q[u].z), flag_sep(q[u].w)) << sh;
                 // whitespace that is not a tab: '\n' (record start), '\r' (lone: error); the rest only matters to the walkers
                 oth |= (w0 & ~flag_tab(q[u].x)) | (w1 & ~flag_tab(q[u].y)) | (w2 & ~flag_tab(q[u].z)) | (w3 & ~flag_tab(q[u].w));
                 hib |= q[u].x | q[u].y | q[u].z | q[u].w;
@@ -316,7 +320,8 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
 #pragma unroll
                 for (int u = 0; u < 4; u++)
                     om |= (unsigned long long)mask16(flag_ws(q[u].x) & ~flag_tab(q[u].x), flag_ws(q[u].y) & ~flag_tab(q[u].y),
-                                                     flag_ws(q[u].z) & ~flag_tab(q[u].z), flag_ws(q[u].w) & ~flag_tab(q[u].w)) << (16 * u);
+                                                     flag_ws(q[u].z) & ~flag_tab(q[u].z), flag_ws(q[u].w) & ~flag_tab(q[u].w))
+                          << (16u * ((u + rot) & 3u));
                 if (g == 0 && tile != 0) keep |= 0x8000ull;                 // is the byte before the tile a newline?
                 om &= keep;
                 while (om) {

@@ -347,7 +347,7 @@ int pt_create(int device, pt_ctx** out) {
         ctx->threads != 512)
         ctx->threads = 256;
     ctx->kernel_ver = env_u32("PANTAS_KERNEL", 2);
-    ctx->fast_geo = env_u32("PANTAS_FAST_T", 24576);
+    ctx->fast_geo = env_u32("PANTAS_FAST_T", 32768);
     *out = ctx;
     return 0;
 }
