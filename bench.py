@@ -59,6 +59,18 @@ def parse_args():
     return ap.parse_args()
 
 
+def measured_traffic(workload: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")) as f:
+            d = json.load(f)
+        if d.get("workload") == workload:
+            return int(d["dram_bytes_read_per_launch"]) + int(d["dram_bytes_write_per_launch"])
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -392,7 +404,8 @@ def main():
             "clocks": clocks,
             "e2e": e2e,
             "roofline": {"bound": "hbm", "kernel": "augment_fast_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": measured_traffic(args.workload) if world == 1 else None,
                          "peak_source": peak_src, "kernel_ms": kern_avg_ms,
                          "algorithmic_bytes_per_launch": int(nbytes)},
         }
