@@ -367,12 +367,14 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         const uint32_t n_lines = n_lines_all;
 
         // ================= records: two threads per record =================
-        // Whole warps per role (a warp that mixes the roles runs them one after the other), and the records dealt
-        // round-robin over a role's warps: every warp of the CTA gets n_lines / (NWARPS / 2) records of ONE role.
+        // Whole warps per role (a warp that mixes the roles runs them one after the other).  A warp takes as long for
+        // one record as for 32, so the records are packed into as few warps as they need: the phase is one pass of
+        // each role, the other warps wait at the barrier and cost no issue slots.
         static_assert(NWARPS >= 2u && NWARPS % 2u == 0u, "half of the warps per role");
         constexpr uint32_t RW = NWARPS / 2u;
         const bool roleA = warp >= RW;
-        for (uint32_t l = (roleA ? warp - RW : warp) + RW * lane; l < n_lines; l += 32u * RW) {
+        const uint32_t nrw = min((n_lines + 31u) >> 5, RW);                // warps per role in use
+        for (uint32_t l = 32u * (roleA ? warp - RW : warp) + lane; l < n_lines && (roleA ? warp - RW : warp) < nrw; l += 32u * nrw) {
             LineRecF& R = recs[l];
             const uint32_t ls = lines[l];
             uint32_t wi = ls >> 5;
