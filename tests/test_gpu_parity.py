@@ -202,3 +202,47 @@ def test_no_graph_is_an_error():
     eng = _engine()
     with pytest.raises(NativeLibraryError):
         eng.reset()
+
+
+@pytest.mark.parametrize("preset,pairs", [("dm-full", 1_000_000), ("hs-chr1", 250_000), ("gene-panel", 500_000)])
+def test_full_size_graphs_are_linear_in_the_gaf(preset, pairs):
+    """Size-independent property at the bench's graph sizes (the CPU oracle would take minutes there):
+    counting a GAF in one piece == counting its halves separately and adding up (sums add, first-touch
+    stamps take the minimum, side tables merge), and every record is accounted for."""
+    import torch
+
+    from pantas_b200.counts import merge_flat
+    from pantas_b200.shard import shard_bounds_bytes
+    from pantas_b200.synth import SynthGraph
+
+    sg = SynthGraph(preset, seed=1003)
+    graph = sg.graph()
+    gaf, n_lines = sg.gaf(pairs, first_pair=0)
+    n = int(gaf.shape[0])
+    d = torch.zeros(n + 32, dtype=torch.uint8, device="cuda")
+    d[:n] = torch.from_numpy(gaf).cuda()
+
+    eng = _engine()
+    eng.set_graph(graph)
+    eng.process_device(d, n, 0, 20)
+    eng.check_data_error()
+    whole = eng.export()
+    assert int(whole.sums[-3]) == n_lines
+    assert eng.stats()["deferred_lines"] < 0.05 * n_lines
+
+    bounds = shard_bounds_bytes(gaf, 3)
+    parts = []
+    for k, (lo, hi) in enumerate(zip(bounds, bounds[1:])):
+        e2 = _engine(PANTAS_FAST_T=[32768, 24576, 16384][k])
+        e2.set_graph(graph)
+        piece = torch.zeros(hi - lo + 32, dtype=torch.uint8, device="cuda")
+        piece[: hi - lo] = d[lo:hi]
+        e2.process_device(piece, hi - lo, lo, 20)
+        e2.check_data_error()
+        parts.append(e2.export())
+        e2.close()
+    merged = merge_flat(parts)
+    assert np.array_equal(merged.sums, whole.sums)
+    assert np.array_equal(merged.stamps, whole.stamps)
+    for a, b in ((merged.novel, whole.novel), (merged.sparse, whole.sparse)):
+        assert sorted(map(tuple, a.tolist())) == sorted(map(tuple, b.tolist()))
