@@ -39,7 +39,16 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-
+// the same for bytes that are read exactly once (the GAF stream): L2 evict-first, so that the stream does not push
+// the node table's sectors out of the L2
+__device__ __forceinline__ void tma_load_1d_stream(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #else   // ---- test harness: the bulk copy is a memcpy that has completed when it returns
 #define PT_DYNAMIC_SMEM(name) uint8_t* const name = emu::S().dyn
@@ -51,6 +60,7 @@ inline void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, ui
     memcpy(dst_smem, src_gmem, bytes);
     *bar += 1;
 }
+inline void tma_load_1d_stream(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) { tma_load_1d(dst_smem, src_gmem, bytes, bar); }
 inline void fence_async_smem() {}
 #endif
 
