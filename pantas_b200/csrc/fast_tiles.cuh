@@ -267,7 +267,8 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         const uint32_t bytes = (uint32_t)(hi - lo);
         fence_async_smem();
         mbar_expect_tx(&mbar, bytes);
-        tma_load_1d_stream(buf + (tile ? 0u : 16u), A.gaf + lo, bytes, &mbar);
+        if (A.stream_hint) tma_load_1d_stream(buf + (tile ? 0u : 16u), A.gaf + lo, bytes, &mbar);
+        else tma_load_1d(buf + (tile ? 0u : 16u), A.gaf + lo, bytes, &mbar);
     };
 
     uint32_t tile = blockIdx.x;
