@@ -48,20 +48,21 @@ enum : uint8_t { ST_FAST = 0, ST_DONE = 1, ST_DEFER = 2 };      // per role; a r
 enum : uint32_t { OP_MATCH = 0, OP_SUB = 1, OP_DEL = 2, OP_INS = 3, OP_EQ = 4 };   // ':' '*' '-' '+' '='  (op = kind | len << 3)
 
 struct __align__(4) LineRecF {
-    int32_t start;        // int(tokens[7])                                    (role P)
-    int32_t end_rel1;     // int(tokens[6]) - int(tokens[8]) - 1               (role P)
-    int32_t start_add;    // cigar_clipping: start_pos += len of a leading '+' (role C, REF:46-47)
-    uint32_t n_tot;       // sum of the cs op lengths                          (role C)
+    int32_t start;        // int(tokens[7])                                    (role B)
+    int32_t end_rel1;     // int(tokens[6]) - int(tokens[8]) - 1               (role B)
+    int32_t start_add;    // cigar_clipping: start_pos += len of a leading '+' (role A, REF:46-47)
+    uint32_t n_tot;       // sum of the cs op lengths                          (role A)
     uint32_t base;        // step-length prefix at the record's first step     (walk)
-    uint16_t s0;          // first entry of the record in the step list        (role P)
-    uint16_t nsteps;      //                                                   (role P)
+    uint16_t s0;          // first entry of the record in the step list        (role B)
+    uint16_t nsteps;      //                                                   (role B)
     uint16_t ls;          // buffer position of the record's first byte        (role B)
-    uint16_t op_off;      // first op of the record in the op pool             (role C)
-    uint8_t stA, stB, stP, stC;   // ST_* per role (one word, see rec_status); walk raises stB
-    uint8_t nops;         //                                                   (role C)
-    uint8_t whyA, whyB, whyP;     // WHY_* when the role says ST_DEFER (role C: always WHY_CS)
+    uint16_t op_off;      // first op of the record in the op pool             (role A)
+    uint8_t nops;         //                                                   (role A)
+    uint8_t stA, stB;     // ST_* per role; walk raises stB
+    uint8_t whyA, whyB;   // WHY_* when the role says ST_DEFER
+    uint8_t pad[3];
 };
-static_assert(sizeof(LineRecF) == 36 && offsetof(LineRecF, stA) == 28, "rec_status reads the four status bytes as one word");
+static_assert(sizeof(LineRecF) == 36 && offsetof(LineRecF, nops) == 28, "rec_status reads nops / stA / stB as one word");
 
 // step list entry
 constexpr uint32_t SE_POS_MASK = 0xFFFFu;     // bits 0..15  buffer position of the separator (sentinel: end of the path column)
@@ -214,15 +215,10 @@ __device__ __forceinline__ uint32_t sep_word(const uint32_t* sm32, uint32_t w, u
 
 __device__ __forceinline__ bool is_lower(uint32_t c) { return c - 'a' <= 25u; }
 
-// Role B has the last word: the reference `continue`s on its filters before it looks at anything else (REF:143-148),
-// and a record without 12 well-formed columns is handed over whatever the other roles made of it.
+// status of a record = the worse of its two roles
 __device__ __forceinline__ uint32_t rec_status(const LineRecF& R) {
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(&R.stA);         // stA | stB << 8 | stP << 16 | stC << 24: one LDS
-    const uint32_t b = (w >> 8) & 0xFFu;
-    return b != ST_FAST ? b : max(max(w & 0xFFu, (w >> 16) & 0xFFu), w >> 24);
-}
-__device__ __forceinline__ int rec_why(const LineRecF& R) {
-    return R.stB == ST_DEFER ? (int)R.whyB : (R.stP == ST_DEFER ? (int)R.whyP : (R.stA == ST_DEFER ? (int)R.whyA : (int)WHY_CS));
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(&R.nops);        // nops | stA << 8 | stB << 16 | whyA << 24: one LDS
+    return max((w >> 8) & 0xFFu, (w >> 16) & 0xFFu);
 }
 
 template <class G>
@@ -371,41 +367,23 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         }
         const uint32_t n_lines = n_lines_all;
 
-        // ================= records: four roles per record, whole warps per role =================
-        // A warp takes as long for one record as for 32 and runs divergent lanes one after the other, so the per-record
-        // work is cut into four independent roles that run on DIFFERENT warps at the same time (each finds the column
-        // boundaries it needs itself: a few POPCs), and the records of a role are packed into as few warps as they need.
-        //   B  12 column boundaries and their shape, MAPQ and '*' filters (REF:143-148)           -> stB (has the last word)
-        //   P  the three coordinates (REF:151-153), the path column -> step-list entries          -> stP
-        //   A  tags: first cs token, first dv:f: token (REF:154-160,172-180), the dv filter       -> stA
-        //   C  the cs string parsed into the tile's op pool (REF:10-50, incl. cigar_clipping)     -> stC
-        constexpr uint32_t NG = NWARPS >= 4u ? 4u : NWARPS;                 // warp groups (fewer than 4: a group takes several roles in turn)
-        constexpr uint32_t WPG = NWARPS / NG;                               // warps per group
-        static_assert(NWARPS % NG == 0u, "warps per role group");
-        const uint32_t wig = warp % WPG;
-        const uint32_t nrw = min((n_lines + 31u) >> 5, WPG);                // warps per role in use
-        const uint32_t nhalf = 2u * nwords;
-        // skip `skip` whitespace bytes from the walker's position, a half word at a time; false: ran off the loaded bytes
-        auto skip_ws = [&](uint32_t& wi, uint32_t& wmk, uint32_t skip) -> bool {
-            for (;;) {
-                const uint32_t c = (uint32_t)__popc(wmk);
-                if (c > skip) break;
-                skip -= c;
-                if (++wi >= nhalf) return false;
-                wmk = wm32[wi];
-            }
-            for (; skip != 0u; skip--) wmk &= wmk - 1u;
-            return true;
-        };
-        for (uint32_t role = warp / WPG; role < 4u; role += NG) {
-        for (uint32_t l = 32u * wig + lane; l < n_lines && wig < nrw; l += 32u * nrw) {
+        // ================= records: two threads per record =================
+        // Whole warps per role (a warp that mixes the roles runs them one after the other).  A warp takes as long for
+        // one record as for 32, so the records are packed into as few warps as they need: the phase is one pass of
+        // each role, the other warps wait at the barrier and cost no issue slots.
+        static_assert(NWARPS >= 2u && NWARPS % 2u == 0u, "half of the warps per role");
+        constexpr uint32_t RW = NWARPS / 2u;
+        const bool roleA = warp >= RW;
+        const uint32_t nrw = min((n_lines + 31u) >> 5, RW);                // warps per role in use
+        for (uint32_t l = 32u * (roleA ? warp - RW : warp) + lane; l < n_lines && (roleA ? warp - RW : warp) < nrw; l += 32u * nrw) {
             LineRecF& R = recs[l];
             const uint32_t ls = lines[l];
             uint32_t wi = ls >> 5;
             uint32_t wmk = wm32[wi] & (~0u << (ls & 31u));
-            if (role == 0u) {
-                // ---------------- role B: column shape, filters
-                int why = WHY_LONG;
+            uint32_t st = ST_FAST;
+            int why = WHY_LONG;
+            if (!roleA) {
+                // ---------------- role B: columns, filters, coordinates, path steps
                 uint32_t e[13];
                 e[0] = ls - 1u;
                 bool ran_off = false, gaps_ok = true;
@@ -414,7 +392,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 for (int j = 1; j <= 12; j++) {
                     e[j] = 0;
                     if (!ran_off) {
-                        if (!next_ws(wm32, nhalf, wi, wmk, e[j])) ran_off = true;   // record runs past the look-ahead
+                        if (!next_ws(wm32, 2u * nwords, wi, wmk, e[j])) ran_off = true;   // record runs past the look-ahead
                         else {
                             gaps_ok &= e[j] - e[j - 1] >= 2u;                        // no empty column
                             if (j < 12) tabs &= buf[e[j]] == '\t' ? 0xFFFFFFFFu : 0u;
@@ -422,6 +400,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                     }
                 }
                 bool slow = ran_off, done = false, no_tags = false;
+                int32_t mapq = 0, plen = 0, start = 0, pend = 0;
                 if (!slow) {
                     // 11 single tabs, then a tab (tags follow) or the end of a 12-column record
                     const uint32_t c12 = buf[e[12]];
@@ -430,52 +409,41 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 }
                 if (!slow) {
                     why = WHY_INTS;
-                    int32_t mapq = 0;
                     slow = !small_uint(buf, e[11] + 1u, e[12], mapq);
                     if (!slow) {
                         if ((int64_t)mapq < A.thr) { sink.reject(); done = true; }                   // REF:143-146
                         else if (e[6] - e[5] == 2u && buf[e[5] + 1u] == '*') done = true;             // REF:147-148
                     }
                 }
+                if (!slow && !done)
+                    slow = !small_uint(buf, e[6] + 1u, e[7], plen) || !small_uint(buf, e[7] + 1u, e[8], start) ||
+                           !small_uint(buf, e[8] + 1u, e[9], pend);
                 if (!slow && !done && no_tags) { slow = true; why = WHY_TAGS; }   // no dv tag: ValueError (REF:179), slow path reports
-                R.ls = (uint16_t)ls;
-                R.stB = (uint8_t)(slow ? ST_DEFER : (done ? ST_DONE : ST_FAST));
-                R.whyB = (uint8_t)why;
-            } else if (role == 1u) {
-                // ---------------- role P: coordinates, path column -> step-list entries
-                int why = WHY_INTS;
-                uint32_t e5 = 0, e6 = 0, e7 = 0, e8 = 0, e9 = 0;
-                // (a record that runs off the loaded bytes, or has no 12 columns, is role B's to hand over: stay quiet)
-                const bool have = skip_ws(wi, wmk, 4u) && next_ws(wm32, nhalf, wi, wmk, e5) && next_ws(wm32, nhalf, wi, wmk, e6) &&
-                                  next_ws(wm32, nhalf, wi, wmk, e7) && next_ws(wm32, nhalf, wi, wmk, e8) &&
-                                  next_ws(wm32, nhalf, wi, wmk, e9) && e6 > e5 + 1u;
-                bool slow = false;
-                int32_t plen = 0, start = 0, pend = 0;
-                uint32_t ns = 0, off = 0;
-                const uint32_t a5 = e5 + 1u, b5 = e6;
-                if (have) {
-                    slow = !small_uint(buf, e6 + 1u, e7, plen) || !small_uint(buf, e7 + 1u, e8, start) || !small_uint(buf, e8 + 1u, e9, pend);
-                    if (!slow) {
-                        // ---- path column (REF:185-197): it must start with a separator; count the steps
-                        why = WHY_PATH;
-                        for (uint32_t w = a5 >> 5; w <= ((b5 - 1u) >> 5); w++) ns += (uint32_t)__popc(sep_word(sm32, w, a5, b5));
-                        if (ns == 0u || ns > (uint32_t)MAX_STEPS || !((sm32[a5 >> 5] >> (a5 & 31u)) & 1u)) {
-                            slow = true;                                          // ('*': role B has said ST_DONE)
-                        } else {
-                            off = atomicAdd(&s_nsteps, ns + 1u);                  // any order: a record only needs a contiguous range
-                            if (off + ns + 1u > (uint32_t)G::STEP_CAP) {          // list full: slow path
-                                slow = true;
-                                why = WHY_STEPS_FULL;
-                                for (uint32_t i = off; i < (uint32_t)G::STEP_CAP; i++) steps[i] = SE_INVALID;
-                            }
+                // ---- path column (REF:185-197): it must start with a separator; count the steps
+                uint32_t ns = 0, off = 0, a5 = 0, b5 = 0;
+                if (!slow && !done) {
+                    why = WHY_PATH;
+                    a5 = e[5] + 1u;
+                    b5 = e[6];
+                    for (uint32_t w = a5 >> 5; w <= ((b5 - 1u) >> 5); w++) ns += (uint32_t)__popc(sep_word(sm32, w, a5, b5));
+                    if (ns == 0u || ns > (uint32_t)MAX_STEPS || !((sm32[a5 >> 5] >> (a5 & 31u)) & 1u)) {
+                        slow = true;
+                    } else {
+                        off = atomicAdd(&s_nsteps, ns + 1u);                      // any order: a record only needs a contiguous range
+                        if (off + ns + 1u > (uint32_t)G::STEP_CAP) {              // list full: slow path
+                            slow = true;
+                            why = WHY_STEPS_FULL;
+                            for (uint32_t i = off; i < (uint32_t)G::STEP_CAP; i++) steps[i] = SE_INVALID;
                         }
                     }
                 }
-                R.stP = (uint8_t)(slow ? ST_DEFER : ST_FAST);
-                R.whyP = (uint8_t)why;
+                st = slow ? ST_DEFER : (done ? ST_DONE : ST_FAST);
+                R.ls = (uint16_t)ls;
+                R.stB = (uint8_t)st;
+                R.whyB = (uint8_t)why;
                 R.nsteps = 0;
                 R.s0 = 0;
-                if (have && !slow) {
+                if (st == ST_FAST) {
                     R.start = start;
                     R.end_rel1 = plen - pend - 1;
                     R.s0 = (uint16_t)off;
@@ -488,27 +456,42 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                         while (m) {
                             const uint32_t q = 32u * w + (uint32_t)(__ffs((int)m) - 1);
                             m &= m - 1u;
-                            steps[i++] = q | common;
+                            steps[i] = q | common | (i == off ? SE_FIRST : 0u) | (i + 1u == off + ns ? SE_LAST : 0u);
+                            i++;
                         }
                     }
-                    steps[off] |= SE_FIRST;
-                    steps[off + ns - 1u] |= SE_LAST;
                     steps[off + ns] = b5 | (l << SE_SLOT_SHIFT) | SE_SENT;
                 }
-            } else if (role == 2u) {
-                // ---------------- role A: tags -> dv filter
-                uint32_t e12 = 0;
+            } else {
+                // ---------------- role A: tags -> dv filter, cs ops
+                uint32_t e11 = 0, e12 = 0;
+                bool ran_off = false;
+                // the first ten column boundaries are role B's business: skip them a half word at a time
+                uint32_t skip = 10;
+                for (;;) {
+                    const uint32_t c = (uint32_t)__popc(wmk);
+                    if (c > skip) break;
+                    skip -= c;
+                    if (++wi >= 2u * nwords) { ran_off = true; break; }
+                    wmk = wm32[wi];
+                }
+                for (; skip != 0u && !ran_off; skip--) wmk &= wmk - 1u;
+                if (!ran_off && !next_ws(wm32, 2u * nwords, wi, wmk, e11)) ran_off = true;
+                if (!ran_off && !next_ws(wm32, 2u * nwords, wi, wmk, e12)) ran_off = true;
+                // role B decides about everything up to column 12; here: is there anything left to do?
+                int32_t mapq = 0;
+                bool idle = ran_off || buf[e12] != '\t' || !small_uint(buf, e11 + 1u, e12, mapq) || (int64_t)mapq < A.thr;
                 bool slow = false, done = false;
-                // no tags at all (or no 12 columns): role B's business
-                if (skip_ws(wi, wmk, 11u) && next_ws(wm32, nhalf, wi, wmk, e12) && buf[e12] == '\t') {
+                uint32_t cs_a = 0, cs_b = 0, dv_a = 0, dv_b = 0;
+                if (!idle) {
                     // ---- tags: [inert]* cs [inert]* dv in any order, within the first few tags
-                    bool cs_seen = false;
-                    uint32_t dv_a = 0, dv_b = 0;
+                    why = WHY_TAGS;
                     uint32_t a = e12 + 1u, b = 0;
-                    if (!next_ws(wm32, nhalf, wi, wmk, b)) slow = true;
+                    if (!next_ws(wm32, 2u * nwords, wi, wmk, b)) slow = true;
                     for (int j = 13; !slow; j++) {
-                        if (!cs_seen && b - a >= 3u && buf[a] == 'c' && buf[a + 1] == 's' && buf[a + 2] == ':') {
-                            cs_seen = true;                                       // role C parses it
+                        if (!cs_b && b - a >= 3u && buf[a] == 'c' && buf[a + 1] == 's' && buf[a + 2] == ':') {
+                            cs_a = a;
+                            cs_b = b;
                         } else if (!dv_b && b - a >= 6u && buf[a] == 'd' && buf[a + 1] == 'v' && buf[a + 2] == ':' &&
                                    buf[a + 3] == 'f' && buf[a + 4] == ':' && pt::is_digit(buf[a + 5]) &&
                                    no_colon(buf, a + 5u, b)) {
@@ -518,10 +501,10 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                             slow = true;
                             break;
                         }
-                        if (cs_seen && dv_b) break;
+                        if (cs_b && dv_b) break;
                         if (buf[b] == '\n' || j >= 18) { slow = true; break; }      // end of the record: a tag is missing
                         a = b + 1u;
-                        if (!next_ws(wm32, nhalf, wi, wmk, b)) { slow = true; break; }
+                        if (!next_ws(wm32, 2u * nwords, wi, wmk, b)) { slow = true; break; }
                     }
                     // ---- dv filter (REF:172-180).  The reference parses cs first, but that has no side effects and
                     //      cannot raise, so a record that dv filters out needs no cs class
@@ -533,102 +516,88 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                             done = true;
                         }
                     }
-                }
-                R.stA = (uint8_t)(slow ? ST_DEFER : (done ? ST_DONE : ST_FAST));
-                R.whyA = (uint8_t)WHY_TAGS;
-            } else {
-                // ---------------- role C: the cs string (REF:10-37): "cs:Z:" then ops spelled the way an aligner spells them:
-                //      ':'<digits>  '*'<2 letters>  '-'<letters>  '+'<letters>  '='<LETTERS>, every length >= 1
-                uint32_t e12 = 0, cs_a = 0, cs_b = 0;
-                bool slow = false;
-                if (skip_ws(wi, wmk, 11u) && next_ws(wm32, nhalf, wi, wmk, e12) && buf[e12] == '\t') {
-                    // the first token that starts with "cs:" among the first six tags (role A sees to it that no earlier
-                    // token could hold the reference's first "cs:" match)
-                    uint32_t a = e12 + 1u, b = 0;
-                    for (int j = 13; j <= 18; j++) {
-                        if (!next_ws(wm32, nhalf, wi, wmk, b)) break;
-                        if (b - a >= 3u && buf[a] == 'c' && buf[a + 1] == 's' && buf[a + 2] == ':') { cs_a = a; cs_b = b; break; }
-                        if (buf[b] == '\n') break;
-                        a = b + 1u;
-                    }
-                }
-                if (cs_b != 0u) {
-                    uint32_t n_tot = 0, nops = 0, op_off = 0;
-                    int32_t start_add = 0;
-                    if (cs_b - cs_a < 7u || buf[cs_a + 3] != 'Z' || buf[cs_a + 4] != ':') slow = true;
-                    uint32_t q = cs_a + 5u;
-                    uint64_t one;
-                    if (!slow && buf[q] == ':' && cs_b - q - 1u <= 7u && step_id(buf, q + 1u, cs_b - q - 1u, one) && one != 0u) {
-                        // cs:Z::<n> -- a perfect match
-                        op_off = atomicAdd(&s_nops, 1u);
-                        if (op_off < (uint32_t)G::OPS_CAP) ops[op_off] = OP_MATCH | ((uint32_t)one << 3);
-                        else slow = true;
-                        nops = 1;
-                        n_tot = (uint32_t)one;
-                    } else if (!slow) {
-                        // every op takes at least two bytes: room for (bytes / 2) ops is enough
-                        const uint32_t room = min((cs_b - q) >> 1, (uint32_t)MAX_OPS);
-                        op_off = atomicAdd(&s_nops, room);
-                        if (op_off + room > (uint32_t)G::OPS_CAP) slow = true;
-                        while (!slow && q < cs_b) {
-                            const uint32_t c = buf[q++];
-                            uint32_t kind, len = 0;
-                            if (c == ':') {
-                                kind = OP_MATCH;
-                                uint32_t nd = 0;
-                                while (q < cs_b && pt::is_digit(buf[q])) { len = len * 10u + (buf[q] - '0'); q++; nd++; }
-                                if (nd == 0u || nd > 7u) slow = true;
-                            } else if (c == '*') {
-                                kind = OP_SUB;
-                                if (q + 2u > cs_b || !is_lower(buf[q]) || !is_lower(buf[q + 1])) slow = true;
-                                q += 2u;
-                                len = 1;
-                            } else if (c == '-' || c == '+') {
-                                kind = c == '-' ? OP_DEL : OP_INS;
-                                while (q < cs_b && is_lower(buf[q])) { q++; len++; }
-                            } else if (c == '=') {
-                                kind = OP_EQ;
-                                while (q < cs_b && buf[q] - 'A' <= 24u) { q++; len++; }      // 'A'..'Y': "cs:Z:" cannot hide in here
-                            } else {
-                                slow = true;
-                                kind = 0;
+                    // ---- cs string (REF:10-37): "cs:Z:" then ops spelled the way an aligner spells them:
+                    //      ':'<digits>  '*'<2 letters>  '-'<letters>  '+'<letters>  '='<LETTERS>, every length >= 1
+                    if (!slow && !done) {
+                        why = WHY_CS;
+                        uint32_t n_tot = 0, nops = 0, op_off = 0;
+                        int32_t start_add = 0;
+                        if (cs_b - cs_a < 7u || buf[cs_a + 3] != 'Z' || buf[cs_a + 4] != ':') slow = true;
+                        uint32_t q = cs_a + 5u;
+                        uint64_t one;
+                        if (!slow && buf[q] == ':' && cs_b - q - 1u <= 7u && step_id(buf, q + 1u, cs_b - q - 1u, one) && one != 0u) {
+                            // cs:Z::<n> -- a perfect match
+                            op_off = atomicAdd(&s_nops, 1u);
+                            if (op_off < (uint32_t)G::OPS_CAP) ops[op_off] = OP_MATCH | ((uint32_t)one << 3);
+                            else slow = true;
+                            nops = 1;
+                            n_tot = (uint32_t)one;
+                        } else if (!slow) {
+                            // every op takes at least two bytes: room for (bytes / 2) ops is enough
+                            const uint32_t room = min((cs_b - q) >> 1, (uint32_t)MAX_OPS);
+                            op_off = atomicAdd(&s_nops, room);
+                            if (op_off + room > (uint32_t)G::OPS_CAP) slow = true;
+                            while (!slow && q < cs_b) {
+                                const uint32_t c = buf[q++];
+                                uint32_t kind, len = 0;
+                                if (c == ':') {
+                                    kind = OP_MATCH;
+                                    uint32_t nd = 0;
+                                    while (q < cs_b && pt::is_digit(buf[q])) { len = len * 10u + (buf[q] - '0'); q++; nd++; }
+                                    if (nd == 0u || nd > 7u) slow = true;
+                                } else if (c == '*') {
+                                    kind = OP_SUB;
+                                    if (q + 2u > cs_b || !is_lower(buf[q]) || !is_lower(buf[q + 1])) slow = true;
+                                    q += 2u;
+                                    len = 1;
+                                } else if (c == '-' || c == '+') {
+                                    kind = c == '-' ? OP_DEL : OP_INS;
+                                    while (q < cs_b && is_lower(buf[q])) { q++; len++; }
+                                } else if (c == '=') {
+                                    kind = OP_EQ;
+                                    while (q < cs_b && buf[q] - 'A' <= 24u) { q++; len++; }      // 'A'..'Y': "cs:Z:" cannot hide in here
+                                } else {
+                                    slow = true;
+                                    kind = 0;
+                                }
+                                // the text must end where the next op starts
+                                if (q < cs_b) {
+                                    const uint32_t d = buf[q];
+                                    if (d != ':' && d != '*' && d != '-' && d != '+' && d != '=') slow = true;
+                                }
+                                if (len == 0u || len > (uint32_t)MAX_NTOT || nops >= room) slow = true;
+                                if (!slow) {
+                                    ops[op_off + nops] = kind | (len << 3);
+                                    nops++;
+                                    n_tot += len;
+                                    if (n_tot > (uint32_t)MAX_NTOT) slow = true;
+                                }
                             }
-                            // the text must end where the next op starts
-                            if (q < cs_b) {
-                                const uint32_t d = buf[q];
-                                if (d != ':' && d != '*' && d != '-' && d != '+' && d != '=') slow = true;
-                            }
-                            if (len == 0u || len > (uint32_t)MAX_NTOT || nops >= room) slow = true;
-                            if (!slow) {
-                                ops[op_off + nops] = kind | (len << 3);
-                                nops++;
-                                n_tot += len;
-                                if (n_tot > (uint32_t)MAX_NTOT) slow = true;
-                            }
-                        }
-                        if (nops == 0u) slow = true;
-                        // cigar_clipping (REF:40-50): only when there are exactly two ops
-                        if (!slow && nops == 2u) {
-                            const uint32_t o0 = ops[op_off], o1 = ops[op_off + 1u];
-                            if ((o0 & 7u) == OP_INS && (o1 & 7u) == OP_MATCH) {
-                                start_add = (int32_t)(o0 >> 3);
-                                ops[op_off] = o1;
-                                nops = 1;
-                                n_tot = o1 >> 3;
-                            } else if ((o0 & 7u) == OP_MATCH && (o1 & 7u) == OP_INS) {
-                                nops = 1;
-                                n_tot = o0 >> 3;
+                            if (nops == 0u) slow = true;
+                            // cigar_clipping (REF:40-50): only when there are exactly two ops
+                            if (!slow && nops == 2u) {
+                                const uint32_t o0 = ops[op_off], o1 = ops[op_off + 1u];
+                                if ((o0 & 7u) == OP_INS && (o1 & 7u) == OP_MATCH) {
+                                    start_add = (int32_t)(o0 >> 3);
+                                    ops[op_off] = o1;
+                                    nops = 1;
+                                    n_tot = o1 >> 3;
+                                } else if ((o0 & 7u) == OP_MATCH && (o1 & 7u) == OP_INS) {
+                                    nops = 1;
+                                    n_tot = o0 >> 3;
+                                }
                             }
                         }
+                        R.n_tot = n_tot;
+                        R.op_off = (uint16_t)op_off;
+                        R.nops = (uint8_t)nops;
+                        R.start_add = start_add;
                     }
-                    R.n_tot = n_tot;
-                    R.op_off = (uint16_t)op_off;
-                    R.nops = (uint8_t)nops;
-                    R.start_add = start_add;
                 }
-                R.stC = (uint8_t)(slow ? ST_DEFER : ST_FAST);
+                st = slow ? ST_DEFER : (done ? ST_DONE : ST_FAST);
+                R.stA = (uint8_t)st;
+                R.whyA = (uint8_t)why;
             }
-        }
         }
         __syncthreads();                                                    // ---- records, ops, step list complete
         const uint32_t n_ent = min(s_nsteps, (uint32_t)G::STEP_CAP);       // step entries incl. sentinels
@@ -807,7 +776,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         __syncthreads();                                                    // ---- every hand-over decision is made; nothing counted so far
         for (uint32_t l = tid; l < n_lines; l += THREADS) {
             const LineRecF& R = recs[l];
-            if (rec_status(R) == ST_DEFER) defer_line(T, t0 + R.ls - 16u, A.file_off, rec_why(R));
+            if (rec_status(R) == ST_DEFER) defer_line(T, t0 + R.ls - 16u, A.file_off, R.stB == ST_DEFER ? R.whyB : R.whyA);
         }
 
         // surviving neighbours of step s inside its record (dropped nodes are skipped)
