@@ -73,7 +73,7 @@ struct ChunkArgs {
     uint32_t over;       // look-ahead bytes after the tile, multiple of 16
     uint32_t list_cap;   // line-start slots in shared memory
     uint32_t n_tiles;
-    uint32_t stream_hint;   // 1: load the GAF with an L2 evict-first policy
+    uint32_t stream_hint;   // bit 0: load the GAF with an L2 evict-first policy; bit 1: count cycles per phase (diagnostics)
 };
 
 // why a record is handed to the slow path (pt_debug_counters)

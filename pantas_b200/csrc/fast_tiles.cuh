@@ -256,6 +256,16 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
     __syncthreads();
 
     DevSink sink(T);
+    // diagnostics (PANTAS_PHASE_CLOCKS=1): cycles thread 0 spends between the barriers = wall cycles of the CTA per phase
+    const bool phase_clk = (A.stream_hint & 2u) != 0u && tid == 0;
+    long long t_prev = phase_clk ? clock64() : 0;
+    auto phase_done = [&](int k) {
+        if (phase_clk) {
+            const long long now = clock64();
+            atomicAdd(&T.sc[SC_PHASE + k], (unsigned long long)(now - t_prev));
+            t_prev = now;
+        }
+    };
     const uint64_t nbytes16 = (A.nbytes + 15ull) & ~15ull;
     uint32_t parity = 0;
     unsigned long long my_lines = 0, my_tiles = 0;
@@ -267,7 +277,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         const uint32_t bytes = (uint32_t)(hi - lo);
         fence_async_smem();
         mbar_expect_tx(&mbar, bytes);
-        if (A.stream_hint) tma_load_1d_stream(buf + (tile ? 0u : 16u), A.gaf + lo, bytes, &mbar);
+        if (A.stream_hint & 1u) tma_load_1d_stream(buf + (tile ? 0u : 16u), A.gaf + lo, bytes, &mbar);
         else tma_load_1d(buf + (tile ? 0u : 16u), A.gaf + lo, bytes, &mbar);
     };
 
@@ -284,6 +294,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         const uint32_t nvec = (lim + 15u) >> 4, nwords = (nvec + 3u) >> 2;
         mbar_wait(&mbar, parity);
         parity ^= 1;
+        phase_done(0);
 
         // ================= scan: whitespace / separator masks, record starts =================
         for (uint32_t g = tid; g < nwords; g += THREADS) {
@@ -347,6 +358,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             }
         }
         __syncthreads();                                                    // ---- masks + record list complete
+        phase_done(1);
         const uint32_t n_lines_all = s_nlines;
         if (tid == 0) { my_lines += n_lines_all; my_tiles++; }
 
@@ -600,6 +612,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             }
         }
         __syncthreads();                                                    // ---- records, ops, step list complete
+        phase_done(2);
         const uint32_t n_ent = min(s_nsteps, (uint32_t)G::STEP_CAP);       // step entries incl. sentinels
         if (tid == 0) s_nlines = 0;                                         // everyone has read it
 
@@ -636,6 +649,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             }
         }
         __syncthreads();                                                    // ---- node indices complete; the bytes and the masks are dead
+        phase_done(3);
         if (tid == 0) {
             s_nsteps = 0;
             s_nops = 0;
@@ -691,6 +705,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             }
         }
         __syncthreads();                                                    // ---- prefix sums, record bases, duplicate / unknown ids known
+        phase_done(4);
 
         // ================= walk 2: every step folds the cs ops that overlap its node =================
         for (uint32_t s = tid; s < n_ent; s += THREADS) {
@@ -774,6 +789,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             }
         }
         __syncthreads();                                                    // ---- every hand-over decision is made; nothing counted so far
+        phase_done(5);
         for (uint32_t l = tid; l < n_lines; l += THREADS) {
             const LineRecF& R = recs[l];
             if (rec_status(R) == ST_DEFER) defer_line(T, t0 + R.ls - 16u, A.file_off, R.stB == ST_DEFER ? R.whyB : R.whyA);
@@ -860,6 +876,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             }
         }
         __syncthreads();                                                    // ---- far-link list complete
+        phase_done(6);
         {
             const uint32_t n_far = min(s_nfar, (uint32_t)G::FAR_CAP);
             for (uint32_t j = tid; j < n_far; j += THREADS)
@@ -889,6 +906,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         // no barrier here: the next tile's scan writes the masks (= the two lists, nobody reads them any more
         // once its first barrier is passed ... which every thread reaches only after finishing the loops above)
         __syncthreads();
+        phase_done(7);
     }
 
     // rejected-record count: warp reduce, one RED per warp

@@ -519,6 +519,7 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
     {   // measured: -4 % kernel time, -25 % DRAM reads (PANTAS_STREAM_HINT=0 switches it off)
         const char* h = getenv("PANTAS_STREAM_HINT");
         A.stream_hint = (h && h[0] == '0') ? 0u : 1u;
+        if (env_u32("PANTAS_PHASE_CLOCKS", 0)) A.stream_hint |= 2u;       // diagnostics: per-phase cycle counters (pt_debug_counters)
     }
     const uint64_t n_tiles = (nbytes + ctx->tile - 1) / ctx->tile;
     if (n_tiles > 0xFFFFFFF0ull) return fail_msg(ctx, PT_ERR_ARG, "chunk too large");
@@ -786,7 +787,7 @@ int pt_debug_counters(pt_ctx* ctx, uint64_t* out, int n) {
     unsigned long long sc[SC_COUNT];
     CK(cudaMemcpyAsync(sc, ctx->T.sc, sizeof sc, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (int k = 0; k < n; k++) out[k] = k < 16 ? sc[SC_WHY + k] : 0;
+    for (int k = 0; k < n; k++) out[k] = k < 32 ? sc[SC_WHY + k] : 0;      // 16 hand-over reasons, then 16 phase clocks
     return 0;
 }
 

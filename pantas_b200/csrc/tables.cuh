@@ -57,7 +57,7 @@ struct __align__(32) SideSlot {
 
 // device scalars (unsigned long long each)
 enum { SC_REJ = 0, SC_LINES, SC_ERR, SC_NOVEL_USED, SC_SPARSE_USED, SC_DEFERRED_TOTAL, SC_TILES, SC_TILE_NEXT, SC_NDEFER,
-       SC_WHY = 16 /* 16 hand-over reasons */, SC_COUNT = 32 };
+       SC_WHY = 16 /* 16 hand-over reasons */, SC_PHASE = 32 /* 16 phase clocks (diagnostics) */, SC_COUNT = 48 };
 
 struct Tables {
     NodeRec* nodes;

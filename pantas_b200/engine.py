@@ -171,6 +171,14 @@ class AugmentEngine:
         self._check(self.lib.pt_debug_counters(self._ctx, out, 16))
         return {k: int(out[i]) for i, k in enumerate(self.WHY)}
 
+    PHASES = ("wait_tma", "scan", "records", "ids", "walk1", "walk2", "count", "lists_end")
+
+    def phase_cycles(self) -> dict:
+        """Cycles per phase of the fast path summed over CTAs (diagnostics; needs PANTAS_PHASE_CLOCKS=1)."""
+        out = (ctypes.c_uint64 * 32)()
+        self._check(self.lib.pt_debug_counters(self._ctx, out, 32))
+        return {k: int(out[16 + i]) for i, k in enumerate(self.PHASES)}
+
     def kernel_time_split(self):
         """(ms fast-path kernel, ms per-record kernel, launches) since the last call."""
         a, b, n = ctypes.c_float(), ctypes.c_float(), ctypes.c_uint64()

@@ -181,6 +181,7 @@ inline unsigned __ballot_sync(unsigned, int pred) {
 }
 
 // ---- intrinsics
+inline long long clock64() { return 0; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }

@@ -44,3 +44,7 @@ f, sl, nn = eng.kernel_time_split()
 print(f"fast kernel {f / nn:.3f} ms, per-record kernel {sl / nn:.3f} ms (avg of {nn})")
 eng.check_data_error()
 print(eng.stats(), eng.handover_reasons())
+if os.environ.get("PANTAS_PHASE_CLOCKS"):
+    pc = eng.phase_cycles()
+    tot = sum(pc.values()) or 1
+    print("phase share of CTA time:", {k: round(100.0 * v / tot, 1) for k, v in pc.items()})
