@@ -85,11 +85,10 @@ struct Geo {
     static constexpr int FAR_CAP = (STEP_CAP / 8 + 31) & ~31;     // links that are not inline: typically 1-2 per record
     static constexpr int DEL_CAP = (LINE_CAP / 2 + 31) & ~31;     // steps with deletion-derived keys
     static constexpr int MASK_BYTES = 4 * NV;                     // whitespace + separator masks; dead after `records`:
-    static constexpr int LIST_BYTES = 12 * FAR_CAP + 12 * DEL_CAP;    // ... the two end-of-tile lists reuse the space
+    static constexpr int LIST_BYTES = 12 * DEL_CAP;                    // ... the list of deletion keys reuses the space
     static constexpr int OFF_WM = (BUF + 127) & ~127;
     static constexpr int OFF_SM = OFF_WM + 2 * NV;
-    static constexpr int OFF_FAR = OFF_WM;
-    static constexpr int OFF_DEL = OFF_WM + 12 * FAR_CAP;
+    static constexpr int OFF_DEL = OFF_WM;
     static constexpr int OFF_STEP = (OFF_WM + (MASK_BYTES > LIST_BYTES ? MASK_BYTES : LIST_BYTES) + 15) & ~15;
     static constexpr int OFF_SIDX = OFF_STEP + 4 * STEP_CAP;
     static constexpr int OFF_SINFO = OFF_SIDX + 4 * STEP_CAP;
@@ -101,6 +100,7 @@ struct Geo {
     static constexpr int REG = 1024 / THREADS < 1 ? 1 : 1024 / THREADS;               // ... leaving >= 64 registers per thread
     static constexpr int MIN_CTAS = FIT < 1 ? 1 : (FIT < REG ? FIT : REG);
     static_assert(BUF <= 65536, "step entries hold 16-bit positions");
+    static_assert(12 * FAR_CAP <= 4 * (STEP_CAP + 4), "the far-link list lives in the step-length prefix array");
     static_assert(LINE_CAP <= 512, "step entries hold 9-bit record slots");
     static_assert(STEP_CAP < 65536 && OPS_CAP < 65536, "records hold 16-bit list offsets");
 };
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
     constexpr uint32_t NWARPS = THREADS / 32;
     PT_DYNAMIC_SMEM(smem);
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t s_nlines, s_nsteps, s_nops, s_nfar, s_ndel;
+    __shared__ uint32_t s_nlines, s_nsteps, s_nops, s_nfar, s_ndel, s_far_next;
     __shared__ uint32_t s_wsum[NWARPS];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -236,7 +236,8 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
     unsigned long long* const sm64 = reinterpret_cast<unsigned long long*>(smem + G::OFF_SM);
     const uint32_t* const wm32 = reinterpret_cast<const uint32_t*>(smem + G::OFF_WM);   // the same masks, as half words
     const uint32_t* const sm32 = reinterpret_cast<const uint32_t*>(smem + G::OFF_SM);
-    uint32_t* const far = reinterpret_cast<uint32_t*>(smem + G::OFF_FAR);      // {from, to, separator position} (reuses the masks)
+    uint32_t* const far = reinterpret_cast<uint32_t*>(smem + G::OFF_SINFO);    // {from, to, separator position}: filled by `count`, when the step-length
+                                                                                 // prefix (same bytes) is dead; drained during the next tile's `records`
     uint32_t* const dels = reinterpret_cast<uint32_t*>(smem + G::OFF_DEL);     // {step, first del, last del}     (reuses the masks)
     uint32_t* const steps = reinterpret_cast<uint32_t*>(smem + G::OFF_STEP);
     uint32_t* const sidx = reinterpret_cast<uint32_t*>(smem + G::OFF_SIDX);
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         s_nops = 0;
         s_nfar = 0;
         s_ndel = 0;
+        s_far_next = 0;
     }
     __syncthreads();
 
@@ -279,6 +281,18 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         mbar_expect_tx(&mbar, bytes);
         if (A.stream_hint & 1u) tma_load_1d_stream(buf + (tile ? 0u : 16u), A.gaf + lo, bytes, &mbar);
         else tma_load_1d(buf + (tile ? 0u : 16u), A.gaf + lo, bytes, &mbar);
+    };
+
+    // Links that are not inline (hash-table probes, one dependent L2 / DRAM round trip each) are listed by `count` and
+    // done one tile later, during `records`, by the warps that phase leaves idle: the probes cost no time of their own.
+    // Threads take entries from a shared counter; far_base = file offset of buf[0] of the tile that listed them.
+    auto drain_far = [&](int64_t far_base) {
+        const uint32_t n_far = min(s_nfar, (uint32_t)G::FAR_CAP);
+        for (;;) {
+            const uint32_t j = atomicAdd(&s_far_next, 1u);
+            if (j >= n_far) break;
+            sink.edge_far(far[3u * j], far[3u * j + 1u], (uint64_t)(far_base + (int64_t)far[3u * j + 2u] + 1) << 2);
+        }
     };
 
     uint32_t tile = blockIdx.x;
@@ -368,9 +382,12 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 const bool nl = p == 15u ? (tile == 0 || buf[p] == '\n') : buf[p] == '\n';
                 if (nl) defer_line(T, t0 + p + 1u - 16u, A.file_off, WHY_LINES_FULL);
             }
+            drain_far(base_off - (int64_t)gridDim.x * G::TILE);            // the previous tile's far links (normally done in `records`)
             __syncthreads();
             if (tid == 0) {
                 s_nlines = 0;
+                s_nfar = 0;
+                s_far_next = 0;
                 const uint32_t nxt = tile + gridDim.x;
                 if (nxt < A.n_tiles) issue_load(nxt);
             }
@@ -611,7 +628,8 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 R.whyA = (uint8_t)why;
             }
         }
-        __syncthreads();                                                    // ---- records, ops, step list complete
+        drain_far(base_off - (int64_t)gridDim.x * G::TILE);                // idle warps at once, the others when their records are done
+        __syncthreads();                                                    // ---- records, ops, step list complete; the far-link list is empty
         phase_done(2);
         const uint32_t n_ent = min(s_nsteps, (uint32_t)G::STEP_CAP);       // step entries incl. sentinels
         if (tid == 0) s_nlines = 0;                                         // everyone has read it
@@ -653,7 +671,8 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         if (tid == 0) {
             s_nsteps = 0;
             s_nops = 0;
-            s_nfar = 0;
+            s_nfar = 0;                                                     // (drained during `records`)
+            s_far_next = 0;
             s_ndel = 0;
             const uint32_t nxt = tile + gridDim.x;
             if (nxt < A.n_tiles) issue_load(nxt);                           // overlaps walk + count
@@ -878,9 +897,6 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         __syncthreads();                                                    // ---- far-link list complete
         phase_done(6);
         {
-            const uint32_t n_far = min(s_nfar, (uint32_t)G::FAR_CAP);
-            for (uint32_t j = tid; j < n_far; j += THREADS)
-                sink.edge_far(far[3u * j], far[3u * j + 1u], (uint64_t)(base_off + (int64_t)far[3u * j + 2u] + 1) << 2);
             // deletion-derived keys: position of the deletion inside the node, IL or OL by orientation
             const uint32_t n_del = min(s_ndel, (uint32_t)G::DEL_CAP);
             for (uint32_t j = tid; j < n_del; j += THREADS) {
@@ -908,6 +924,8 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         __syncthreads();
         phase_done(7);
     }
+
+    drain_far(A.file_off + (int64_t)(tile - gridDim.x) * G::TILE - 16);    // the last tile's far links
 
     // rejected-record count: warp reduce, one RED per warp
     uint32_t r = sink.rej;
