@@ -39,6 +39,9 @@
 namespace fastp {
 
 constexpr uint32_t NONE32 = 0xffffffffu;
+// sidx[] entry: node index in the low 30 bits (larger indices: slow path), two flags on top: could this tile still lower the
+// node's IL / OL first-touch stamp?  (NONE32: no such node)
+constexpr uint32_t SX_IDX_MASK = 0x3FFFFFFFu, SX_NEED_IL = 1u << 30, SX_NEED_OL = 1u << 31;
 constexpr int MAX_STEPS = 250;                // longer paths take the slow path
 constexpr int MAX_OPS = 48;                   // more cs ops: slow path
 constexpr uint32_t L_CLAMP = 1u << 23;        // step lengths are clamped here (> any cs length the fast path takes)
@@ -92,7 +95,8 @@ struct Geo {
     static constexpr int OFF_STEP = (OFF_WM + (MASK_BYTES > LIST_BYTES ? MASK_BYTES : LIST_BYTES) + 15) & ~15;
     static constexpr int OFF_SIDX = OFF_STEP + 4 * STEP_CAP;
     static constexpr int OFF_SINFO = OFF_SIDX + 4 * STEP_CAP;
-    static constexpr int OFF_OPS = OFF_SINFO + 4 * (STEP_CAP + 4);
+    static constexpr int OFF_SD01 = OFF_SINFO + 4 * (STEP_CAP + 4);   // inline link deltas of every step's node
+    static constexpr int OFF_OPS = OFF_SD01 + 4 * STEP_CAP;
     static constexpr int OFF_LINES = OFF_OPS + 4 * OPS_CAP;
     static constexpr int OFF_REC = (OFF_LINES + 2 * LINE_CAP + 7) & ~7;
     static constexpr int SMEM_BYTES = (OFF_REC + (int)sizeof(LineRecF) * LINE_CAP + 127) & ~127;
@@ -242,6 +246,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
     uint32_t* const steps = reinterpret_cast<uint32_t*>(smem + G::OFF_STEP);
     uint32_t* const sidx = reinterpret_cast<uint32_t*>(smem + G::OFF_SIDX);
     uint32_t* const sinfo = reinterpret_cast<uint32_t*>(smem + G::OFF_SINFO);  // step-length prefix
+    uint32_t* const sd01 = reinterpret_cast<uint32_t*>(smem + G::OFF_SD01);    // NodeRec.d01 of the step's node (from `ids`: `count` loads nothing)
     uint32_t* const ops = reinterpret_cast<uint32_t*>(smem + G::OFF_OPS);
     uint16_t* const lines = reinterpret_cast<uint16_t*>(smem + G::OFF_LINES);
     LineRecF* const recs = reinterpret_cast<LineRecF*>(smem + G::OFF_REC);
@@ -634,13 +639,18 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         const uint32_t n_ent = min(s_nsteps, (uint32_t)G::STEP_CAP);       // step entries incl. sentinels
         if (tid == 0) s_nlines = 0;                                         // everyone has read it
 
-        // ================= ids: one thread per path step: id -> node index, node length =================
-        // UI steps per thread and iteration: their node-record loads are all in flight before the first is stored
-        // (the load also brings the node's sector into L2 for the count phase).  `sinfo` holds the lengths until walk 1.
+        // ================= ids: one thread per path step: id -> node index, the node record's read half =================
+        // UI steps per thread and iteration: their node-record loads (one 16-byte LDG each) are all in flight before the
+        // first is stored.  Everything the later phases need of the record is kept in shared memory -- length (sinfo, until
+        // walk 1), inline link deltas (sd01), and whether this tile could still lower a first-touch stamp (two flag bits in
+        // sidx; stamps only decrease, so an older value only errs towards one RED.MIN too many): `count` loads nothing.
         {
             constexpr int UI = 4;
+            const int64_t rel0 = base_off + 16 - T.epoch_base;              // below every stamp this tile can produce
+            const uint32_t rel_tile = rel0 < 0 ? 0u : (uint32_t)rel0;
             for (uint32_t s00 = 0; s00 < n_ent; s00 += THREADS * UI) {
-                uint32_t idx_[UI], len_[UI];
+                uint32_t idx_[UI];
+                DevSink::Hot hot_[UI];
 #pragma unroll
                 for (int u = 0; u < UI; u++) {
                     const uint32_t s = s00 + THREADS * u + tid;
@@ -652,17 +662,27 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                             const uint32_t end = steps[s + 1u] & SE_POS_MASK;       // next separator, or the sentinel
                             uint64_t id;
                             uint32_t ix;
-                            if (buf[p] == ((se & SE_REV) ? '<' : '>') && step_id(buf, p + 1u, end - p - 1u, id) && sink.id_to_idx(id, ix)) idx = ix;
+                            if (buf[p] == ((se & SE_REV) ? '<' : '>') && step_id(buf, p + 1u, end - p - 1u, id) && sink.id_to_idx(id, ix) &&
+                                ix < SX_IDX_MASK)
+                                idx = ix;
                         }
                     }
                     idx_[u] = idx;                                          // NONE32: KeyError in the reference, `walk` hands the record over
                 }
 #pragma unroll
-                for (int u = 0; u < UI; u++) len_[u] = idx_[u] != NONE32 ? sink.load_len(idx_[u]) : 0u;
+                for (int u = 0; u < UI; u++) {
+                    hot_[u].len = 0; hot_[u].il = 0; hot_[u].ol = 0; hot_[u].d01 = 0;
+                    if (idx_[u] != NONE32) hot_[u] = sink.load_hot(idx_[u]);
+                }
 #pragma unroll
                 for (int u = 0; u < UI; u++) {
                     const uint32_t s = s00 + THREADS * u + tid;
-                    if (s < n_ent) { sidx[s] = idx_[u]; sinfo[s] = len_[u]; }
+                    if (s < n_ent) {
+                        sidx[s] = idx_[u] == NONE32 ? NONE32
+                                                    : (idx_[u] | (hot_[u].il > rel_tile ? SX_NEED_IL : 0u) | (hot_[u].ol > rel_tile ? SX_NEED_OL : 0u));
+                        sinfo[s] = hot_[u].len;
+                        sd01[s] = hot_[u].d01;
+                    }
                 }
             }
         }
@@ -692,7 +712,8 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                         const uint32_t idx = sidx[s];
                         const uint32_t len = sinfo[s];                      // left there by `ids`
                         // unknown id: KeyError (REF:214); collapsible duplicate (REF:188): the slow path redoes the record
-                        if (idx == NONE32 || len == pt::NODE_LEN_ABSENT || (!(se & SE_FIRST) && idx == sidx[s - 1u])) {
+                        if (idx == NONE32 || len == pt::NODE_LEN_ABSENT ||
+                            (!(se & SE_FIRST) && sidx[s - 1u] != NONE32 && (idx & SX_IDX_MASK) == (sidx[s - 1u] & SX_IDX_MASK))) {
                             R.stB = ST_DEFER;
                             R.whyB = WHY_WALK;
                         } else {
@@ -833,32 +854,14 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         };
 
         // ================= count: one thread per surviving step =================
-        // UB steps per thread and iteration: their node-record loads (one 16-byte LDG each, L2 hits
-        // thanks to the prefetch) are all in flight before the first one is used.
+        // (no global loads here: `ids` left what is needed of the node records in shared memory)
         {
-            constexpr int UB = 2;
-            for (uint32_t s00 = 0; s00 < n_ent; s00 += THREADS * UB) {
-                uint32_t se_[UB], idx_[UB];
-                DevSink::Hot hot_[UB];
-#pragma unroll
-                for (int u = 0; u < UB; u++) {
-                    const uint32_t s = s00 + THREADS * u + tid;
-                    uint32_t se = s < n_ent ? steps[s] : SE_INVALID;
-                    if (se != SE_INVALID && ((se & (SE_SENT | SE_DROPPED)) || rec_status(recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK]) != ST_FAST))
-                        se = SE_INVALID;
-                    se_[u] = se;
-                    idx_[u] = 0;
-                    hot_[u].len = 0; hot_[u].il = 0; hot_[u].ol = 0; hot_[u].d01 = 0;
-                    if (se != SE_INVALID) {
-                        idx_[u] = sidx[s];
-                        hot_[u] = sink.load_hot(idx_[u]);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < UB; u++) {
-                    const uint32_t s = s00 + THREADS * u + tid;
-                    const uint32_t se = se_[u], idx = idx_[u];
-                    if (se == SE_INVALID) continue;
+            for (uint32_t s = tid; s < n_ent; s += THREADS) {
+                {
+                    const uint32_t se = steps[s];
+                    if (se == SE_INVALID || (se & (SE_SENT | SE_DROPPED)) || rec_status(recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK]) != ST_FAST)
+                        continue;
+                    const uint32_t sx = sidx[s], idx = sx & SX_IDX_MASK;
                     const bool rev = (se & SE_REV) != 0u;
                     const uint32_t ps = prev_survivor(s), nx = next_survivor(s);
                     const bool first = ps == NONE32, last = nx == NONE32;   // among the surviving nodes (REF:276-353: i == 0, i == last)
@@ -870,8 +873,8 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                     int eslot = -1;
                     uint32_t other = 0;
                     if (have_edge) {
-                        other = sidx[rev ? ps : nx];
-                        eslot = DevSink::inline_slot(hot_[u].d01, idx, other);
+                        other = sidx[rev ? ps : nx] & SX_IDX_MASK;
+                        eslot = DevSink::inline_slot(sd01[s], idx, other);
                     }
                     sink.bump(idx, eslot);                                              // REF:263-269, 357-363
                     if (have_edge && eslot < 0) {
@@ -887,10 +890,8 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                             sink.edge_far(idx, other, (uint64_t)(base_off + (int64_t)ep + 1) << 2);
                         }
                     }
-                    DevSink::Stamps st;
-                    st.il = hot_[u].il;
-                    st.ol = hot_[u].ol;
-                    sink.dense(idx, il_cond ? n_count : 0, ol_cond ? n_count : 0, stamp | 1u, st);   // REF:298-351
+                    sink.dense_flagged(idx, il_cond ? n_count : 0, ol_cond ? n_count : 0, stamp | 1u, (sx & SX_NEED_IL) != 0u,
+                                       (sx & SX_NEED_OL) != 0u);           // REF:298-351
                 }
             }
         }
@@ -903,7 +904,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 const uint32_t s = dels[3u * j], f = dels[3u * j + 1u], g = dels[3u * j + 2u];
                 const uint32_t se = steps[s];
                 if (rec_status(recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK]) != ST_FAST) continue;
-                const uint32_t idx = sidx[s];
+                const uint32_t idx = sidx[s] & SX_IDX_MASK;
                 const int64_t len = (int64_t)sink.load_len(idx);
                 const bool rev = (se & SE_REV) != 0u;
                 const bool not_first = prev_survivor(s) != NONE32, not_last = next_survivor(s) != NONE32;

@@ -197,6 +197,15 @@ struct DevSink {
         if (ol > 0 && rel < st.ol) atomicMin(&T.nodes[idx].ol_stamp, rel);
     }
 
+    // the same with the stamp test made by the caller (per tile: could this tile lower the stamp at all?)
+    __device__ __forceinline__ void dense_flagged(uint32_t idx, int64_t il, int64_t ol, uint64_t stamp, bool need_il, bool need_ol) {
+        if (il != 1) atomicAdd(&T.il_adj32[idx], (int32_t)(il - 1));
+        if (ol != 1) atomicAdd(&T.ol_adj32[idx], (int32_t)(ol - 1));
+        const uint32_t rel = (uint32_t)((int64_t)(stamp >> 2) - T.epoch_base);
+        if (il > 0 && need_il) atomicMin(&T.nodes[idx].il_stamp, rel);
+        if (ol > 0 && need_ol) atomicMin(&T.nodes[idx].ol_stamp, rel);
+    }
+
     // ---- the per-record interface of line_core.cuh (slow path)
     __device__ __forceinline__ void count_node(uint32_t idx) { atomicAdd(&T.nodes[idx].c0, 1ull); }
     __device__ __forceinline__ void sparse(uint32_t idx, int dir, int64_t pos, uint64_t stamp) {
