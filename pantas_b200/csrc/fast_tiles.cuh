@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
     constexpr uint32_t NWARPS = THREADS / 32;
     PT_DYNAMIC_SMEM(smem);
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t s_nlines, s_nsteps, s_nops, s_nfar, s_ndel, s_far_next, s_ncs;
+    __shared__ uint32_t s_nlines, s_nsteps, s_nops, s_nfar, s_ndel, s_far_next, s_ncs, s_a_done;
     __shared__ uint32_t s_wsum[NWARPS];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -262,7 +262,9 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         s_ndel = 0;
         s_far_next = 0;
         s_ncs = 0;
+        s_a_done = 0;
     }
+    for (uint32_t k = tid; k < (uint32_t)G::LINE_CAP; k += THREADS) cslist[3u * k] = 0;    // no entry published
     __syncthreads();
 
     DevSink sink(T);
@@ -481,6 +483,9 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         constexpr uint32_t RW = NWARPS / 2u;
         const bool roleA = warp >= RW;
         const uint32_t nrw = min((n_lines + 31u) >> 5, RW);                // warps per role in use
+        // cs strings that are not "cs:Z::<n>" (one read in eight): a warp pays for its slowest lane, so role A lists them and
+        // the last warp -- idle in this phase whenever a role does not need all its warps -- parses them meanwhile
+        const bool cs_async = nrw < RW;
         for (uint32_t l = 32u * (roleA ? warp - RW : warp) + lane; l < n_lines && (roleA ? warp - RW : warp) < nrw; l += 32u * nrw) {
             LineRecF& R = recs[l];
             const uint32_t ls = lines[l];
@@ -570,7 +575,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 }
             } else {
                 // ---------------- role A: tags -> dv filter, cs ops
-                uint32_t e11 = 0, e12 = 0;
+                uint32_t e11 = 0, e12 = 0, cs_q = 0, cs_e = 0;
                 bool ran_off = false;
                 // the first ten column boundaries are role B's business: skip them a half word at a time
                 uint32_t skip = 10;
@@ -639,16 +644,47 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                             R.nops = 1;
                             R.start_add = 0;
                         } else if (!slow) {
-                            const uint32_t k = atomicAdd(&s_ncs, 1u);      // < LINE_CAP: one entry per record at most
-                            cslist[3u * k] = (uint16_t)l;
-                            cslist[3u * k + 1u] = (uint16_t)q;
-                            cslist[3u * k + 2u] = (uint16_t)cs_b;
+                            cs_q = q;
+                            cs_e = cs_b;
                         }
                     }
                 }
                 st = slow ? ST_DEFER : (done ? ST_DONE : ST_FAST);
                 R.stA = (uint8_t)st;
                 R.whyA = (uint8_t)why;
+                if (cs_e != 0u) {                                           // a cs string that is not a perfect match (status written first:
+                    if (cs_async) {                                         //  the parser may raise it)
+                        const uint32_t k = atomicAdd(&s_ncs, 1u);          // < LINE_CAP: one entry per record at most
+                        cslist[3u * k + 1u] = (uint16_t)cs_q;
+                        cslist[3u * k + 2u] = (uint16_t)cs_e;
+                        __threadfence_block();
+                        *reinterpret_cast<volatile uint16_t*>(&cslist[3u * k]) = (uint16_t)(l | 0x8000u);   // published
+                    } else {
+                        parse_cs_general(R, cs_q, cs_e);
+                    }
+                }
+            }
+        }
+        if (cs_async) {
+            if (roleA && warp - RW < nrw) {                                 // a warp of role A is through with its records
+                __syncwarp();
+                if (lane == 0u) { __threadfence_block(); atomicAdd(&s_a_done, 1u); }
+            }
+            if (warp == NWARPS - 1u) {
+                for (uint32_t k = lane; k < (uint32_t)G::LINE_CAP; k += 32u) {
+                    uint32_t ent;
+                    for (;;) {
+                        ent = *reinterpret_cast<volatile uint16_t*>(&cslist[3u * k]);
+                        if (ent & 0x8000u) break;
+                        // nothing more will come once every warp of role A is done and entry k was never handed out
+                        if (*reinterpret_cast<volatile uint32_t*>(&s_a_done) >= nrw && k >= *reinterpret_cast<volatile uint32_t*>(&s_ncs)) { ent = 0; break; }
+                        spin_pause();
+                    }
+                    if (ent == 0u) break;
+                    __threadfence_block();
+                    parse_cs_general(recs[ent & 0x7FFFu], cslist[3u * k + 1u], cslist[3u * k + 2u]);
+                    cslist[3u * k] = 0;
+                }
             }
         }
         drain_far(base_off - (int64_t)gridDim.x * G::TILE);                // idle warps at once, the others when their records are done
@@ -656,12 +692,6 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         phase_done(2);
         const uint32_t n_ent = min(s_nsteps, (uint32_t)G::STEP_CAP);       // step entries incl. sentinels
         if (tid == 0) s_nlines = 0;                                         // everyone has read it
-
-        // the listed cs strings: the last warp, before its share of `ids` (the ops are not needed before walk 2)
-        if (warp == NWARPS - 1u) {
-            const uint32_t n_cs = s_ncs;
-            for (uint32_t k = lane; k < n_cs; k += 32u) parse_cs_general(recs[cslist[3u * k]], cslist[3u * k + 1u], cslist[3u * k + 2u]);
-        }
 
         // ================= ids: one thread per path step: id -> node index, the node record's read half =================
         // UI steps per thread and iteration: their node-record loads (one 16-byte LDG each) are all in flight before the
@@ -718,7 +748,8 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             s_nfar = 0;                                                     // (drained during `records`)
             s_far_next = 0;
             s_ndel = 0;
-            s_ncs = 0;                                                      // (parsed during `ids`)
+            s_ncs = 0;                                                      // (parsed during `records`)
+            s_a_done = 0;
             const uint32_t nxt = tile + gridDim.x;
             if (nxt < A.n_tiles) issue_load(nxt);                           // overlaps walk + count
         }
