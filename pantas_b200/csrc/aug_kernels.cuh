@@ -50,7 +50,6 @@ __device__ __forceinline__ void tma_load_1d_stream(void* dst_smem, const void* s
                  : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void spin_pause() { __nanosleep(32); }             // inside a wait on shared memory written by other warps
 #else   // ---- test harness: the bulk copy is a memcpy that has completed when it returns
 #define PT_DYNAMIC_SMEM(name) uint8_t* const name = emu::S().dyn
 // (*bar = number of completed phases; a waiter yields until the phase with its parity is complete)
@@ -63,8 +62,6 @@ inline void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, ui
 }
 inline void tma_load_1d_stream(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) { tma_load_1d(dst_smem, src_gmem, bytes, bar); }
 inline void fence_async_smem() {}
-inline void spin_pause() { emu::yield(); }
-inline void __threadfence_block() {}
 #endif
 
 struct ChunkArgs {

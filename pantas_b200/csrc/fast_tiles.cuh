@@ -99,8 +99,7 @@ struct Geo {
     static constexpr int OFF_OPS = OFF_SD01 + 4 * STEP_CAP;
     static constexpr int OFF_LINES = OFF_OPS + 4 * OPS_CAP;
     static constexpr int OFF_REC = (OFF_LINES + 2 * LINE_CAP + 7) & ~7;
-    static constexpr int OFF_CSL = (OFF_REC + (int)sizeof(LineRecF) * LINE_CAP + 7) & ~7;
-    static constexpr int SMEM_BYTES = (OFF_CSL + 6 * LINE_CAP + 127) & ~127;
+    static constexpr int SMEM_BYTES = (OFF_REC + (int)sizeof(LineRecF) * LINE_CAP + 127) & ~127;
     static constexpr int FIT = (227 * 1024) / (SMEM_BYTES + 1024);                    // CTAs per SM by shared memory
     static constexpr int REG = 1024 / THREADS < 1 ? 1 : 1024 / THREADS;               // ... leaving >= 64 registers per thread
     static constexpr int MIN_CTAS = FIT < 1 ? 1 : (FIT < REG ? FIT : REG);
@@ -232,7 +231,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
     constexpr uint32_t NWARPS = THREADS / 32;
     PT_DYNAMIC_SMEM(smem);
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t s_nlines, s_nsteps, s_nops, s_nfar, s_ndel, s_far_next, s_ncs, s_a_done;
+    __shared__ uint32_t s_nlines, s_nsteps, s_nops, s_nfar, s_ndel, s_far_next;
     __shared__ uint32_t s_wsum[NWARPS];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -251,7 +250,6 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
     uint32_t* const ops = reinterpret_cast<uint32_t*>(smem + G::OFF_OPS);
     uint16_t* const lines = reinterpret_cast<uint16_t*>(smem + G::OFF_LINES);
     LineRecF* const recs = reinterpret_cast<LineRecF*>(smem + G::OFF_REC);
-    uint16_t* const cslist = reinterpret_cast<uint16_t*>(smem + G::OFF_CSL);   // {record, first op, end} of the cs strings that are not "cs:Z::<n>"
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
@@ -261,10 +259,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         s_nfar = 0;
         s_ndel = 0;
         s_far_next = 0;
-        s_ncs = 0;
-        s_a_done = 0;
     }
-    for (uint32_t k = tid; k < (uint32_t)G::LINE_CAP; k += THREADS) cslist[3u * k] = 0;    // no entry published
     __syncthreads();
 
     DevSink sink(T);
@@ -303,75 +298,6 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             if (j >= n_far) break;
             sink.edge_far(far[3u * j], far[3u * j + 1u], (uint64_t)(far_base + (int64_t)far[3u * j + 2u] + 1) << 2);
         }
-    };
-
-    // cs strings other than "cs:Z::<n>" (REF:10-37): ops spelled the way an aligner spells them:
-    //   ':'<digits>  '*'<2 letters>  '-'<letters>  '+'<letters>  '='<LETTERS>, every length >= 1; cigar_clipping (REF:40-50)
-    auto parse_cs_general = [&](LineRecF& R, uint32_t q, const uint32_t cs_b) {
-        bool slow = false;
-        uint32_t n_tot = 0, nops = 0, op_off = 0;
-        int32_t start_add = 0;
-        {
-                            // every op takes at least two bytes: room for (bytes / 2) ops is enough
-                            const uint32_t room = min((cs_b - q) >> 1, (uint32_t)MAX_OPS);
-                            op_off = atomicAdd(&s_nops, room);
-                            if (op_off + room > (uint32_t)G::OPS_CAP) slow = true;
-                            while (!slow && q < cs_b) {
-                                const uint32_t c = buf[q++];
-                                uint32_t kind, len = 0;
-                                if (c == ':') {
-                                    kind = OP_MATCH;
-                                    uint32_t nd = 0;
-                                    while (q < cs_b && pt::is_digit(buf[q])) { len = len * 10u + (buf[q] - '0'); q++; nd++; }
-                                    if (nd == 0u || nd > 7u) slow = true;
-                                } else if (c == '*') {
-                                    kind = OP_SUB;
-                                    if (q + 2u > cs_b || !is_lower(buf[q]) || !is_lower(buf[q + 1])) slow = true;
-                                    q += 2u;
-                                    len = 1;
-                                } else if (c == '-' || c == '+') {
-                                    kind = c == '-' ? OP_DEL : OP_INS;
-                                    while (q < cs_b && is_lower(buf[q])) { q++; len++; }
-                                } else if (c == '=') {
-                                    kind = OP_EQ;
-                                    while (q < cs_b && buf[q] - 'A' <= 24u) { q++; len++; }      // 'A'..'Y': "cs:Z:" cannot hide in here
-                                } else {
-                                    slow = true;
-                                    kind = 0;
-                                }
-                                // the text must end where the next op starts
-                                if (q < cs_b) {
-                                    const uint32_t d = buf[q];
-                                    if (d != ':' && d != '*' && d != '-' && d != '+' && d != '=') slow = true;
-                                }
-                                if (len == 0u || len > (uint32_t)MAX_NTOT || nops >= room) slow = true;
-                                if (!slow) {
-                                    ops[op_off + nops] = kind | (len << 3);
-                                    nops++;
-                                    n_tot += len;
-                                    if (n_tot > (uint32_t)MAX_NTOT) slow = true;
-                                }
-                            }
-                            if (nops == 0u) slow = true;
-                            // cigar_clipping (REF:40-50): only when there are exactly two ops
-                            if (!slow && nops == 2u) {
-                                const uint32_t o0 = ops[op_off], o1 = ops[op_off + 1u];
-                                if ((o0 & 7u) == OP_INS && (o1 & 7u) == OP_MATCH) {
-                                    start_add = (int32_t)(o0 >> 3);
-                                    ops[op_off] = o1;
-                                    nops = 1;
-                                    n_tot = o1 >> 3;
-                                } else if ((o0 & 7u) == OP_MATCH && (o1 & 7u) == OP_INS) {
-                                    nops = 1;
-                                    n_tot = o0 >> 3;
-                                }
-                            }
-                        }
-        R.n_tot = n_tot;
-        R.op_off = (uint16_t)op_off;
-        R.nops = (uint8_t)nops;
-        R.start_add = start_add;
-        if (slow) { R.stA = ST_DEFER; R.whyA = (uint8_t)WHY_CS; }
     };
 
     uint32_t tile = blockIdx.x;
@@ -483,9 +409,6 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         constexpr uint32_t RW = NWARPS / 2u;
         const bool roleA = warp >= RW;
         const uint32_t nrw = min((n_lines + 31u) >> 5, RW);                // warps per role in use
-        // cs strings that are not "cs:Z::<n>" (one read in eight): a warp pays for its slowest lane, so role A lists them and
-        // the last warp -- idle in this phase whenever a role does not need all its warps -- parses them meanwhile
-        const bool cs_async = nrw < RW;
         for (uint32_t l = 32u * (roleA ? warp - RW : warp) + lane; l < n_lines && (roleA ? warp - RW : warp) < nrw; l += 32u * nrw) {
             LineRecF& R = recs[l];
             const uint32_t ls = lines[l];
@@ -575,7 +498,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 }
             } else {
                 // ---------------- role A: tags -> dv filter, cs ops
-                uint32_t e11 = 0, e12 = 0, cs_q = 0, cs_e = 0;
+                uint32_t e11 = 0, e12 = 0;
                 bool ran_off = false;
                 // the first ten column boundaries are role B's business: skip them a half word at a time
                 uint32_t skip = 10;
@@ -627,64 +550,87 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                             done = true;
                         }
                     }
-                    // ---- cs string (REF:10-37).  "cs:Z::<n>" (a perfect match, 85 % of the reads) is done here; any other
-                    //      string goes to a short list that ONE warp parses during `ids` (a warp pays for its slowest lane:
-                    //      one lane in eight with a long cs string would make every warp of this role run the op loop)
+                    // ---- cs string (REF:10-37): "cs:Z:" then ops spelled the way an aligner spells them:
+                    //      ':'<digits>  '*'<2 letters>  '-'<letters>  '+'<letters>  '='<LETTERS>, every length >= 1
                     if (!slow && !done) {
                         why = WHY_CS;
+                        uint32_t n_tot = 0, nops = 0, op_off = 0;
+                        int32_t start_add = 0;
                         if (cs_b - cs_a < 7u || buf[cs_a + 3] != 'Z' || buf[cs_a + 4] != ':') slow = true;
-                        const uint32_t q = cs_a + 5u;
+                        uint32_t q = cs_a + 5u;
                         uint64_t one;
                         if (!slow && buf[q] == ':' && cs_b - q - 1u <= 7u && step_id(buf, q + 1u, cs_b - q - 1u, one) && one != 0u) {
-                            const uint32_t op_off = atomicAdd(&s_nops, 1u);
+                            // cs:Z::<n> -- a perfect match
+                            op_off = atomicAdd(&s_nops, 1u);
                             if (op_off < (uint32_t)G::OPS_CAP) ops[op_off] = OP_MATCH | ((uint32_t)one << 3);
                             else slow = true;
-                            R.n_tot = (uint32_t)one;
-                            R.op_off = (uint16_t)op_off;
-                            R.nops = 1;
-                            R.start_add = 0;
+                            nops = 1;
+                            n_tot = (uint32_t)one;
                         } else if (!slow) {
-                            cs_q = q;
-                            cs_e = cs_b;
+                            // every op takes at least two bytes: room for (bytes / 2) ops is enough
+                            const uint32_t room = min((cs_b - q) >> 1, (uint32_t)MAX_OPS);
+                            op_off = atomicAdd(&s_nops, room);
+                            if (op_off + room > (uint32_t)G::OPS_CAP) slow = true;
+                            while (!slow && q < cs_b) {
+                                const uint32_t c = buf[q++];
+                                uint32_t kind, len = 0;
+                                if (c == ':') {
+                                    kind = OP_MATCH;
+                                    uint32_t nd = 0;
+                                    while (q < cs_b && pt::is_digit(buf[q])) { len = len * 10u + (buf[q] - '0'); q++; nd++; }
+                                    if (nd == 0u || nd > 7u) slow = true;
+                                } else if (c == '*') {
+                                    kind = OP_SUB;
+                                    if (q + 2u > cs_b || !is_lower(buf[q]) || !is_lower(buf[q + 1])) slow = true;
+                                    q += 2u;
+                                    len = 1;
+                                } else if (c == '-' || c == '+') {
+                                    kind = c == '-' ? OP_DEL : OP_INS;
+                                    while (q < cs_b && is_lower(buf[q])) { q++; len++; }
+                                } else if (c == '=') {
+                                    kind = OP_EQ;
+                                    while (q < cs_b && buf[q] - 'A' <= 24u) { q++; len++; }      // 'A'..'Y': "cs:Z:" cannot hide in here
+                                } else {
+                                    slow = true;
+                                    kind = 0;
+                                }
+                                // the text must end where the next op starts
+                                if (q < cs_b) {
+                                    const uint32_t d = buf[q];
+                                    if (d != ':' && d != '*' && d != '-' && d != '+' && d != '=') slow = true;
+                                }
+                                if (len == 0u || len > (uint32_t)MAX_NTOT || nops >= room) slow = true;
+                                if (!slow) {
+                                    ops[op_off + nops] = kind | (len << 3);
+                                    nops++;
+                                    n_tot += len;
+                                    if (n_tot > (uint32_t)MAX_NTOT) slow = true;
+                                }
+                            }
+                            if (nops == 0u) slow = true;
+                            // cigar_clipping (REF:40-50): only when there are exactly two ops
+                            if (!slow && nops == 2u) {
+                                const uint32_t o0 = ops[op_off], o1 = ops[op_off + 1u];
+                                if ((o0 & 7u) == OP_INS && (o1 & 7u) == OP_MATCH) {
+                                    start_add = (int32_t)(o0 >> 3);
+                                    ops[op_off] = o1;
+                                    nops = 1;
+                                    n_tot = o1 >> 3;
+                                } else if ((o0 & 7u) == OP_MATCH && (o1 & 7u) == OP_INS) {
+                                    nops = 1;
+                                    n_tot = o0 >> 3;
+                                }
+                            }
                         }
+                        R.n_tot = n_tot;
+                        R.op_off = (uint16_t)op_off;
+                        R.nops = (uint8_t)nops;
+                        R.start_add = start_add;
                     }
                 }
                 st = slow ? ST_DEFER : (done ? ST_DONE : ST_FAST);
                 R.stA = (uint8_t)st;
                 R.whyA = (uint8_t)why;
-                if (cs_e != 0u) {                                           // a cs string that is not a perfect match (status written first:
-                    if (cs_async) {                                         //  the parser may raise it)
-                        const uint32_t k = atomicAdd(&s_ncs, 1u);          // < LINE_CAP: one entry per record at most
-                        cslist[3u * k + 1u] = (uint16_t)cs_q;
-                        cslist[3u * k + 2u] = (uint16_t)cs_e;
-                        __threadfence_block();
-                        *reinterpret_cast<volatile uint16_t*>(&cslist[3u * k]) = (uint16_t)(l | 0x8000u);   // published
-                    } else {
-                        parse_cs_general(R, cs_q, cs_e);
-                    }
-                }
-            }
-        }
-        if (cs_async) {
-            if (roleA && warp - RW < nrw) {                                 // a warp of role A is through with its records
-                __syncwarp();
-                if (lane == 0u) { __threadfence_block(); atomicAdd(&s_a_done, 1u); }
-            }
-            if (warp == NWARPS - 1u) {
-                for (uint32_t k = lane; k < (uint32_t)G::LINE_CAP; k += 32u) {
-                    uint32_t ent;
-                    for (;;) {
-                        ent = *reinterpret_cast<volatile uint16_t*>(&cslist[3u * k]);
-                        if (ent & 0x8000u) break;
-                        // nothing more will come once every warp of role A is done and entry k was never handed out
-                        if (*reinterpret_cast<volatile uint32_t*>(&s_a_done) >= nrw && k >= *reinterpret_cast<volatile uint32_t*>(&s_ncs)) { ent = 0; break; }
-                        spin_pause();
-                    }
-                    if (ent == 0u) break;
-                    __threadfence_block();
-                    parse_cs_general(recs[ent & 0x7FFFu], cslist[3u * k + 1u], cslist[3u * k + 2u]);
-                    cslist[3u * k] = 0;
-                }
             }
         }
         drain_far(base_off - (int64_t)gridDim.x * G::TILE);                // idle warps at once, the others when their records are done
@@ -748,8 +694,6 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             s_nfar = 0;                                                     // (drained during `records`)
             s_far_next = 0;
             s_ndel = 0;
-            s_ncs = 0;                                                      // (parsed during `records`)
-            s_a_done = 0;
             const uint32_t nxt = tile + gridDim.x;
             if (nxt < A.n_tiles) issue_load(nxt);                           // overlaps walk + count
         }
