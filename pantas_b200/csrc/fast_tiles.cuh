@@ -88,8 +88,9 @@ struct Geo {
     static constexpr int FAR_CAP = (STEP_CAP / 8 + 31) & ~31;     // links that are not inline: typically 1-2 per record
     static constexpr int DEL_CAP = (LINE_CAP / 2 + 31) & ~31;     // steps with deletion-derived keys
     static constexpr int MASK_BYTES = 4 * NV;                     // whitespace + separator masks; dead after `records`:
-    static constexpr int LIST_BYTES = 12 * DEL_CAP;                    // ... the list of deletion keys reuses the space
+    static constexpr int LIST_BYTES = 12 * DEL_CAP + 2 * STEP_CAP;     // ... the list of deletion keys and walk 2's list of multi-op steps reuse the space
     static constexpr int OFF_WM = (BUF + 127) & ~127;
+    static constexpr int OFF_HEAVY = OFF_WM + 12 * DEL_CAP;
     static constexpr int OFF_SM = OFF_WM + 2 * NV;
     static constexpr int OFF_DEL = OFF_WM;
     static constexpr int OFF_STEP = (OFF_WM + (MASK_BYTES > LIST_BYTES ? MASK_BYTES : LIST_BYTES) + 15) & ~15;
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
     constexpr uint32_t NWARPS = THREADS / 32;
     PT_DYNAMIC_SMEM(smem);
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t s_nlines, s_nsteps, s_nops, s_nfar, s_ndel, s_far_next;
+    __shared__ uint32_t s_nlines, s_nsteps, s_nops, s_nfar, s_ndel, s_far_next, s_nheavy;
     __shared__ uint32_t s_wsum[NWARPS];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
     uint32_t* const far = reinterpret_cast<uint32_t*>(smem + G::OFF_SINFO);    // {from, to, separator position}: filled by `count`, when the step-length
                                                                                  // prefix (same bytes) is dead; drained during the next tile's `records`
     uint32_t* const dels = reinterpret_cast<uint32_t*>(smem + G::OFF_DEL);     // {step, first del, last del}     (reuses the masks)
+    uint16_t* const heavy = reinterpret_cast<uint16_t*>(smem + G::OFF_HEAVY);  // steps of multi-op records, for walk 2's dense pass (reuses the masks)
     uint32_t* const steps = reinterpret_cast<uint32_t*>(smem + G::OFF_STEP);
     uint32_t* const sidx = reinterpret_cast<uint32_t*>(smem + G::OFF_SIDX);
     uint32_t* const sinfo = reinterpret_cast<uint32_t*>(smem + G::OFF_SINFO);  // step-length prefix
@@ -259,6 +261,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         s_nfar = 0;
         s_ndel = 0;
         s_far_next = 0;
+        s_nheavy = 0;
     }
     __syncthreads();
 
@@ -694,6 +697,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
             s_nfar = 0;                                                     // (drained during `records`)
             s_far_next = 0;
             s_ndel = 0;
+            s_nheavy = 0;
             const uint32_t nxt = tile + gridDim.x;
             if (nxt < A.n_tiles) issue_load(nxt);                           // overlaps walk + count
         }
@@ -748,6 +752,8 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         phase_done(4);
 
         // ================= walk 2: every step folds the cs ops that overlap its node =================
+        // Pass 1 settles the steps of single-op records (a perfect match, mostly) and lists the others; pass 2 folds the listed
+        // steps, dense: a warp pays for its slowest lane, and one read in eight has a cs string with several ops.
         for (uint32_t s = tid; s < n_ent; s += THREADS) {
             const uint32_t se = steps[s];
             if (se == SE_INVALID || (se & SE_SENT)) continue;
@@ -773,6 +779,19 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                                                               : (se | ((kind != OP_SUB ? 1u : 0u) << SE_NCNT_SHIFT));
                 continue;
             }
+            {                                                               // several ops: pass 2
+                const uint32_t h = atomicAdd(&s_nheavy, 1u);
+                heavy[h] = (uint16_t)s;
+            }
+        }
+        __syncthreads();                                                    // ---- list of multi-op steps complete
+        for (uint32_t h = tid; h < s_nheavy; h += THREADS) {
+            const uint32_t s = heavy[h];
+            const uint32_t se = steps[s];
+            LineRecF& R = recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK];
+            const uint32_t Ak = sinfo[s] - R.base, Lk = sinfo[s + 1u] - sinfo[s], n_tot = R.n_tot;
+            const uint32_t* op = ops + R.op_off;
+            const uint32_t nops = R.nops;
             const uint32_t Bk = min(Ak + Lk, n_tot);
             // pieces of the node = ops overlapping [Ak, Bk), clipped; compact_align as a running fold (REF:63-94)
             uint32_t j = 0, o_start = 0, o_end = op[0] >> 3;
