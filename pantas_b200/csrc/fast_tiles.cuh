@@ -151,6 +151,32 @@ __device__ __forceinline__ bool tag_is_inert(const uint8_t* s, uint32_t a, uint3
     return token_is_inert(s, a, b);
 }
 
+// ---- the same tests on whole words (role A: a third of the shared-memory loads of the byte versions)
+// eight bytes at buffer position a (any alignment), first byte lowest; reads up to 11 bytes past a (the buffer is padded)
+__device__ __forceinline__ unsigned long long ld8(const uint8_t* s, uint32_t a) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(s + (a & ~3u));
+    const uint32_t sh = (a & 3u) * 8u;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    return (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
+}
+// is one of the lowest n (<= 8) bytes of x a ':' ?
+__device__ __forceinline__ bool has_colon8(unsigned long long x, uint32_t n) {
+    const unsigned long long keep = n >= 8u ? ~0ull : ~(~0ull << (8u * n));
+    const unsigned long long y = (x ^ 0x3A3A3A3A3A3A3A3Aull) | ~keep;      // 0 exactly where a kept byte is ':'
+    const unsigned long long t = (y & 0x7F7F7F7F7F7F7F7Full) + 0x7F7F7F7F7F7F7F7Full;
+    return (~(t | y) & 0x8080808080808080ull) != 0ull;
+}
+// no ':' in [a, b); first8 = ld8(s, a) if the caller has it already
+__device__ __forceinline__ bool no_colon_w(const uint8_t* s, uint32_t a, uint32_t b) {
+    if (b - a > 48u) return false;
+    for (uint32_t q = a; q < b; q += 8u)
+        if (has_colon8(ld8(s, q), b - q)) return false;
+    return true;
+}
+constexpr unsigned long long TAG_CS3 = 0x3A7363ull;                          // "cs:"
+constexpr unsigned long long TAG_DV5 = 0x3A663A7664ull;                      // "dv:f:"
+constexpr unsigned long long TAG_AS5 = 0x3A693A5341ull;                      // "AS:i:"
+
 // four ASCII digits, most significant in the lowest byte, already xor'ed with '0'
 __device__ __forceinline__ uint32_t val4(uint32_t w) {
     w = ((w * 2561u) >> 8) & 0x00FF00FFu;
@@ -526,15 +552,19 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                     uint32_t a = e12 + 1u, b = 0;
                     if (!next_ws(wm32, 2u * nwords, wi, wmk, b)) slow = true;
                     for (int j = 13; !slow; j++) {
-                        if (!cs_b && b - a >= 3u && buf[a] == 'c' && buf[a + 1] == 's' && buf[a + 2] == ':') {
+                        const unsigned long long t8 = ld8(buf, a);          // the token's first eight bytes
+                        if (!cs_b && b - a >= 3u && (t8 & 0xFFFFFFull) == TAG_CS3) {
                             cs_a = a;
                             cs_b = b;
-                        } else if (!dv_b && b - a >= 6u && buf[a] == 'd' && buf[a + 1] == 'v' && buf[a + 2] == ':' &&
-                                   buf[a + 3] == 'f' && buf[a + 4] == ':' && pt::is_digit(buf[a + 5]) &&
-                                   no_colon(buf, a + 5u, b)) {
+                        } else if (!dv_b && b - a >= 6u && (t8 & 0xFFFFFFFFFFull) == TAG_DV5 && pt::is_digit((uint32_t)(t8 >> 40) & 0xFFu) &&
+                                   no_colon_w(buf, a + 5u, b)) {
                             dv_a = a + 5u;
                             dv_b = b;
-                        } else if (!tag_is_inert(buf, a, b)) {
+                        } else if (b - a >= 6u && (t8 & 0xFFFFFFFFFFull) == TAG_AS5) {
+                            // "AS:i:<int>", the tag the aligner writes first: inert when nothing after the prefix is a ':'
+                            const bool ok = b - a <= 8u ? !has_colon8(t8 >> 40, b - a - 5u) : no_colon_w(buf, a + 5u, b);
+                            if (!ok) { slow = true; break; }
+                        } else if (!token_is_inert(buf, a, b)) {
                             slow = true;
                             break;
                         }
