@@ -545,7 +545,8 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 int32_t mapq = 0;
                 bool idle = ran_off || buf[e12] != '\t' || !small_uint(buf, e11 + 1u, e12, mapq) || (int64_t)mapq < A.thr;
                 bool slow = false, done = false;
-                uint32_t cs_a = 0, cs_b = 0, dv_a = 0, dv_b = 0;
+                uint32_t cs_a = 0, cs_b = 0, dv_a = 0, dv_b = 0, dv3 = 0;
+                unsigned long long cs8 = 0;
                 if (!idle) {
                     // ---- tags: [inert]* cs [inert]* dv in any order, within the first few tags
                     why = WHY_TAGS;
@@ -556,10 +557,12 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                         if (!cs_b && b - a >= 3u && (t8 & 0xFFFFFFull) == TAG_CS3) {
                             cs_a = a;
                             cs_b = b;
+                            cs8 = t8;
                         } else if (!dv_b && b - a >= 6u && (t8 & 0xFFFFFFFFFFull) == TAG_DV5 && pt::is_digit((uint32_t)(t8 >> 40) & 0xFFu) &&
                                    no_colon_w(buf, a + 5u, b)) {
                             dv_a = a + 5u;
                             dv_b = b;
+                            dv3 = (uint32_t)(t8 >> 40);                     // the first three bytes of the number
                         } else if (b - a >= 6u && (t8 & 0xFFFFFFFFFFull) == TAG_AS5) {
                             // "AS:i:<int>", the tag the aligner writes first: inert when nothing after the prefix is a ':'
                             const bool ok = b - a <= 8u ? !has_colon8(t8 >> 40, b - a - 5u) : no_colon_w(buf, a + 5u, b);
@@ -576,7 +579,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                     // ---- dv filter (REF:172-180).  The reference parses cs first, but that has no side effects and
                     //      cannot raise, so a record that dv filters out needs no cs class
                     if (!slow) {
-                        const uint32_t f = buf[dv_a], g = dv_a + 1u < dv_b ? buf[dv_a + 1u] : 0u, h = dv_a + 2u < dv_b ? buf[dv_a + 2u] : 0u;
+                        const uint32_t f = dv3 & 0xFFu, g = dv_a + 1u < dv_b ? (dv3 >> 8) & 0xFFu : 0u, h = dv_a + 2u < dv_b ? (dv3 >> 16) & 0xFFu : 0u;
                         if (f == '0' && g == '.' && h == '0') {
                             // 0.0xxx: never greater
                         } else if (pt::dv_token_greater(buf, (int)dv_a, (int)dv_b)) {
@@ -589,10 +592,10 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                         why = WHY_CS;
                         uint32_t n_tot = 0, nops = 0, op_off = 0;
                         int32_t start_add = 0;
-                        if (cs_b - cs_a < 7u || buf[cs_a + 3] != 'Z' || buf[cs_a + 4] != ':') slow = true;
+                        if (cs_b - cs_a < 7u || (cs8 & 0xFFFF000000ull) != 0x3A5A000000ull) slow = true;      // "cs:Z:"
                         uint32_t q = cs_a + 5u;
                         uint64_t one;
-                        if (!slow && buf[q] == ':' && cs_b - q - 1u <= 7u && step_id(buf, q + 1u, cs_b - q - 1u, one) && one != 0u) {
+                        if (!slow && ((cs8 >> 40) & 0xFFu) == ':' && cs_b - q - 1u <= 7u && step_id(buf, q + 1u, cs_b - q - 1u, one) && one != 0u) {
                             // cs:Z::<n> -- a perfect match
                             op_off = atomicAdd(&s_nops, 1u);
                             if (op_off < (uint32_t)G::OPS_CAP) ops[op_off] = OP_MATCH | ((uint32_t)one << 3);
