@@ -704,11 +704,9 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                         }
                     }
                     idx_[u] = idx;                                          // NONE32: KeyError in the reference, `walk` hands the record over
-                }
-#pragma unroll
-                for (int u = 0; u < UI; u++) {
+                    // issued at once: the load is in flight while the next id is parsed
                     hot_[u].len = 0; hot_[u].il = 0; hot_[u].ol = 0; hot_[u].d01 = 0;
-                    if (idx_[u] != NONE32) hot_[u] = sink.load_hot(idx_[u]);
+                    if (idx != NONE32) hot_[u] = sink.load_hot(idx);
                 }
 #pragma unroll
                 for (int u = 0; u < UI; u++) {
