@@ -437,8 +437,12 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         static_assert(NWARPS >= 2u && NWARPS % 2u == 0u, "half of the warps per role");
         constexpr uint32_t RW = NWARPS / 2u;
         const bool roleA = warp >= RW;
-        const uint32_t nrw = min((n_lines + 31u) >> 5, RW);                // warps per role in use
-        for (uint32_t l = 32u * (roleA ? warp - RW : warp) + lane; l < n_lines && (roleA ? warp - RW : warp) < nrw; l += 32u * nrw) {
+#ifndef PT_ROLE_LANES
+#define PT_ROLE_LANES 32u                                                   // records per role warp (tuning: fewer = shorter divergent streams, more warps)
+#endif
+        constexpr uint32_t RL = PT_ROLE_LANES;
+        const uint32_t nrw = min((n_lines + RL - 1u) / RL, RW);            // warps per role in use
+        for (uint32_t l = RL * (roleA ? warp - RW : warp) + lane; l < n_lines && lane < RL && (roleA ? warp - RW : warp) < nrw; l += RL * nrw) {
             LineRecF& R = recs[l];
             const uint32_t ls = lines[l];
             uint32_t wi = ls >> 5;
@@ -681,7 +685,10 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
         // walk 1), inline link deltas (sd01), and whether this tile could still lower a first-touch stamp (two flag bits in
         // sidx; stamps only decrease, so an older value only errs towards one RED.MIN too many): `count` loads nothing.
         {
-            constexpr int UI = 4;
+#ifndef PT_IDS_UNROLL
+#define PT_IDS_UNROLL 4
+#endif
+            constexpr int UI = PT_IDS_UNROLL;
             const int64_t rel0 = base_off + 16 - T.epoch_base;              // below every stamp this tile can produce
             const uint32_t rel_tile = rel0 < 0 ? 0u : (uint32_t)rel0;
             for (uint32_t s00 = 0; s00 < n_ent; s00 += THREADS * UI) {

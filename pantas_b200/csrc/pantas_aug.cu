@@ -560,6 +560,9 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
         typedef fastp::Geo<49152, 1024, 768> GJ;
         typedef fastp::Geo<40960, 1024, 512> GK;
         typedef fastp::Geo<49152, 1024, 1024> GL;
+        typedef fastp::Geo<28672, 1024, 512> GM;
+        typedef fastp::Geo<32768, 1024, 384> GN;
+        typedef fastp::Geo<30720, 1024, 512> GO;
         typedef fastp::Geo<1024, 256, 64> GT;    // tests: many tile boundaries, records longer than the look-ahead
         uint32_t ft;
 #define PT_PICK(Gx) { fkern = fastp::augment_fast_kernel<Gx>; fsmem = (size_t)Gx::SMEM_BYTES; ft = Gx::TILE; f_threads = Gx::THREADS; }
@@ -575,6 +578,9 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
         else if (ctx->fast_geo == 49152) PT_PICK(GJ)
         else if (ctx->fast_geo == 40960) PT_PICK(GK)
         else if (ctx->fast_geo == 49153) PT_PICK(GL)
+        else if (ctx->fast_geo == 28672) PT_PICK(GM)
+        else if (ctx->fast_geo == 32770) PT_PICK(GN)
+        else if (ctx->fast_geo == 30720) PT_PICK(GO)
         else if (ctx->fast_geo == 24576) PT_PICK(GA)
         else PT_PICK(GA)
 #undef PT_PICK
