@@ -242,7 +242,6 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
 
-    from pantas_b200.dist import allreduce_sums
     from pantas_b200.engine import AugmentEngine
 
     K, W = args.steps, max(args.warmup, 3)
@@ -273,7 +272,7 @@ def main():
         """the one-shot counter reduction that ends a multi-GPU job"""
         sums, stamps, novel, sparse = eng.export_device()
         if world > 1:
-            allreduce_sums(sums)                                            # pantas_b200/dist.py: the product's reduction
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
             dist.all_reduce(stamps, op=dist.ReduceOp.MIN)
         return sums, stamps, novel, sparse
 

@@ -2,8 +2,7 @@
 
 One process per GPU.  The data path has no collective; the only exchange is this
 one-shot reduction after the last chunk: ONE all_reduce(SUM) over the int64
-counter buffer [NC | IL0adj | OLadj | RC | rej, n_lines] (exchanged as int32
-when the job's totals provably fit) and one all_reduce(MIN)
+counter buffer [NC | IL0adj | OLadj | RC | rej, n_lines] and one all_reduce(MIN)
 over the first-touch stamps (NCCL over NVLink on the GPU box, gloo in the CPU
 tests), plus an all_gather of the two small side tables.
 """
@@ -26,25 +25,6 @@ def reduce_error(err_word: int, device, group=None) -> int:
     return int(t.item())
 
 
-def allreduce_sums(sums, group=None):
-    """In-place job-wide SUM of the int64 counter buffer.  The counters are sums of non-negative per-record
-    contributions and (IL/OL) small signed adjustments; when every rank's largest magnitude times the number of
-    ranks stays below 2^31 the exchange is done on an int32 copy -- half the bytes over NVLink, same result."""
-    import torch
-    import torch.distributed as dist
-
-    world = dist.get_world_size(group)
-    peak = sums.abs().max().reshape(1) if sums.numel() else torch.zeros(1, dtype=sums.dtype, device=sums.device)
-    dist.all_reduce(peak, op=dist.ReduceOp.MAX, group=group)
-    if int(peak.item()) * world < (1 << 31) - 1:
-        small = sums.to(torch.int32)
-        dist.all_reduce(small, op=dist.ReduceOp.SUM, group=group)
-        sums.copy_(small)
-    else:
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    return sums
-
-
 def allreduce_results(sums, stamps, novel, sparse, n_nodes: int, n_edges: int, group=None) -> FlatResult:
     """sums/stamps/novel/sparse: torch tensors (CUDA under NCCL, CPU under gloo).
     Returns the job-wide FlatResult on every rank."""
@@ -52,7 +32,7 @@ def allreduce_results(sums, stamps, novel, sparse, n_nodes: int, n_edges: int, g
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
-    allreduce_sums(sums, group)
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(stamps, op=dist.ReduceOp.MIN, group=group)
 
     def gather_rows(rows):
