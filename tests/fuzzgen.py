@@ -235,3 +235,29 @@ def make_risky_case(seed: int):
     else:
         recs.append(f"x{seed}\t10\t0\t10\t+\t>{ids[0]}\t20\t0\t5\t5\t5\t6x\tcs:Z::5\tdv:f:0")
     return gfa, "\n".join(recs) + "\n"
+
+
+def spread_ids(gfa: str, gaf: str, pivot: int, shift: int):
+    """Move every node id > pivot up by `shift`: links across the gap are farther than an inline delta (2^15)."""
+    import re
+
+    def mv(tok):
+        return str(int(tok) + shift) if tok.isdigit() and int(tok) > pivot else tok
+
+    g = []
+    for line in gfa.split("\n"):
+        t = line.split("\t")
+        if t[0] == "S" and len(t) >= 3:
+            t[1] = mv(t[1])
+        elif t[0] == "L" and len(t) >= 5:
+            t[1], t[3] = mv(t[1]), mv(t[3])
+        elif t[0] == "P" and len(t) >= 3:
+            t[2] = ",".join(mv(x[:-1]) + x[-1] if x[:-1].isdigit() else x for x in t[2].split(","))
+        g.append("\t".join(t))
+    a = []
+    for line in gaf.split("\n"):
+        t = line.split("\t")
+        if len(t) > 5:
+            t[5] = re.sub(r"\d+", lambda m: mv(m.group(0)), t[5])
+        a.append("\t".join(t))
+    return "\n".join(g), "\n".join(a)

@@ -128,3 +128,17 @@ def test_fuzz_production_geometry(seed, tmp_path):
     assert res[0] == "ok", res
     assert res[1] == orc.out
     assert res[2] == orc.rej
+
+
+@pytest.mark.parametrize("seed", range(7600, 7612))
+def test_far_links_are_counted_one_tile_later(seed, tmp_path):
+    """Links too far apart for a node's inline deltas go through the hash table; the fast path lists them per tile and
+    drains the list during the next tile's records phase (and after the last tile): many small tiles, several CTAs."""
+    gfa, gaf = fuzzgen.make_case(seed, n_nodes=24, n_reads=150, weird=False)
+    gfa, gaf = fuzzgen.spread_ids(gfa, gaf, pivot=12, shift=40000)
+    orc = run_oracle(gaf.encode(), gfa.encode())
+    assert orc.rc == 0
+    res = pipeline(tmp_path, gfa, gaf, geo=seed % 3, grid=1 + seed % 4)
+    assert res[0] == "ok", res
+    assert res[1] == orc.out
+    assert res[2] == orc.rej

@@ -246,3 +246,17 @@ def test_full_size_graphs_are_linear_in_the_gaf(preset, pairs):
     assert np.array_equal(merged.stamps, whole.stamps)
     for a, b in ((merged.novel, whole.novel), (merged.sparse, whole.sparse)):
         assert sorted(map(tuple, a.tolist())) == sorted(map(tuple, b.tolist()))
+
+
+@pytest.mark.parametrize("seed", range(9100, 9108))
+def test_far_links_vs_oracle(seed, tmp_path):
+    """Links farther apart than an inline delta: hash-table probes, listed per tile and drained one tile later."""
+    gfa, gaf = fuzzgen.make_case(seed, n_nodes=30, n_reads=3000, weird=False)
+    gfa, gaf = fuzzgen.spread_ids(gfa, gaf, pivot=15, shift=50000)
+    orc = run_oracle(gaf.encode(), gfa.encode())
+    assert orc.rc == 0
+    eng = _engine(PANTAS_FAST_T=[32768, 1024, 24576, 16384][seed % 4])
+    res = gpu_pipeline(tmp_path, gfa, gaf, eng=eng, chunks=1 + seed % 2)
+    assert res[0] == "ok", res
+    assert res[1] == orc.out
+    assert res[2] == orc.rej
