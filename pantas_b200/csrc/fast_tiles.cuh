@@ -88,11 +88,10 @@ struct Geo {
     static constexpr int FAR_CAP = (STEP_CAP / 8 + 31) & ~31;     // links that are not inline: typically 1-2 per record
     static constexpr int DEL_CAP = (LINE_CAP / 2 + 31) & ~31;     // steps with deletion-derived keys
     static constexpr int MASK_BYTES = 4 * NV;                     // whitespace + separator masks; dead after `records`:
-    static constexpr int LIST_BYTES = 12 * DEL_CAP + 2 * STEP_CAP;     // ... the list of deletion keys and walk 2's list of multi-op steps reuse the space
+    static constexpr int LIST_BYTES = 2 * STEP_CAP;                    // ... walk 2's list of multi-op steps reuses the space
     static constexpr int OFF_WM = (BUF + 127) & ~127;
-    static constexpr int OFF_HEAVY = OFF_WM + 12 * DEL_CAP;
+    static constexpr int OFF_HEAVY = OFF_WM;
     static constexpr int OFF_SM = OFF_WM + 2 * NV;
-    static constexpr int OFF_DEL = OFF_WM;
     static constexpr int OFF_STEP = (OFF_WM + (MASK_BYTES > LIST_BYTES ? MASK_BYTES : LIST_BYTES) + 15) & ~15;
     static constexpr int OFF_SIDX = OFF_STEP + 4 * STEP_CAP;
     static constexpr int OFF_SINFO = OFF_SIDX + 4 * STEP_CAP;
@@ -100,7 +99,8 @@ struct Geo {
     static constexpr int OFF_OPS = OFF_SD01 + 4 * STEP_CAP;
     static constexpr int OFF_LINES = OFF_OPS + 4 * OPS_CAP;
     static constexpr int OFF_REC = (OFF_LINES + 2 * LINE_CAP + 7) & ~7;
-    static constexpr int SMEM_BYTES = (OFF_REC + (int)sizeof(LineRecF) * LINE_CAP + 127) & ~127;
+    static constexpr int OFF_DEL = (OFF_REC + (int)sizeof(LineRecF) * LINE_CAP + 7) & ~7;   // deletion keys: read while the next tile is scanned
+    static constexpr int SMEM_BYTES = (OFF_DEL + 12 * DEL_CAP + 127) & ~127;
     static constexpr int FIT = (227 * 1024) / (SMEM_BYTES + 1024);                    // CTAs per SM by shared memory
     static constexpr int REG = 1024 / THREADS < 1 ? 1 : 1024 / THREADS;               // ... leaving >= 64 registers per thread
     static constexpr int MIN_CTAS = FIT < 1 ? 1 : (FIT < REG ? FIT : REG);
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
     const uint32_t* const sm32 = reinterpret_cast<const uint32_t*>(smem + G::OFF_SM);
     uint32_t* const far = reinterpret_cast<uint32_t*>(smem + G::OFF_SINFO);    // {from, to, separator position}: filled by `count`, when the step-length
                                                                                  // prefix (same bytes) is dead; drained during the next tile's `records`
-    uint32_t* const dels = reinterpret_cast<uint32_t*>(smem + G::OFF_DEL);     // {step, first del, last del}     (reuses the masks)
+    uint32_t* const dels = reinterpret_cast<uint32_t*>(smem + G::OFF_DEL);     // {step, first del, last del}
     uint16_t* const heavy = reinterpret_cast<uint16_t*>(smem + G::OFF_HEAVY);  // steps of multi-op records, for walk 2's dense pass (reuses the masks)
     uint32_t* const steps = reinterpret_cast<uint32_t*>(smem + G::OFF_STEP);
     uint32_t* const sidx = reinterpret_cast<uint32_t*>(smem + G::OFF_SIDX);
@@ -952,8 +952,8 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 }
             }
         }
-        __syncthreads();                                                    // ---- far-link list complete
         phase_done(6);
+        // no barrier: the list of deletion keys is complete since walk 2, the far-link list is read one tile later
         {
             // deletion-derived keys: position of the deletion inside the node, IL or OL by orientation
             const uint32_t n_del = min(s_ndel, (uint32_t)G::DEL_CAP);
@@ -977,11 +977,13 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) augment_fast_kernel(C
                 }
             }
         }
-        // no barrier here: the next tile's scan writes the masks (= the two lists, nobody reads them any more
-        // once its first barrier is passed ... which every thread reaches only after finishing the loops above)
-        __syncthreads();
+        // No barrier at the end of the tile: a thread that is done goes on to scan the next tile (its bytes arrived long ago).
+        // The scan writes the masks, the record-start list and its counter; nothing a straggler of this tile still reads
+        // (step list, node indices, records, the two lists), and every thread passes the scan's barrier only after it is
+        // through here.
         phase_done(7);
     }
+    __syncthreads();                                                        // the last tile's far-link list is complete
 
     drain_far(A.file_off + (int64_t)(tile - gridDim.x) * G::TILE - 16);    // the last tile's far links
 
