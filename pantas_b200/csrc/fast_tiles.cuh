@@ -1,39 +1,45 @@
-// fast_tiles.cuh -- the fast path of the augment kernel (included by pantas_aug.cu inside its
-// anonymous namespace, after tables.cuh, the TMA helpers, ChunkArgs and defer_line()).
+// fast_tiles.cuh -- the fast path of the augment kernel (included by aug_kernels.cuh after tables.cuh, the TMA
+// helpers, ChunkArgs and defer_line(); compiled for sm_100a by pantas_aug.cu and for the CPU emulator by
+// tests/hostsim/fastsim.cpp).
 //
 // Reference loop body: /root/reference/scripts/alignments_augmentation_from_gaf.py:142-363 (REF:n).
 //
 // A persistent CTA takes tiles of the GAF chunk (TILE bytes + OV bytes of look-ahead, one 1-D TMA
-// bulk copy, UBLKCP) and runs data-parallel phases over the tile in shared memory:
+// bulk copy, UBLKCP, L2 evict-first) and runs phases over the tile in shared memory:
 //
-//   scan     one thread per 64 bytes (4 x LDS.128), branch-free SWAR: a 64-bit whitespace mask and a
-//            64-bit path-separator ('>' '<') mask per group; record starts ('\n') go to a list;
-//            lone '\r' and non-ASCII bytes are (fatal) errors.
-//   records  TWO threads per record, both walking the whitespace mask from the record start:
+//   scan     one thread per 64 bytes (4 x LDS.128 in a lane-rotated order: no bank conflicts), branch-free
+//            SWAR: a 64-bit whitespace mask and a 64-bit path-separator ('>' '<') mask per group; record
+//            starts ('\n') go to a list; lone '\r' and non-ASCII bytes are (fatal) errors.
+//   records  two roles per record, whole warps per role, the records packed into as few warps as they need
+//            (a warp takes as long for one record as for 32); both walk the whitespace mask as 32-bit halves:
 //              B  the 12 column boundaries (single tabs, no empty column), MAPQ and '*' filters
 //                 (REF:143-148), the three coordinates (REF:151-153), then the separator mask of
 //                 the path column -> one entry per path step (+ a sentinel) in the tile's step list;
-//              A  the tags: first cs token, first dv:f: token (REF:154-160,172-180), the dv filter,
-//                 and the cs string parsed into the tile's op pool (REF:10-50, incl. cigar_clipping).
+//              A  skips ten boundaries by popcount; the tags, classified on whole words: first cs token,
+//                 first dv:f: token (REF:154-160,172-180), the dv filter, and the cs string parsed into the
+//                 tile's op pool (REF:10-50, incl. cigar_clipping).
 //            Anything unusual -- other whitespace in the columns, integers that are not plain
 //            digits, tags that could confuse the reference's regexes, '~' or zero-length or oddly
 //            spelled cs ops -- hands the record to the exact per-record path (line_core.cuh via
-//            augment_deferred_kernel).
-//   ids      one thread per path step: SWAR decimal parse of the id out of shared memory, node
-//            index, L2 prefetch of the node record.  After this phase the bytes are dead and the
-//            next tile's TMA copy is issued: it overlaps the table traffic of the remaining phases.
+//            augment_deferred_kernel).  The warps this phase leaves idle drain the PREVIOUS tile's list of
+//            links that are not inline (hash-table probes: their latency costs nothing here).
+//   ids      one thread per path step: SWAR decimal parse of the id out of shared memory, node index, one
+//            16-byte load of the node record's read half, issued as soon as the index is known; length,
+//            inline link deltas and two stamp flags stay in shared memory.  After this phase the bytes are
+//            dead and the next tile's TMA copy is issued: it overlaps the remaining phases.
 //   walk     one thread per path step.  The reference's merge walk (REF:205-255) gives node k the
 //            ops that overlap [A_k, A_k + L_k) in cs coordinates, where A is the prefix sum of the
-//            node lengths L (first / last node shortened, REF:215-218): a block-wide prefix sum,
+//            node lengths L (first / last node shortened, REF:215-218): a block-wide prefix sum (walk 1),
 //            then every step finds its op pieces independently and folds clear_align /
 //            compact_align (REF:63-107) over them: dropped or not, number of counting ops,
-//            deletion-derived IL/OL keys.  Collapsible duplicate ids (REF:188), unknown ids and a
+//            deletion-derived IL/OL keys (walk 2: steps of single-op records at once, the others listed
+//            and folded in a dense second pass).  Collapsible duplicate ids (REF:188), unknown ids and a
 //            cs string shorter than the path hand the record over.  Nothing has been counted yet,
 //            so the hand-over is clean.
-//   count    one thread per surviving step: NC / IL / OL / RC events (REF:263-363): one RED.ADD.64
-//            on the node's sector (tables.cuh), RED.MIN for first-touch stamps only when earlier.
-//            Links that are not inline and deletion-derived keys are collected in two short lists
-//            and done by all threads at the end of the tile (hash-table work, all lanes busy).
+//   count    one thread per surviving step, no global loads: NC / IL / OL / RC events (REF:263-363): one
+//            RED.ADD.64 on the node's sector (tables.cuh), RED.MIN for first-touch stamps only when this
+//            tile could lower them.  Links that are not inline go to the list the next records phase
+//            drains; deletion-derived keys follow at once.  No barrier closes the tile.
 #pragma once
 
 namespace fastp {
