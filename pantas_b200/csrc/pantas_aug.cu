@@ -4,15 +4,16 @@
 //   /root/reference/scripts/alignments_augmentation_from_gaf.py:138-371   (REF:n)
 // Data flow on the device (DESIGN.md has the full picture):
 //
-//   GAF bytes in HBM --cp.async.bulk (TMA 1-D)--> per-warp shared-memory mini-tile
-//     fast_tiles.cuh   warp-autonomous fast path: byte-parallel event scan, one lane per record
-//                      for the columns / filters / cs class, one lane per path step for the counts
+//   GAF bytes in HBM --cp.async.bulk (TMA 1-D, L2 evict-first)--> a CTA's shared-memory tile
+//     fast_tiles.cuh   the fast path: persistent CTAs, barrier-separated phases over the tile (byte-parallel
+//                      SWAR scan, records by role warps, one thread per path step for ids / walk / count)
 //     line_core.cuh    exact thread-per-record path for every record the fast path declines
 //                      (augment_deferred_kernel, bytes from global memory)
 //     tables.cuh       NodeRec[idx] = one 32-byte sector per node: len, first-touch stamps, two
 //                      inline out-links and the fused NC|RC counters (one RED.ADD.64 per path step);
 //                      64-bit-key open-addressing tables for the remaining links (known: ovf,
 //                      unknown: novel) and for deletion-derived IL/OL keys (sparse)
+//   (aug_kernels.cuh holds the device code; this file adds the round-1a tile kernel kept for tests and the host side.)
 //
 // No tensor cores: nothing here is a contraction.  No CPU fallback: every entry
 // point fails if the device is not sm_100.
