@@ -14,7 +14,7 @@ scaling) and the step ends with the one-shot NCCL reduction of the counters.
   value     alignments/s, whole job, GAF already resident in HBM
   e2e       same through the host-buffer C-ABI call: pinned host GAF -> H2D ->
             kernels -> export -> D2H of the reduced counters
-  roofline  augment_fast_kernel: GAF bytes parsed / kernel time vs measured HBM copy peak
+  roofline  augment_team_kernel: GAF bytes parsed / kernel time vs measured HBM copy peak
   cpu_baseline  the CPU oracle port (oracle/augment_oracle.c) on a bounded sample, 1 core
 `--impl reference` times that CPU port on all host cores instead (the reference
 itself is pure Python and is not present on the GPU box; its measured speed in
@@ -403,7 +403,7 @@ def main():
             "deferred_records": st["deferred_lines"],
             "clocks": clocks,
             "e2e": e2e,
-            "roofline": {"bound": "hbm", "kernel": "augment_fast_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "augment_team_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(args.workload) if world == 1 else None,
                          "peak_source": peak_src, "kernel_ms": kern_avg_ms,

@@ -8,7 +8,7 @@ import subprocess
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(PKG, "csrc", "pantas_aug.cu")
-DEPS = [SRC, os.path.join(PKG, "csrc", "aug_kernels.cuh"), os.path.join(PKG, "csrc", "tables.cuh"), os.path.join(PKG, "csrc", "line_core.cuh"), os.path.join(PKG, "csrc", "fast_tiles.cuh"), os.path.join(os.path.dirname(PKG), "include", "pantas_aug.h")]
+DEPS = [SRC, os.path.join(PKG, "csrc", "aug_kernels.cuh"), os.path.join(PKG, "csrc", "tables.cuh"), os.path.join(PKG, "csrc", "line_core.cuh"), os.path.join(PKG, "csrc", "team_tiles.cuh"), os.path.join(os.path.dirname(PKG), "include", "pantas_aug.h")]
 LIB = os.path.join(PKG, "libpantas_aug.so")
 
 NVCC_FLAGS = [

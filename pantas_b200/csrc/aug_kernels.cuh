@@ -1,5 +1,5 @@
 // aug_kernels.cuh -- device code of the augment pass: tables + event sink (tables.cuh), TMA helpers,
-// the fast path (fast_tiles.cuh), the exact per-record kernel and the per-chunk epilogue.  Included by
+// the fast path (team_tiles.cuh), the exact per-record kernel and the per-chunk epilogue.  Included by
 // pantas_aug.cu inside its anonymous namespace (after line_core.cuh) -- and, with PT_EMU defined, by the
 // CPU-only test harness tests/hostsim/fastsim.cpp, which runs the same kernels thread by thread.
 #pragma once
@@ -69,11 +69,9 @@ struct ChunkArgs {
     uint64_t nbytes;
     int64_t file_off;
     int64_t thr;
-    uint32_t tile;       // bytes per tile, multiple of 16
-    uint32_t over;       // look-ahead bytes after the tile, multiple of 16
-    uint32_t list_cap;   // line-start slots in shared memory
     uint32_t n_tiles;
-    uint32_t stream_hint;   // bit 0: load the GAF with an L2 evict-first policy; bit 1: count cycles per phase (diagnostics)
+    uint32_t stream_hint;   // bit 0: load the GAF with an L2 evict-first policy
+    uint32_t ablate;        // diagnostics (PANTAS_ABLATE): 0 = the whole pass, k = every tile stops after phase k (timing only)
 };
 
 // why a record is handed to the slow path (pt_debug_counters)
@@ -86,7 +84,7 @@ __device__ __forceinline__ void defer_line(const Tables& T, uint64_t chunk_pos, 
     else report_error(T, pt::PT_X_DEFER_FULL, file_off + (int64_t)chunk_pos);
 }
 
-#include "fast_tiles.cuh"
+#include "team_tiles.cuh"
 
 // Records that did not fit a tile's look-ahead window: same logic, bytes from global memory.
 __global__ void __launch_bounds__(128) augment_deferred_kernel(ChunkArgs A, Tables T) {
@@ -110,10 +108,13 @@ __global__ void __launch_bounds__(128) augment_deferred_kernel(ChunkArgs A, Tabl
     if ((threadIdx.x & 31) == 0 && r) atomicAdd(&T.sc[SC_REJ], (unsigned long long)r);
 }
 
-// After both kernels of a chunk: fold the per-chunk scalars.
+// After both kernels of a chunk: fold the per-chunk scalars, reset the fast kernel's low-water mark.
 __global__ void end_chunk_kernel(Tables T) {
-    T.sc[SC_DEFERRED_TOTAL] += min(T.sc[SC_NDEFER], (unsigned long long)T.deferred_cap);
-    T.sc[SC_NDEFER] = 0;
-    T.sc[SC_TILE_NEXT] = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < T.team_cap; i += gridDim.x * blockDim.x) T.team_tile[i] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        T.sc[SC_DEFERRED_TOTAL] += min(T.sc[SC_NDEFER], (unsigned long long)T.deferred_cap);
+        T.sc[SC_NDEFER] = 0;
+        T.sc[SC_LWM] = 0;
+    }
 }
 

@@ -23,8 +23,9 @@
 //
 //   sink.id_to_idx / load_len           node id -> dense index, length       (REF:214)
 //   sink.count_node(idx)                NC[idx] += 1                         (REF:263-269)
-//   sink.dense(idx, il, ol, stamp, st)  IL[idx][0] += il, OL[idx][len] += ol, stored as
-//                                       (il - 1), (ol - 1) relative to NC    (REF:298-313,335-351)
+//   sink.dense(idx, il, ol, stamp, st, has_in, has_out)
+//                                       IL[idx][0] += il, OL[idx][len] += ol; has_in / has_out: this occurrence is the
+//                                       `to` / the `from` of a link of the same read (REF:298-313,335-351)
 //   sink.sparse(idx, dir, pos, stamp)   IL/OL[idx][pos] += 1, deletion-derived keys
 //                                                                            (REF:281-297,317-333)
 //   sink.edge(from, to, stamp, pf)      RC[(from,to)] += 1                   (REF:357-363)
@@ -500,7 +501,8 @@ PT_HD void walk_simple(const LineCtx& cx, const LineRec& rec, Sink& sink) {
             const uint64_t stamp = (uint64_t)(cx.base_off + cur_at) << 2;
             if (pd.valid) {
                 const bool not_first = !pd.is_first;
-                sink.dense(pd.idx, (rev || not_first) ? 1 : 0, (!rev || not_first) ? 1 : 0, pd.stamp | 1u, pd.st);
+                sink.dense(pd.idx, (rev || not_first) ? 1 : 0, (!rev || not_first) ? 1 : 0, pd.stamp | 1u, pd.st, rev || not_first,
+                           !rev || not_first);
                 if (rev) sink.edge(cur_idx, pd.idx, stamp, pf);
                 else sink.edge(pd.idx, cur_idx, stamp, pf);
             }
@@ -523,7 +525,7 @@ PT_HD void walk_simple(const LineCtx& cx, const LineRec& rec, Sink& sink) {
     if (pd.valid) {
         // last surviving node: i == last; i != 0 unless it is also the first
         const bool not_first = !pd.is_first;
-        sink.dense(pd.idx, (!rev && not_first) ? 1 : 0, (rev && not_first) ? 1 : 0, pd.stamp | 1u, pd.st);
+        sink.dense(pd.idx, (!rev && not_first) ? 1 : 0, (rev && not_first) ? 1 : 0, pd.stamp | 1u, pd.st, !rev && not_first, rev && not_first);
     }
 }
 
@@ -630,7 +632,7 @@ PT_HD void flush_pending(const Pending<Stamps>& p, bool is_last, bool rev, Sink&
             else sink.sparse(p.idx, 0, p.last_len, p.stamp | 2u);
         }
     }
-    sink.dense(p.idx, il_touch, ol_touch, p.stamp | 1u, p.st);
+    sink.dense(p.idx, il_touch, ol_touch, p.stamp | 1u, p.st, il_cond, ol_cond);
 }
 
 template <class Sink>

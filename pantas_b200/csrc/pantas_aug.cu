@@ -4,20 +4,21 @@
 //   /root/reference/scripts/alignments_augmentation_from_gaf.py:138-371   (REF:n)
 // Data flow on the device (DESIGN.md has the full picture):
 //
-//   GAF bytes in HBM --cp.async.bulk (TMA 1-D, L2 evict-first)--> a CTA's shared-memory tile
-//     fast_tiles.cuh   the fast path: persistent CTAs, barrier-separated phases over the tile (byte-parallel
-//                      SWAR scan, records by role warps, one thread per path step for ids / walk / count)
+//   GAF bytes in HBM --cp.async.bulk (TMA 1-D, L2 evict-first)--> a team's shared-memory tile
+//     team_tiles.cuh   the fast path: persistent two-warp teams, ten per SM, phases over an 8 KiB tile (byte-parallel
+//                      SWAR scan, records by role warps, one thread per path step for ids / fold / count)
 //     line_core.cuh    exact thread-per-record path for every record the fast path declines
 //                      (augment_deferred_kernel, bytes from global memory)
-//     tables.cuh       NodeRec[idx] = one 32-byte sector per node: len, first-touch stamps, two
-//                      inline out-links and the fused NC|RC counters (one RED.ADD.64 per path step);
-//                      64-bit-key open-addressing tables for the remaining links (known: ovf,
-//                      unknown: novel) and for deletion-derived IL/OL keys (sparse)
-//   (aug_kernels.cuh holds the device code; this file adds the round-1a tile kernel kept for tests and the host side.)
+//     tables.cuh       NodeHot[idx] = 16 bytes per node (meta word + three counters): one 16-byte load and
+//                      one 32-bit RED per path step, the table stays in the L2; 64-bit-key open-addressing
+//                      tables for the remaining links (known: ovf, unknown: novel) and for deletion-derived
+//                      IL/OL keys (sparse)
+//   (aug_kernels.cuh holds the device code; this file is the host side.)
 //
 // No tensor cores: nothing here is a contraction.  No CPU fallback: every entry
 // point fails if the device is not sm_100.
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -29,166 +30,6 @@
 namespace {
 
 #include "aug_kernels.cuh"
-
-constexpr int N_BUCKETS = 32;       // walk order: perfect-match records by path length, then the rest
-
-template <int THREADS, int MIN_CTAS>
-__global__ void __launch_bounds__(THREADS, MIN_CTAS) augment_tiles_kernel(ChunkArgs A, Tables T) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t s_nlines;
-    __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_bucket[N_BUCKETS];
-
-    const int tid = threadIdx.x;
-    uint8_t* buf = smem;                                      // [16 + tile + over + 16]
-    const uint32_t buf_bytes = 32u + A.tile + A.over;
-    uint32_t* list = reinterpret_cast<uint32_t*>(smem + ((buf_bytes + 127u) & ~127u));   // [list_cap]
-    pt::LineRec* recs = reinterpret_cast<pt::LineRec*>(list + ((A.list_cap + 31u) & ~31u));   // [THREADS]
-
-    if (tid == 0) mbar_init(&mbar, 1);
-    __syncthreads();
-
-    DevSink sink(T);
-    const uint64_t nbytes16 = (A.nbytes + 15ull) & ~15ull;
-    uint32_t parity = 0;
-    unsigned long long my_lines = 0, my_tiles = 0;
-
-    for (;;) {
-        if (tid == 0) {
-            s_tile = (uint32_t)atomicAdd(&T.sc[SC_TILE_NEXT], 1ull);
-            s_nlines = 0;
-        }
-        if (tid < N_BUCKETS) s_bucket[tid] = 0;
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= A.n_tiles) break;
-
-        const uint64_t t0 = (uint64_t)tile * A.tile;
-        const uint64_t t1 = min(t0 + A.tile, A.nbytes);             // owned line starts are in [t0, t1)
-        const uint64_t lo = tile ? t0 - 16 : 0;
-        const uint64_t hi = min(t0 + A.tile + A.over, nbytes16);     // loaded bytes [lo, hi)
-        const uint32_t skip = tile ? 0u : 16u;                       // buffer position 16 == byte t0
-        if (tid == 0) {
-            const uint32_t bytes = (uint32_t)(hi - lo);
-            mbar_expect_tx(&mbar, bytes);
-            tma_load_1d(buf + skip, A.gaf + lo, bytes, &mbar);
-        }
-        mbar_wait(&mbar, parity);
-        parity ^= 1;
-
-        // ---- phase 1: cooperative scan of [t0 - 1, t1) for line starts, CR, non-ASCII
-        {
-            const uint32_t owned = (uint32_t)(t1 - t0);
-            const uint32_t v_end = (16u + owned + 15u) >> 4;
-            if (tile == 0 && tid == 0 && A.nbytes > 0) {
-                const uint32_t j = atomicAdd(&s_nlines, 1u);
-                if (j < A.list_cap) list[j] = 16u; else defer_line(T, 0, A.file_off);
-            }
-            for (uint32_t v = tid + (tile ? 0u : 1u); v < v_end; v += THREADS) {
-                const uint4 q4 = *reinterpret_cast<const uint4*>(buf + 16u * v);
-                const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
-                const uint64_t v_abs = t0 + 16ull * v - 16ull;      // file-chunk position of the vector
-                const bool tail = v_abs + 16 > A.nbytes;            // bytes past the chunk end are garbage
-                uint32_t any_hi = (w[0] | w[1] | w[2] | w[3]) & 0x80808080u;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t a = w[k] & 0x7F7F7F7Fu;
-                    // 0x80 in every byte whose low 7 bits are in [0x0A, 0x0D]
-                    uint32_t m = (a + 0x76767676u) & ~(a + 0x72727272u) & 0x80808080u;
-                    while (m) {
-                        const int byte = (__ffs(m) - 1) >> 3;
-                        m &= m - 1;
-                        const uint32_t x = 16u * v + 4u * k + byte;        // buffer position
-                        const uint64_t abs_pos = v_abs + 4u * k + byte;
-                        if (abs_pos >= A.nbytes) continue;
-                        const uint32_t c = (w[k] >> (8 * byte)) & 0xFFu;
-                        if (c == '\n') {
-                            if (x + 1 >= 16u && abs_pos + 1 < t1) {
-                                const uint32_t j = atomicAdd(&s_nlines, 1u);
-                                if (j < A.list_cap) list[j] = x + 1;
-                                else defer_line(T, abs_pos + 1, A.file_off);
-                            }
-                        } else if (c == '\r' && x >= 16u) {
-                            if (abs_pos + 1 < A.nbytes && buf[x + 1] != '\n')
-                                report_error(T, pt::PT_U_BARE_CR, A.file_off + (int64_t)abs_pos);
-                        }
-                    }
-                }
-                if (any_hi) {
-                    if (!tail && v >= 1) report_error(T, pt::PT_U_NON_ASCII, A.file_off + (int64_t)v_abs);
-                    else
-                        for (int b = 0; b < 16; b++)
-                            if (v_abs + b < A.nbytes && 16u * v + b >= 16u && buf[16u * v + b] >= 0x80)
-                                report_error(T, pt::PT_U_NON_ASCII, A.file_off + (int64_t)(v_abs + b));
-                }
-            }
-        }
-        __syncthreads();
-
-        const uint32_t total = s_nlines;
-        const uint32_t nl = min(total, A.list_cap);
-        if (tid == 0) { my_lines += total; my_tiles++; }
-        pt::LineCtx cx;
-        cx.s = buf;
-        cx.lim = (int)(16u + (uint32_t)(min(hi, A.nbytes) - t0));
-        cx.lim_final = (hi >= A.nbytes);
-        cx.base_off = A.file_off + (int64_t)t0 - 16;
-
-        for (uint32_t base = 0; base < nl; base += THREADS) {
-            // ---- phase 2: front half, one thread per record; survivors pick a bucket
-            pt::LineRec rec;
-            int cls = pt::LINE_DONE;
-            uint32_t bucket = 0, rank = 0;
-            const uint32_t l = base + tid;
-            if (l < nl) {
-                const uint32_t p = list[l];
-                cls = pt::front_line(cx, (int)p, A.thr, sink, rec);
-                // records with a non-trivial cs string take the slow, divergent walk: they are
-                // redone by augment_deferred_kernel so that no tile waits for them
-                if (cls == pt::LINE_DEFER || cls == pt::LINE_GENERAL) {
-                    defer_line(T, t0 + p - 16u, A.file_off);
-                    cls = pt::LINE_DONE;
-                } else if (cls == pt::LINE_SIMPLE) {
-                    bucket = min((uint32_t)(rec.b5 - rec.a5) >> 4, (uint32_t)N_BUCKETS - 1u);
-                    rank = atomicAdd(&s_bucket[bucket], 1u);
-                }
-            }
-            __syncthreads();
-            // ---- regroup: records of one class and similar path length sit next to each other
-            uint32_t n_surv = 0;
-            {
-                uint32_t before = 0;
-#pragma unroll
-                for (int bkt = 0; bkt < N_BUCKETS; bkt++) {
-                    const uint32_t c = s_bucket[bkt];
-                    if ((uint32_t)bkt < bucket) before += c;
-                    n_surv += c;
-                }
-                if (cls == pt::LINE_SIMPLE) recs[before + rank] = rec;
-            }
-            __syncthreads();
-            if (tid < N_BUCKETS) s_bucket[tid] = 0;     // next round / next tile (ordered by the sync below)
-            // ---- phase 3: walk, one thread per surviving record
-            if ((uint32_t)tid < n_surv) {
-                const pt::LineRec r = recs[tid];
-                pt::walk_simple(cx, r, sink);
-            }
-            __syncthreads();   // every read of buf / list / recs is done before they are reused
-        }
-        if (nl == 0) __syncthreads();
-    }
-
-    // rejected-record count: warp reduce, one RED per warp
-    uint32_t r = sink.rej;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-    if ((tid & 31) == 0 && r) atomicAdd(&T.sc[SC_REJ], (unsigned long long)r);
-    if (tid == 0) {
-        if (my_lines) atomicAdd(&T.sc[SC_LINES], my_lines);
-        if (my_tiles) atomicAdd(&T.sc[SC_TILES], my_tiles);
-    }
-}
 
 }  // namespace
 
@@ -213,13 +54,13 @@ struct pt_ctx {
     uint64_t stage_bytes;
     int64_t next_ticket;
     uint64_t launches;
-    uint32_t tile, over, list_cap, threads;
-    int ctas_per_sm;
-    uint32_t kernel_ver;         // 2: warp-autonomous fast path (fast_tiles.cuh) + slow path; 1: tile kernel of round 1a
-    uint32_t fast_geo;           // mini-tile bytes of the fast path
-    int fast_ctas_per_sm;
+    uint32_t geo;                // tile bytes of the fast path (PANTAS_TEAM_TILE)
+    int teams_per_sm;
+    uint32_t ablate;             // PANTAS_ABLATE (diagnostics)
+    bool l2_window;              // an access-policy window over the node table is set on `stream`
+    size_t persist_max, window_max;
     bool profile;
-    cudaEvent_t* prof_ev;        // pairs
+    cudaEvent_t* prof_ev;        // triples
     uint32_t prof_n, prof_cap;
     char err[512];
 };
@@ -248,7 +89,7 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
     const char* v = getenv(name);
     if (!v || !*v) return dflt;
     long x = strtol(v, NULL, 10);
-    return x > 0 ? (uint32_t)x : dflt;
+    return x >= 0 ? (uint32_t)x : dflt;
 }
 static int grid_for(uint64_t n, int threads, int cap_blocks) {
     uint64_t b = (n + threads - 1) / threads;
@@ -259,11 +100,36 @@ static int grid_for(uint64_t n, int threads, int cap_blocks) {
 
 static void free_graph_tables(pt_ctx* ctx) {
     Tables& T = ctx->T;
-    cudaFree(T.nodes); cudaFree(T.il_adj32); cudaFree(T.ol_adj32); cudaFree(T.ovf); cudaFree(T.ovf_edge);
-    cudaFree(T.inl_edge); cudaFree(T.novel); cudaFree(T.sparse); cudaFree(T.nc64); cudaFree(T.il_adj64);
-    cudaFree(T.ol_adj64); cudaFree(T.il_st64); cudaFree(T.ol_st64); cudaFree(T.rc64);
-    T.nodes = NULL; T.il_adj32 = T.ol_adj32 = NULL; T.ovf = NULL; T.ovf_edge = T.inl_edge = NULL;
-    T.novel = T.sparse = NULL; T.nc64 = T.il_adj64 = T.ol_adj64 = NULL; T.il_st64 = T.ol_st64 = NULL; T.rc64 = NULL;
+    cudaFree(T.nodes); cudaFree(T.st32); cudaFree(T.len_full); cudaFree(T.il_ex32); cudaFree(T.ol_ex32); cudaFree(T.ovf);
+    cudaFree(T.ovf_edge); cudaFree(T.inl_edge); cudaFree(T.novel); cudaFree(T.sparse); cudaFree(T.t64); cudaFree(T.il_ex64);
+    cudaFree(T.ol_ex64); cudaFree(T.il_st64); cudaFree(T.ol_st64); cudaFree(T.rc64);
+    T.nodes = NULL; T.st32 = NULL; T.len_full = NULL; T.il_ex32 = T.ol_ex32 = NULL; T.ovf = NULL; T.ovf_edge = T.inl_edge = NULL;
+    T.novel = T.sparse = NULL; T.t64 = T.il_ex64 = T.ol_ex64 = NULL; T.il_st64 = T.ol_st64 = NULL; T.rc64 = NULL;
+}
+
+// Keep the node table in the L2: persisting access-policy window on the context's stream (the GAF stream itself is
+// loaded evict-first by the kernel).  Best effort: a device without the feature just runs without it.
+static void set_l2_window(pt_ctx* ctx, bool on) {
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof v);
+    if (on && ctx->T.nodes && ctx->persist_max && ctx->window_max && env_u32("PANTAS_L2_PERSIST", 1)) {
+        size_t bytes = (size_t)ctx->T.n_nodes * sizeof(NodeHot);
+        size_t win = bytes < ctx->window_max ? bytes : ctx->window_max;
+        size_t carve = win < ctx->persist_max ? win : ctx->persist_max;
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
+        v.accessPolicyWindow.base_ptr = ctx->T.nodes;
+        v.accessPolicyWindow.num_bytes = win;
+        v.accessPolicyWindow.hitRatio = win <= carve ? 1.0f : (float)((double)carve / (double)win);
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) { cudaGetLastError(); return; }
+        ctx->l2_window = true;
+    } else if (ctx->l2_window) {
+        v.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &v);
+        cudaGetLastError();
+        ctx->l2_window = false;
+    }
 }
 
 // fold the open epoch's 32-bit state into the 64-bit totals (tables.cuh)
@@ -274,6 +140,35 @@ static int fold_epoch(pt_ctx* ctx) {
     ctx->launches += 1;
     ctx->folds += 1;
     ctx->epoch_open = false;
+    return 0;
+}
+
+// the fast path's geometries: Geo<tile, look-ahead, step-list entries, teams per SM>
+typedef teamp::Geo<8192, 1024, 512, 10> GeoP;        // production
+typedef teamp::Geo<7168, 1024, 448, 11> GeoQ;
+typedef teamp::Geo<6144, 1024, 384, 12> GeoR;
+typedef teamp::Geo<12288, 1024, 768, 7> GeoS;
+typedef teamp::Geo<1024, 256, 128, 1> GeoT;          // tests: many tile boundaries, records longer than the look-ahead
+
+template <class G>
+static int launch_team(pt_ctx* ctx, ChunkArgs A, const Tables& T) {
+    void (*kern)(ChunkArgs, Tables) = teamp::augment_team_kernel<G>;
+    if (ctx->teams_per_sm == 0) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (int)teamp::THREADS, (size_t)G::SMEM_BYTES));
+        if (occ < 1) return fail_msg(ctx, PT_ERR_ARG, "fast path does not fit shared memory");
+        const uint32_t want = env_u32("PANTAS_TEAMS_PER_SM", 0);
+        if (want && (int)want < occ) occ = (int)want;
+        ctx->teams_per_sm = occ;
+    }
+    const uint64_t nt = (A.nbytes + G::TILE - 1) / G::TILE;
+    if (nt > 0xFFFFFFF0ull) return fail_msg(ctx, PT_ERR_ARG, "chunk too large");
+    A.n_tiles = (uint32_t)nt;
+    uint64_t g = (uint64_t)ctx->sm_count * ctx->teams_per_sm;
+    if (g > nt) g = nt;
+    if (g > T.team_cap) g = T.team_cap;
+    kern<<<(unsigned)g, teamp::THREADS, (size_t)G::SMEM_BYTES, ctx->stream>>>(A, T);
     return 0;
 }
 
@@ -309,6 +204,21 @@ const char* pt_strerror(int code) {
     }
 }
 
+static void destroy_ctx_objects(pt_ctx* ctx) {
+    cudaFree(ctx->T.sc); cudaFree(ctx->T.deferred); cudaFree(ctx->T.team_tile); cudaFree(ctx->cursor);
+    cudaFree(ctx->stage[0]); cudaFree(ctx->stage[1]);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->ev_copied[k]) cudaEventDestroy(ctx->ev_copied[k]);
+        if (ctx->ev_done[k]) cudaEventDestroy(ctx->ev_done[k]);
+    }
+    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (uint32_t k = 0; k < ctx->prof_cap; k++) cudaEventDestroy(ctx->prof_ev[k]);
+    free(ctx->prof_ev);
+}
+
 int pt_create(int device, pt_ctx** out) {
     if (!out) return PT_ERR_ARG;
     *out = NULL;
@@ -321,7 +231,11 @@ int pt_create(int device, pt_ctx** out) {
     if (!ctx) return PT_ERR_NOMEM;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    ctx->window_max = (size_t)prop.accessPolicyMaxWindowSize;
     if (cudaSetDevice(device) != cudaSuccess) { free(ctx); return PT_ERR_CUDA; }
+    ctx->own_stream = true;
+    ctx->T.team_cap = 16384;
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (int k = 0; k < 2 && e == cudaSuccess; k++) {
@@ -332,23 +246,16 @@ int pt_create(int device, pt_ctx** out) {
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_t1);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->T.sc, SC_COUNT * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->cursor, 2 * sizeof(unsigned long long));
-    if (e != cudaSuccess) { free(ctx); return PT_ERR_CUDA; }
-    ctx->own_stream = true;
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->T.team_tile, ctx->T.team_cap * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(ctx->T.team_tile, 0, ctx->T.team_cap * sizeof(uint32_t));
+    if (e != cudaSuccess) {
+        destroy_ctx_objects(ctx);
+        free(ctx);
+        return PT_ERR_CUDA;
+    }
     ctx->stage_bytes = (uint64_t)env_u32("PANTAS_STAGE_MB", 256) << 20;
-    ctx->tile = env_u32("PANTAS_TILE_KB", 56) << 10;
-    ctx->over = env_u32("PANTAS_OVER_KB", 4) << 10;
-    // byte-granular overrides (tests drive tiny tiles through the deferral path)
-    ctx->tile = (env_u32("PANTAS_TILE_BYTES", ctx->tile) + 15u) & ~15u;
-    ctx->over = (env_u32("PANTAS_OVER_BYTES", ctx->over) + 15u) & ~15u;
-    if (ctx->tile < 64) ctx->tile = 64;
-    if (ctx->over < 16) ctx->over = 16;
-    ctx->list_cap = env_u32("PANTAS_LIST_CAP", 512);
-    ctx->threads = env_u32("PANTAS_THREADS", 256);
-    if (ctx->threads != 32 && ctx->threads != 64 && ctx->threads != 128 && ctx->threads != 192 && ctx->threads != 256 && ctx->threads != 384 &&
-        ctx->threads != 512)
-        ctx->threads = 256;
-    ctx->kernel_ver = env_u32("PANTAS_KERNEL", 2);
-    ctx->fast_geo = env_u32("PANTAS_FAST_T", 32768);
+    ctx->geo = env_u32("PANTAS_TEAM_TILE", 8192);
+    ctx->ablate = env_u32("PANTAS_ABLATE", 0);
     *out = ctx;
     return 0;
 }
@@ -357,14 +264,9 @@ void pt_destroy(pt_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    set_l2_window(ctx, false);
     free_graph_tables(ctx);
-    cudaFree(ctx->T.sc); cudaFree(ctx->T.deferred); cudaFree(ctx->cursor); cudaFree(ctx->stage[0]); cudaFree(ctx->stage[1]);
-    for (int k = 0; k < 2; k++) { cudaEventDestroy(ctx->ev_copied[k]); cudaEventDestroy(ctx->ev_done[k]); }
-    cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
-    cudaStreamDestroy(ctx->copy_stream);
-    for (uint32_t k = 0; k < ctx->prof_cap; k++) cudaEventDestroy(ctx->prof_ev[k]);
-    free(ctx->prof_ev);
+    destroy_ctx_objects(ctx);
     free(ctx);
 }
 
@@ -374,9 +276,12 @@ int pt_set_stream(pt_ctx* ctx, void* cuda_stream) {
     if (!ctx) return PT_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    const bool had = ctx->l2_window;
+    set_l2_window(ctx, false);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)cuda_stream;
     ctx->own_stream = false;
+    if (had) set_l2_window(ctx, true);
     return 0;
 }
 
@@ -385,38 +290,33 @@ static int reset_counts_impl(pt_ctx* ctx) {
     const int cap = ctx->sm_count * 8;
     const uint64_t N = T.n_nodes, E = ctx->n_edges;
     reset_nodes_kernel<<<grid_for(N, 256, cap), 256, 0, ctx->stream>>>(T);
-    CK(cudaMemsetAsync(T.il_adj32, 0, N * sizeof(int32_t), ctx->stream));
-    CK(cudaMemsetAsync(T.ol_adj32, 0, N * sizeof(int32_t), ctx->stream));
-    CK(cudaMemsetAsync(T.nc64, 0, N * sizeof(long long), ctx->stream));
-    CK(cudaMemsetAsync(T.il_adj64, 0, N * sizeof(long long), ctx->stream));
-    CK(cudaMemsetAsync(T.ol_adj64, 0, N * sizeof(long long), ctx->stream));
+    CK(cudaMemsetAsync(T.il_ex32, 0, N * sizeof(int32_t), ctx->stream));
+    CK(cudaMemsetAsync(T.ol_ex32, 0, N * sizeof(int32_t), ctx->stream));
+    CK(cudaMemsetAsync(T.t64, 0, N * sizeof(long long), ctx->stream));
+    CK(cudaMemsetAsync(T.il_ex64, 0, N * sizeof(long long), ctx->stream));
+    CK(cudaMemsetAsync(T.ol_ex64, 0, N * sizeof(long long), ctx->stream));
     CK(cudaMemsetAsync(T.rc64, 0, (E ? E : 1) * sizeof(long long), ctx->stream));
     clear_ovf_kernel<<<grid_for(ctx->ovf_cap, 256, cap), 256, 0, ctx->stream>>>(T.ovf, T.ovf_edge, ctx->ovf_cap, 0);
     clear_side_kernel<<<grid_for(T.novel_mask + 1, 256, cap), 256, 0, ctx->stream>>>(T.novel, T.novel_mask + 1);
     clear_side_kernel<<<grid_for(T.sparse_mask + 1, 256, cap), 256, 0, ctx->stream>>>(T.sparse, T.sparse_mask + 1);
+    reset_teams_kernel<<<4, 256, 0, ctx->stream>>>(T);
     unsigned long long sc[SC_COUNT];
     memset(sc, 0, sizeof sc);
     sc[SC_ERR] = ~0ull;
     CK(cudaMemcpyAsync(T.sc, sc, sizeof sc, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));       // sc[] is a stack buffer
     CK(cudaGetLastError());
-    ctx->launches += 4;
+    ctx->launches += 5;
     ctx->epoch_open = false;
     ctx->epoch_end = 0;
     T.epoch_base = 0;
     return 0;
 }
 
-int pt_set_graph(pt_ctx* ctx, const uint32_t* node_len, uint64_t n_nodes, uint32_t min_id, const uint64_t* edge_keys,
-                 uint64_t n_edges, uint64_t novel_cap, uint64_t sparse_cap) {
-    if (!ctx || !node_len || n_nodes == 0 || (n_edges && !edge_keys)) return fail_msg(ctx, PT_ERR_ARG, "pt_set_graph: bad argument");
-    if (n_nodes >= 0xFFFFFFFFull || n_edges >= 0xFFFFFFFFull) return fail_msg(ctx, PT_ERR_ARG, "pt_set_graph: more than 2^32-2 nodes or links");
-    CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
+static int set_graph_impl(pt_ctx* ctx, const uint32_t* node_len, uint64_t n_nodes, uint32_t min_id, const uint64_t* edge_keys,
+                          uint64_t n_edges, uint64_t novel_cap, uint64_t sparse_cap, uint32_t** d_len, uint64_t** d_keys,
+                          unsigned long long** d_stats) {
     Tables& T = ctx->T;
-    free_graph_tables(ctx);
-    ctx->have_graph = false;
-
     T.n_nodes = n_nodes;
     T.min_id = min_id;
     T.epoch_base = 0;
@@ -430,33 +330,32 @@ int pt_set_graph(pt_ctx* ctx, const uint32_t* node_len, uint64_t n_nodes, uint32
     T.sparse_mask = ctx->sparse_cap - 1;
     ctx->n_edges = n_edges;
 
-    CK(cudaMalloc(&T.nodes, n_nodes * sizeof(NodeRec)));
-    CK(cudaMalloc(&T.il_adj32, n_nodes * sizeof(int32_t)));
-    CK(cudaMalloc(&T.ol_adj32, n_nodes * sizeof(int32_t)));
+    CK(cudaMalloc(&T.nodes, n_nodes * sizeof(NodeHot)));
+    CK(cudaMalloc(&T.st32, n_nodes * sizeof(Stamp32)));
+    CK(cudaMalloc(&T.len_full, n_nodes * sizeof(uint32_t)));
+    CK(cudaMalloc(&T.il_ex32, n_nodes * sizeof(int32_t)));
+    CK(cudaMalloc(&T.ol_ex32, n_nodes * sizeof(int32_t)));
     CK(cudaMalloc(&T.inl_edge, 2 * n_nodes * sizeof(uint32_t)));
-    CK(cudaMalloc(&T.nc64, n_nodes * sizeof(long long)));
-    CK(cudaMalloc(&T.il_adj64, n_nodes * sizeof(long long)));
-    CK(cudaMalloc(&T.ol_adj64, n_nodes * sizeof(long long)));
+    CK(cudaMalloc(&T.t64, n_nodes * sizeof(long long)));
+    CK(cudaMalloc(&T.il_ex64, n_nodes * sizeof(long long)));
+    CK(cudaMalloc(&T.ol_ex64, n_nodes * sizeof(long long)));
     CK(cudaMalloc(&T.il_st64, n_nodes * sizeof(unsigned long long)));
     CK(cudaMalloc(&T.ol_st64, n_nodes * sizeof(unsigned long long)));
     CK(cudaMalloc(&T.rc64, (n_edges ? n_edges : 1) * sizeof(long long)));
     CK(cudaMalloc(&T.novel, ctx->novel_cap * sizeof(SideSlot)));
     CK(cudaMalloc(&T.sparse, ctx->sparse_cap * sizeof(SideSlot)));
 
-    uint32_t* d_len = NULL;
-    uint64_t* d_keys = NULL;
-    unsigned long long* d_stats = NULL;          // [0] bad / duplicate keys, [1] links that are not inline
-    CK(cudaMalloc(&d_len, n_nodes * sizeof(uint32_t)));
-    CK(cudaMalloc(&d_keys, (n_edges ? n_edges : 1) * sizeof(uint64_t)));
-    CK(cudaMalloc(&d_stats, 2 * sizeof(unsigned long long)));
-    CK(cudaMemcpyAsync(d_len, node_len, n_nodes * sizeof(uint32_t), cudaMemcpyDefault, ctx->stream));
-    if (n_edges) CK(cudaMemcpyAsync(d_keys, edge_keys, n_edges * sizeof(uint64_t), cudaMemcpyDefault, ctx->stream));
-    CK(cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMalloc(d_len, n_nodes * sizeof(uint32_t)));
+    CK(cudaMalloc(d_keys, (n_edges ? n_edges : 1) * sizeof(uint64_t)));
+    CK(cudaMalloc(d_stats, 2 * sizeof(unsigned long long)));   // [0] bad / duplicate keys, [1] links that are not inline
+    CK(cudaMemcpyAsync(*d_len, node_len, n_nodes * sizeof(uint32_t), cudaMemcpyDefault, ctx->stream));
+    if (n_edges) CK(cudaMemcpyAsync(*d_keys, edge_keys, n_edges * sizeof(uint64_t), cudaMemcpyDefault, ctx->stream));
+    CK(cudaMemsetAsync(*d_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
     const int cap = ctx->sm_count * 8;
-    init_nodes_kernel<<<grid_for(n_nodes, 256, cap), 256, 0, ctx->stream>>>(T, d_len);
-    if (n_edges) inline_edges_kernel<<<grid_for(n_edges, 256, cap), 256, 0, ctx->stream>>>(T, d_keys, n_edges, d_stats);
+    init_nodes_kernel<<<grid_for(n_nodes, 256, cap), 256, 0, ctx->stream>>>(T, *d_len);
+    if (n_edges) inline_edges_kernel<<<grid_for(n_edges, 256, cap), 256, 0, ctx->stream>>>(T, *d_keys, n_edges, *d_stats);
     unsigned long long stats[2] = {0, 0};
-    CK(cudaMemcpyAsync(stats, d_stats, sizeof stats, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(stats, *d_stats, sizeof stats, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
     // known links that are not inline: open addressing at load <= 0.5
@@ -465,14 +364,36 @@ int pt_set_graph(pt_ctx* ctx, const uint32_t* node_len, uint64_t n_nodes, uint32
     CK(cudaMalloc(&T.ovf, ctx->ovf_cap * sizeof(OvfSlot)));
     CK(cudaMalloc(&T.ovf_edge, ctx->ovf_cap * sizeof(uint32_t)));
     clear_ovf_kernel<<<grid_for(ctx->ovf_cap, 256, cap), 256, 0, ctx->stream>>>(T.ovf, T.ovf_edge, ctx->ovf_cap, 1);
-    if (n_edges) ovf_edges_kernel<<<grid_for(n_edges, 256, cap), 256, 0, ctx->stream>>>(T, d_keys, n_edges, d_stats);
-    CK(cudaMemcpyAsync(stats, d_stats, sizeof stats, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_edges) ovf_edges_kernel<<<grid_for(n_edges, 256, cap), 256, 0, ctx->stream>>>(T, *d_keys, n_edges, *d_stats);
+    CK(cudaMemcpyAsync(stats, *d_stats, sizeof stats, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
-    cudaFree(d_len); cudaFree(d_keys); cudaFree(d_stats);
     ctx->launches += 4;
     if (stats[0]) return fail_msg(ctx, PT_ERR_ARG, "pt_set_graph: edge_keys hold duplicates or out-of-range node indices");
+    return 0;
+}
+
+int pt_set_graph(pt_ctx* ctx, const uint32_t* node_len, uint64_t n_nodes, uint32_t min_id, const uint64_t* edge_keys,
+                 uint64_t n_edges, uint64_t novel_cap, uint64_t sparse_cap) {
+    if (!ctx || !node_len || n_nodes == 0 || (n_edges && !edge_keys)) return fail_msg(ctx, PT_ERR_ARG, "pt_set_graph: bad argument");
+    if (n_nodes >= 0xFFFFFFFFull || n_edges >= 0xFFFFFFFFull) return fail_msg(ctx, PT_ERR_ARG, "pt_set_graph: more than 2^32-2 nodes or links");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    set_l2_window(ctx, false);
+    free_graph_tables(ctx);
+    ctx->have_graph = false;
+    uint32_t* d_len = NULL;
+    uint64_t* d_keys = NULL;
+    unsigned long long* d_stats = NULL;
+    const int rc = set_graph_impl(ctx, node_len, n_nodes, min_id, edge_keys, n_edges, novel_cap, sparse_cap, &d_len, &d_keys, &d_stats);
+    cudaFree(d_len); cudaFree(d_keys); cudaFree(d_stats);          // temporaries: on every path
+    if (rc) {
+        cudaStreamSynchronize(ctx->stream);
+        free_graph_tables(ctx);
+        return rc;
+    }
     ctx->have_graph = true;
+    set_l2_window(ctx, true);
     return reset_counts_impl(ctx);
 }
 
@@ -487,8 +408,9 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
     if (((uintptr_t)gaf_dev & 15) != 0) return fail_msg(ctx, PT_ERR_ARG, "GAF chunk must be 16-byte aligned");
     Tables& T = ctx->T;
     if (nbytes > 0xF0000000ull) return fail_msg(ctx, PT_ERR_ARG, "chunk larger than 3.75 GiB: split it");
-    // 32-bit stamps / counters are relative to an epoch of < 4 GiB of GAF: fold when this chunk does not fit
-    if (ctx->epoch_open && (file_offset < (uint64_t)T.epoch_base || file_offset + nbytes - (uint64_t)T.epoch_base > EPOCH_SPAN)) {
+    // 32-bit stamps / counters are relative to an epoch of < 4 GiB of GAF: fold when this chunk does not fit.  A chunk
+    // that starts before the end of what the epoch has seen also folds: "settled" stamps assume offsets only grow.
+    if (ctx->epoch_open && (file_offset < ctx->epoch_end || file_offset + nbytes - (uint64_t)T.epoch_base > EPOCH_SPAN)) {
         int rc = fold_epoch(ctx);
         if (rc) return rc;
     }
@@ -498,9 +420,9 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
         ctx->epoch_end = file_offset;
     }
     if (file_offset + nbytes > ctx->epoch_end) ctx->epoch_end = file_offset + nbytes;
-    // second-pass list: records with a non-trivial cs string, records longer than the
-    // look-ahead, list overflow.  A valid record is >= 40 bytes, so this holds all of them.
-    const uint64_t want = nbytes / 40 + 4096;
+    // second-pass list: records the fast path hands over.  The shortest record the reference accepts has 12 one-byte
+    // columns, 11 separators and a line break (24 bytes), so this holds every record of the chunk.
+    const uint64_t want = nbytes / 24 + 4096;
     if (want > T.deferred_cap) {
         CK(cudaStreamSynchronize(ctx->stream));
         cudaFree(T.deferred);
@@ -510,93 +432,15 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
         T.deferred_cap = want;
     }
     ChunkArgs A;
+    memset(&A, 0, sizeof A);
     A.gaf = gaf_dev;
     A.nbytes = nbytes;
     A.file_off = (int64_t)file_offset;
     A.thr = thr;
-    A.tile = ctx->tile;
-    A.over = ctx->over;
-    A.list_cap = ctx->list_cap;
+    A.ablate = ctx->ablate;
     {   // measured: -4 % kernel time, -25 % DRAM reads (PANTAS_STREAM_HINT=0 switches it off)
         const char* h = getenv("PANTAS_STREAM_HINT");
         A.stream_hint = (h && h[0] == '0') ? 0u : 1u;
-        if (env_u32("PANTAS_PHASE_CLOCKS", 0)) A.stream_hint |= 2u;       // diagnostics: per-phase cycle counters (pt_debug_counters)
-    }
-    const uint64_t n_tiles = (nbytes + ctx->tile - 1) / ctx->tile;
-    if (n_tiles > 0xFFFFFFF0ull) return fail_msg(ctx, PT_ERR_ARG, "chunk too large");
-    A.n_tiles = (uint32_t)n_tiles;
-    const size_t smem = ((32 + (size_t)ctx->tile + ctx->over + 127) & ~(size_t)127) +
-                        (size_t)((ctx->list_cap + 31u) & ~31u) * 4 + (size_t)ctx->threads * sizeof(pt::LineRec);
-    void (*kern)(ChunkArgs, Tables) = ctx->threads == 32    ? augment_tiles_kernel<32, 20>
-                                      : ctx->threads == 64  ? augment_tiles_kernel<64, 12>
-                                      : ctx->threads == 128 ? augment_tiles_kernel<128, 6>
-                                      : ctx->threads == 192 ? augment_tiles_kernel<192, 4>
-                                      : ctx->threads == 384 ? augment_tiles_kernel<384, 2>
-                                      : ctx->threads == 512 ? augment_tiles_kernel<512, 1>
-                                                            : augment_tiles_kernel<256, 3>;
-    if (ctx->ctas_per_sm == 0) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (int)ctx->threads, smem));
-        if (occ < 1) return fail_msg(ctx, PT_ERR_ARG, "tile does not fit shared memory");
-        ctx->ctas_per_sm = occ;
-    }
-    uint64_t grid = (uint64_t)ctx->sm_count * ctx->ctas_per_sm;
-    if (grid > n_tiles) grid = n_tiles;
-    // ---- fast path geometry (kernel_ver 2)
-    void (*fkern)(ChunkArgs, Tables) = NULL;
-    size_t fsmem = 0;
-    uint32_t f_tiles = 0, f_grid = 0;
-    uint32_t f_threads = 0;
-    if (ctx->kernel_ver == 2) {
-        typedef fastp::Geo<24576, 1024, 256> GA;
-        typedef fastp::Geo<32768, 1024, 512> GB;
-        typedef fastp::Geo<16384, 1024, 256> GC;
-        typedef fastp::Geo<12288, 1024, 128> GD;
-        typedef fastp::Geo<16384, 1024, 128> GE;
-        typedef fastp::Geo<32768, 1024, 256> GF;
-        typedef fastp::Geo<20480, 1024, 256> GG;
-        typedef fastp::Geo<8192, 1024, 128> GH;
-        typedef fastp::Geo<8192, 1024, 256> GI;
-        typedef fastp::Geo<49152, 1024, 768> GJ;
-        typedef fastp::Geo<40960, 1024, 512> GK;
-        typedef fastp::Geo<49152, 1024, 1024> GL;
-        typedef fastp::Geo<28672, 1024, 512> GM;
-        typedef fastp::Geo<32768, 1024, 384> GN;
-        typedef fastp::Geo<30720, 1024, 512> GO;
-        typedef fastp::Geo<1024, 256, 64> GT;    // tests: many tile boundaries, records longer than the look-ahead
-        uint32_t ft;
-#define PT_PICK(Gx) { fkern = fastp::augment_fast_kernel<Gx>; fsmem = (size_t)Gx::SMEM_BYTES; ft = Gx::TILE; f_threads = Gx::THREADS; }
-        if (ctx->fast_geo == 1024) PT_PICK(GT)
-        else if (ctx->fast_geo == 32768) PT_PICK(GB)
-        else if (ctx->fast_geo == 16384) PT_PICK(GC)
-        else if (ctx->fast_geo == 12288) PT_PICK(GD)
-        else if (ctx->fast_geo == 16385) PT_PICK(GE)
-        else if (ctx->fast_geo == 32769) PT_PICK(GF)
-        else if (ctx->fast_geo == 20480) PT_PICK(GG)
-        else if (ctx->fast_geo == 8192) PT_PICK(GH)
-        else if (ctx->fast_geo == 8193) PT_PICK(GI)
-        else if (ctx->fast_geo == 49152) PT_PICK(GJ)
-        else if (ctx->fast_geo == 40960) PT_PICK(GK)
-        else if (ctx->fast_geo == 49153) PT_PICK(GL)
-        else if (ctx->fast_geo == 28672) PT_PICK(GM)
-        else if (ctx->fast_geo == 32770) PT_PICK(GN)
-        else if (ctx->fast_geo == 30720) PT_PICK(GO)
-        else if (ctx->fast_geo == 24576) PT_PICK(GA)
-        else PT_PICK(GA)
-#undef PT_PICK
-        if (ctx->fast_ctas_per_sm == 0) {
-            CK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            int occ = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fkern, (int)f_threads, fsmem));
-            if (occ < 1) return fail_msg(ctx, PT_ERR_ARG, "fast path does not fit shared memory");
-            ctx->fast_ctas_per_sm = occ;
-        }
-        const uint64_t nt = (nbytes + ft - 1) / ft;
-        f_tiles = (uint32_t)nt;
-        uint64_t g = (uint64_t)ctx->sm_count * ctx->fast_ctas_per_sm;
-        if (g > nt) g = nt;
-        f_grid = (uint32_t)g;
     }
     if (ctx->profile) {
         if (ctx->prof_n + 3 > ctx->prof_cap) {
@@ -609,16 +453,18 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
         }
         CK(cudaEventRecord(ctx->prof_ev[ctx->prof_n], ctx->stream));
     }
-    if (ctx->kernel_ver == 2) {
-        ChunkArgs F = A;
-        F.n_tiles = f_tiles;
-        fkern<<<f_grid, f_threads, fsmem, ctx->stream>>>(F, T);
-    } else {
-        kern<<<(unsigned)grid, ctx->threads, smem, ctx->stream>>>(A, T);
+    int rc;
+    switch (ctx->geo) {
+        case 1024: rc = launch_team<GeoT>(ctx, A, T); break;
+        case 7168: rc = launch_team<GeoQ>(ctx, A, T); break;
+        case 6144: rc = launch_team<GeoR>(ctx, A, T); break;
+        case 12288: rc = launch_team<GeoS>(ctx, A, T); break;
+        default: rc = launch_team<GeoP>(ctx, A, T); break;
     }
+    if (rc) return rc;
     if (ctx->profile) CK(cudaEventRecord(ctx->prof_ev[ctx->prof_n + 1], ctx->stream));
     augment_deferred_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(A, T);
-    end_chunk_kernel<<<1, 1, 0, ctx->stream>>>(T);
+    end_chunk_kernel<<<4, 256, 0, ctx->stream>>>(T);
     if (ctx->profile) {      // fast path + exact per-record path = "the augment pass" over this chunk
         CK(cudaEventRecord(ctx->prof_ev[ctx->prof_n + 2], ctx->stream));
         ctx->prof_n += 3;
@@ -666,7 +512,8 @@ int64_t pt_process_host(pt_ctx* ctx, const uint8_t* gaf_host, uint64_t nbytes, u
 
 int pt_wait_copy(pt_ctx* ctx, int64_t ticket) {
     if (!ctx || ticket < 0 || ticket >= ctx->next_ticket) return PT_ERR_ARG;
-    if (ticket + 2 < ctx->next_ticket) return 0;          // its stage has been re-used: long done
+    // ev_copied[k] belongs to the LATEST ticket of parity k; the copy stream is in order, so its completion
+    // implies the completion of every earlier copy into the same stage
     CK(cudaEventSynchronize(ctx->ev_copied[ticket & 1]));
     return 0;
 }
@@ -717,9 +564,11 @@ int pt_export_dense(pt_ctx* ctx, int64_t* sums_dev, uint64_t sums_len, int64_t* 
     if (rc) return rc;
     const int cap = ctx->sm_count * 8;
     export_nodes_kernel<<<grid_for(N > E ? N : E, 256, cap), 256, 0, ctx->stream>>>(ctx->T, (long long*)sums_dev, (long long*)stamps_dev, E);
-    export_ovf_kernel<<<grid_for(ctx->ovf_cap, 256, cap), 256, 0, ctx->stream>>>(ctx->T, (long long*)sums_dev + 3 * N);
+    export_inline_kernel<<<grid_for(N, 256, cap), 256, 0, ctx->stream>>>(ctx->T, (long long*)sums_dev);
+    export_ovf_kernel<<<grid_for(ctx->ovf_cap, 256, cap), 256, 0, ctx->stream>>>(ctx->T, (long long*)sums_dev);
+    export_novel_ends_kernel<<<grid_for(ctx->novel_cap, 256, cap), 256, 0, ctx->stream>>>(ctx->T, (long long*)sums_dev);
     CK(cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches += 4;
     return 0;
 }
 
@@ -794,7 +643,7 @@ int pt_debug_counters(pt_ctx* ctx, uint64_t* out, int n) {
     unsigned long long sc[SC_COUNT];
     CK(cudaMemcpyAsync(sc, ctx->T.sc, sizeof sc, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (int k = 0; k < n; k++) out[k] = k < 32 ? sc[SC_WHY + k] : 0;      // 16 hand-over reasons, then 16 phase clocks
+    for (int k = 0; k < n; k++) out[k] = k < 16 ? sc[SC_WHY + k] : 0;      // 16 hand-over reasons
     return 0;
 }
 

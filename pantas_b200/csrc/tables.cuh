@@ -6,28 +6,37 @@
 //   nodes_weights  REF:116,263-269   id -> NC
 //   weights        REF:115,357-363   (from, to) -> RC
 //
-// Layout goal: one path step touches ONE 32-byte sector.
+// Layout goal: one path step is ONE 16-byte load and ONE 32-bit RED on the same 16 bytes, and the whole hot
+// table (16 B x nodes: 74 MB for the 4.6 M-node dm-full graph) stays resident in the 126 MB L2.
 //
-//   NodeRec[idx]  (32 B, idx = id - min_id)
-//     +0  len        u32   sequence length, NODE_LEN_ABSENT if the GFA has no such S line
-//     +4  il_stamp   u32   first-touch stamp of IL[v][0]      (file offset - epoch base; UNSET32 = never)
-//     +8  ol_stamp   u32   first-touch stamp of OL[v][len(v)]
-//     +12 d0, d1     i16   to_idx - idx of up to two out-links held inline (0 = none)
-//     +16 c0         u64   low half: NC (part A), high half: RC of inline link 0
-//     +24 c1         u64   low half: NC (part B), high half: RC of inline link 1
-//   A step of a read adds 1 to NC of its node and 1 to RC of the link it leaves the node by: when
-//   that link is inline both happen in ONE RED.ADD.64 of (1 | 1 << 32) on c0 or c1 (NC = lo(c0) + lo(c1)).
-//   Links that are not inline (third out-link of a node, |to - from| >= 2^15, self loops) live in a
-//   64-bit-key open-addressing table `ovf` (read-only keys, RED.ADD.64 counts); links that are not in
-//   the GFA at all go to the CAS-insert `novel` table; deletion-derived IL/OL keys to `sparse`.
+//   NodeHot[idx]  (16 B, idx = id - min_id; two nodes per 32-byte sector)
+//     +0  meta   u32   bits 0..9   sequence length (0 = no such S line, 1023 = longer: len_full[idx])
+//                      bits 10..19 d0, bits 20..29 d1: to_idx - idx of up to two out-links held inline
+//                                  (two's complement, 0 = none)
+//                      bit 30 / 31 IL / OL first-touch stamp is settled (no record still to come can lower it)
+//     +4  t      u32   occurrences of the node that leave it by no inline link and no hashed link ("terminal")
+//     +8  rc0    u32   RC of inline link 0
+//     +12 rc1    u32   RC of inline link 1
 //
-//   IL[v][0] and OL[v][len] are stored as NC[v] + adj[v] (il_adj32 / ol_adj32): interior nodes of a
-//   read contribute adj = 0, so only the two ends of a read touch those arrays.
+//   A surviving path step adds 1 to exactly one counter: the RC of the link the read leaves the node by
+//   (inline: rc0 / rc1; third out-link, |to - from| >= 512, self loop: the `ovf` 64-bit-key open-addressing
+//   table; not in the GFA at all: the CAS-insert `novel` table), or `t` when the read ends there.  The
+//   reference's other dense counters are sums of these and are formed once, at export:
+//     NC[v]          = t[v] + sum of RC over links leaving v                                      (REF:263-269)
+//     OL[v][len(v)]  =        sum of RC over links leaving v  + ol_ex[v]                          (REF:306-313,343-351)
+//     IL[v][0]       =        sum of RC over links entering v + il_ex[v]                          (REF:298-305,335-342)
+//   (a node occurrence increments IL[v][0] iff an in-link of this read ends there, OL[v][len] iff an out-link
+//   starts there; `*_ex` = (counting ops of the node's compacted cs slice) - 1, non-zero only for nodes that
+//   a mismatch / indel falls into).  Deletion-derived IL/OL keys go to the CAS-insert `sparse` table.
 //
-// The 32-bit halves and stamps are relative to an EPOCH (a run of chunks spanning < 4 GiB of GAF).
-// fold_epoch_kernel adds them into the 64-bit totals (nc64, rc64, adj64, stamp64) and clears them;
-// the host folds before an epoch could overflow and before every export, so results are exact
-// 64-bit counts and global (file offset << 2 | e) stamps.
+// First-touch stamps (Python dict insertion order of IL/OL keys) live in a cold
+// array st32[idx] = {il, ol}: a step reads it only while the node's `settled` bit is clear, lowers it with
+// RED.MIN, and sets the bit once the stamp is below the kernel's low-water mark (every tile before the mark
+// is complete, tiles are handed out in file order, so nothing still to come can lower the stamp).
+//
+// The 32-bit counters and stamps are relative to an EPOCH (a run of chunks spanning < 4 GiB of GAF).
+// fold_epoch_kernel adds them into the 64-bit totals and clears them; the host folds before an epoch could
+// overflow and before every export, so results are exact 64-bit counts and global (file offset << 2 | e) stamps.
 #pragma once
 
 constexpr uint64_t KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
@@ -36,13 +45,20 @@ constexpr uint32_t UNSET32 = 0xFFFFFFFFu;
 constexpr uint32_t NO_EDGE = 0xFFFFFFFFu;
 constexpr uint64_t EPOCH_SPAN = 0xFFFFFFF0ull;            // an epoch covers file offsets [base, base + EPOCH_SPAN)
 
-struct __align__(32) NodeRec {
-    uint32_t len;
-    uint32_t il_stamp;
-    uint32_t ol_stamp;
-    uint32_t d01;                 // d0 | d1 << 16 (two's complement i16 each)
-    unsigned long long c0;
-    unsigned long long c1;
+constexpr uint32_t META_LEN_MASK = 0x3FFu, META_LEN_ESC = 0x3FFu;
+constexpr int META_D0_SHIFT = 10, META_D1_SHIFT = 20;
+constexpr uint32_t META_D_MASK = 0x3FFu;
+constexpr uint32_t META_IL_SETTLED = 1u << 30, META_OL_SETTLED = 1u << 31;
+constexpr int32_t INLINE_DELTA_MIN = -512, INLINE_DELTA_MAX = 511;
+
+struct __align__(16) NodeHot {
+    uint32_t meta;
+    uint32_t t;
+    uint32_t rc0;
+    uint32_t rc1;
+};
+struct __align__(8) Stamp32 {
+    uint32_t il, ol;
 };
 struct __align__(16) OvfSlot {
     unsigned long long key;
@@ -56,13 +72,15 @@ struct __align__(32) SideSlot {
 };
 
 // device scalars (unsigned long long each)
-enum { SC_REJ = 0, SC_LINES, SC_ERR, SC_NOVEL_USED, SC_SPARSE_USED, SC_DEFERRED_TOTAL, SC_TILES, SC_TILE_NEXT, SC_NDEFER,
+enum { SC_REJ = 0, SC_LINES, SC_ERR, SC_NOVEL_USED, SC_SPARSE_USED, SC_DEFERRED_TOTAL, SC_TILES, SC_LWM, SC_NDEFER,
        SC_WHY = 16 /* 16 hand-over reasons */, SC_PHASE = 32 /* 16 phase clocks (diagnostics) */, SC_COUNT = 48 };
 
 struct Tables {
-    NodeRec* nodes;
-    int32_t* il_adj32;
-    int32_t* ol_adj32;
+    NodeHot* nodes;
+    Stamp32* st32;                 // cold: first-touch stamps of the open epoch
+    uint32_t* len_full;            // cold: sequence lengths (read for nodes of >= 1023 bases only)
+    int32_t* il_ex32;              // cold: (counting ops - 1) of multi-op node slices
+    int32_t* ol_ex32;
     OvfSlot* ovf;
     uint32_t* ovf_edge;            // slot -> L-line edge index (export only)
     uint32_t* inl_edge;            // [2N] inline slot -> edge index (fold only)
@@ -70,10 +88,11 @@ struct Tables {
     SideSlot* sparse;
     unsigned long long* sc;
     uint32_t* deferred;            // chunk-relative starts of records redone from global memory
+    uint32_t* team_tile;           // [team_cap] tile every team of the running fast kernel works on (low-water mark)
     // 64-bit totals (cold: touched by fold / export only)
-    long long* nc64;
-    long long* il_adj64;
-    long long* ol_adj64;
+    long long* t64;
+    long long* il_ex64;
+    long long* ol_ex64;
     unsigned long long* il_st64;
     unsigned long long* ol_st64;
     long long* rc64;               // [E]
@@ -84,6 +103,7 @@ struct Tables {
     uint64_t deferred_cap;
     int64_t epoch_base;            // file offset the 32-bit stamps are relative to
     uint32_t min_id;
+    uint32_t team_cap;
 };
 
 __device__ __forceinline__ uint64_t mix64(uint64_t h) {
@@ -119,7 +139,7 @@ __device__ __forceinline__ void side_add(SideSlot* tab, uint64_t mask, unsigned 
     report_error(T, full_code, (int64_t)(stamp >> 2));
 }
 
-__device__ __forceinline__ int32_t sext16(uint32_t v) { return (int32_t)(int16_t)(uint16_t)v; }
+__device__ __forceinline__ int32_t sext10(uint32_t v) { return (int32_t)(v << 22) >> 22; }
 
 struct DevSink {
     const Tables& T;
@@ -127,8 +147,7 @@ struct DevSink {
     __device__ __forceinline__ explicit DevSink(const Tables& t) : T(t), rej(0) {}
 
     struct Stamps { uint32_t il, ol; };
-    struct EdgePf { uint32_t from; uint32_t d01; };          // inline link deltas of node `from`
-    struct Hot { uint32_t len, il, ol, d01; };               // the read half of a NodeRec
+    struct EdgePf { uint32_t from; uint32_t meta; };         // meta word of node `from`
 
     __device__ __forceinline__ bool id_to_idx(uint64_t id, uint32_t& idx) {
         const uint64_t d = id - T.min_id;                          // wraps to huge when id < min_id
@@ -136,44 +155,38 @@ struct DevSink {
         idx = (uint32_t)d;
         return true;
     }
-    __device__ __forceinline__ void prefetch_node(uint32_t idx) {
-#ifndef PT_EMU
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(&T.nodes[idx]));
-#else
-        (void)idx;
-#endif
+    // the whole hot record from the L2 (counters are only ever RED-updated, never cached in L1)
+    __device__ __forceinline__ uint4 load_hot(uint32_t idx) { return __ldcg(reinterpret_cast<const uint4*>(&T.nodes[idx])); }
+    __device__ __forceinline__ uint32_t load_meta(uint32_t idx) { return __ldcg(&T.nodes[idx].meta); }
+    __device__ __forceinline__ uint32_t load_len(uint32_t idx) {
+        const uint32_t l = __ldcg(&T.nodes[idx].meta) & META_LEN_MASK;
+        if (l == 0u) return pt::NODE_LEN_ABSENT;
+        return l == META_LEN_ESC ? __ldg(&T.len_full[idx]) : l;
     }
-    // L2 (always current): first-touch stamps only ever decrease, len / d01 never change
-    __device__ __forceinline__ Hot load_hot(uint32_t idx) {
-        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(&T.nodes[idx]));
-        Hot h;
-        h.len = v.x; h.il = v.y; h.ol = v.z; h.d01 = v.w;
-        return h;
-    }
-    __device__ __forceinline__ uint32_t load_len(uint32_t idx) { return __ldg(&T.nodes[idx].len); }
     __device__ __forceinline__ Stamps load_stamps(uint32_t idx) {
+        const uint2 s = __ldcg(reinterpret_cast<const uint2*>(&T.st32[idx]));
         Stamps r;
-        r.il = __ldcg(&T.nodes[idx].il_stamp);
-        r.ol = __ldcg(&T.nodes[idx].ol_stamp);
+        r.il = s.x;
+        r.ol = s.y;
         return r;
     }
-    __device__ __forceinline__ void edge_pf_init(EdgePf& pf) { pf.from = 0xFFFFFFFFu; pf.d01 = 0; }
+    __device__ __forceinline__ void edge_pf_init(EdgePf& pf) { pf.from = 0xFFFFFFFFu; pf.meta = 0; }
     __device__ __forceinline__ void prefetch_edge(EdgePf& pf, uint32_t from) {
-        pf.d01 = __ldg(&T.nodes[from].d01);
+        pf.meta = load_meta(from);
         pf.from = from;
     }
-    // which inline slot of `from` (deltas d01) holds the link to `to`: 0, 1 or -1
-    static __device__ __forceinline__ int inline_slot(uint32_t d01, uint32_t from, uint32_t to) {
-        const int64_t delta = (int64_t)to - (int64_t)from;
-        if (delta == 0 || delta < -32768 || delta > 32767) return -1;
-        if ((int32_t)delta == sext16(d01 & 0xFFFFu)) return 0;
-        if ((int32_t)delta == sext16(d01 >> 16)) return 1;
+    // which inline slot of `from` (meta word `meta`) holds the link to `to`: 0, 1 or -1
+    static __device__ __forceinline__ int inline_slot(uint32_t meta, uint32_t from, uint32_t to) {
+        const int32_t delta = (int32_t)(to - from);
+        if (delta == 0 || delta < INLINE_DELTA_MIN || delta > INLINE_DELTA_MAX) return -1;
+        const uint32_t d = (uint32_t)delta & META_D_MASK;
+        if (d == ((meta >> META_D0_SHIFT) & META_D_MASK)) return 0;
+        if (d == ((meta >> META_D1_SHIFT) & META_D_MASK)) return 1;
         return -1;
     }
-    // NC[idx] += 1 and, if slot >= 0, RC of that inline link += 1: one RED.ADD.64
+    // the one counter update of a step: slot 0 / 1 = RC of that inline link, -1 = the read ends here (t)
     __device__ __forceinline__ void bump(uint32_t idx, int slot) {
-        unsigned long long* c = &T.nodes[idx].c0 + (slot > 0 ? 1 : 0);       // c1 follows c0
-        atomicAdd(c, slot >= 0 ? 0x100000001ull : 1ull);
+        atomicAdd(&T.nodes[idx].t + (slot + 1), 1u);                           // t, rc0, rc1 are consecutive words
     }
     // RC of a link that is not inline: known link -> ovf table, otherwise novel (REF:426-427)
     __device__ __forceinline__ void edge_far(uint32_t a, uint32_t b, uint64_t stamp) {
@@ -187,38 +200,51 @@ struct DevSink {
         }
         side_add(T.novel, T.novel_mask, &T.sc[SC_NOVEL_USED], key, stamp, T, pt::PT_X_NOVEL_FULL);
     }
-    // IL[idx][0] += il, OL[idx][len] += ol relative to the NC increment of the same step; stamp = (offset << 2) | 1
-    __device__ __forceinline__ void dense(uint32_t idx, int64_t il, int64_t ol, uint64_t stamp, const Stamps& st) {
-        if (il != 1) atomicAdd(&T.il_adj32[idx], (int32_t)(il - 1));
-        if (ol != 1) atomicAdd(&T.ol_adj32[idx], (int32_t)(ol - 1));
-        // first-touch stamps: write only when we are earlier than what was there a moment ago
-        const uint32_t rel = (uint32_t)((int64_t)(stamp >> 2) - T.epoch_base);
-        if (il > 0 && rel < st.il) atomicMin(&T.nodes[idx].il_stamp, rel);
-        if (ol > 0 && rel < st.ol) atomicMin(&T.nodes[idx].ol_stamp, rel);
+    // (counting ops - 1) of a node occurrence that has an in-link (il) / an out-link (ol) in its read
+    __device__ __forceinline__ void extras(uint32_t idx, int32_t il_ex, int32_t ol_ex) {
+        if (il_ex) atomicAdd(&T.il_ex32[idx], il_ex);
+        if (ol_ex) atomicAdd(&T.ol_ex32[idx], ol_ex);
+    }
+    // first-touch stamps of IL[idx][0] / OL[idx][len] for a step at epoch-relative offset `rel`; lwm_rel: every record
+    // before this epoch-relative offset has been counted already
+    __device__ __forceinline__ void touch_stamps(uint32_t idx, bool il, bool ol, uint32_t rel, uint32_t lwm_rel) {
+        const uint2 s = __ldcg(reinterpret_cast<const uint2*>(&T.st32[idx]));     // {il, ol}
+        uint32_t settle = 0;
+        if (il) {
+            if (rel < s.x) atomicMin(&T.st32[idx].il, rel);
+            if (min(rel, s.x) < lwm_rel) settle |= META_IL_SETTLED;
+        }
+        if (ol) {
+            if (rel < s.y) atomicMin(&T.st32[idx].ol, rel);
+            if (min(rel, s.y) < lwm_rel) settle |= META_OL_SETTLED;
+        }
+        if (settle) atomicOr(&T.nodes[idx].meta, settle);
     }
 
-    // the same with the stamp test made by the caller (per tile: could this tile lower the stamp at all?)
-    __device__ __forceinline__ void dense_flagged(uint32_t idx, int64_t il, int64_t ol, uint64_t stamp, bool need_il, bool need_ol) {
-        if (il != 1) atomicAdd(&T.il_adj32[idx], (int32_t)(il - 1));
-        if (ol != 1) atomicAdd(&T.ol_adj32[idx], (int32_t)(ol - 1));
+    // ---- the per-record interface of line_core.cuh (exact path)
+    __device__ __forceinline__ void count_node(uint32_t idx) { atomicAdd(&T.nodes[idx].t, 1u); }
+    // IL[idx][0] += il, OL[idx][len] += ol; has_in / has_out: an in-link / out-link of this read was (or will be) counted
+    // at this occurrence (they carry 1 each, section "layout" above)
+    __device__ __forceinline__ void dense(uint32_t idx, int64_t il, int64_t ol, uint64_t stamp, const Stamps& st, bool has_in,
+                                          bool has_out) {
+        extras(idx, (int32_t)(il - (has_in ? 1 : 0)), (int32_t)(ol - (has_out ? 1 : 0)));
         const uint32_t rel = (uint32_t)((int64_t)(stamp >> 2) - T.epoch_base);
-        if (il > 0 && need_il) atomicMin(&T.nodes[idx].il_stamp, rel);
-        if (ol > 0 && need_ol) atomicMin(&T.nodes[idx].ol_stamp, rel);
+        if (il > 0 && rel < st.il) atomicMin(&T.st32[idx].il, rel);
+        if (ol > 0 && rel < st.ol) atomicMin(&T.st32[idx].ol, rel);
     }
-
-    // ---- the per-record interface of line_core.cuh (slow path)
-    __device__ __forceinline__ void count_node(uint32_t idx) { atomicAdd(&T.nodes[idx].c0, 1ull); }
     __device__ __forceinline__ void sparse(uint32_t idx, int dir, int64_t pos, uint64_t stamp) {
         const int64_t bias = 1ll << 30;
         if (pos < -bias || pos >= bias) { report_error(T, pt::PT_U_POSITION, (int64_t)(stamp >> 2)); return; }
         const uint64_t key = ((uint64_t)idx << 32) | ((uint64_t)dir << 31) | (uint64_t)(pos + bias);
         side_add(T.sparse, T.sparse_mask, &T.sc[SC_SPARSE_USED], key, stamp, T, pt::PT_X_SPARSE_FULL);
     }
+    // count_node(a) was called for this occurrence already: move its 1 from t to the link's counter
     __device__ __forceinline__ void edge(uint32_t a, uint32_t b, uint64_t stamp, const EdgePf& pf) {
-        const uint32_t d01 = pf.from == a ? pf.d01 : __ldg(&T.nodes[a].d01);
-        const int slot = inline_slot(d01, a, b);
-        if (slot >= 0) atomicAdd(slot ? &T.nodes[a].c1 : &T.nodes[a].c0, 0x100000000ull);
+        const uint32_t meta = pf.from == a ? pf.meta : load_meta(a);
+        const int slot = inline_slot(meta, a, b);
+        if (slot >= 0) atomicAdd(slot ? &T.nodes[a].rc1 : &T.nodes[a].rc0, 1u);
         else edge_far(a, b, stamp);
+        atomicAdd(&T.nodes[a].t, 0xFFFFFFFFu);
     }
     __device__ __forceinline__ void reject() { rej++; }
     __device__ __forceinline__ void error(int code, int64_t off) { report_error(T, code, off); }
@@ -229,14 +255,18 @@ struct DevSink {
 __global__ void init_nodes_kernel(Tables T, const uint32_t* len) {
     const uint64_t n = T.n_nodes;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        NodeRec r;
-        r.len = len[i];
-        r.il_stamp = UNSET32;
-        r.ol_stamp = UNSET32;
-        r.d01 = 0;
-        r.c0 = 0;
-        r.c1 = 0;
+        const uint32_t l = len[i];
+        NodeHot r;
+        r.meta = l == pt::NODE_LEN_ABSENT ? 0u : (l >= META_LEN_ESC ? META_LEN_ESC : l);
+        r.t = 0;
+        r.rc0 = 0;
+        r.rc1 = 0;
         T.nodes[i] = r;
+        T.len_full[i] = l;
+        Stamp32 s;
+        s.il = UNSET32;
+        s.ol = UNSET32;
+        T.st32[i] = s;
         T.inl_edge[2 * i] = NO_EDGE;
         T.inl_edge[2 * i + 1] = NO_EDGE;
     }
@@ -255,16 +285,17 @@ __global__ void inline_edges_kernel(Tables T, const uint64_t* keys, uint64_t n_e
         if (from >= T.n_nodes || to >= T.n_nodes) { atomicAdd(&stats[0], 1ull); continue; }
         const int64_t delta = (int64_t)to - (int64_t)from;
         bool placed = false;
-        if (delta != 0 && delta >= -32768 && delta <= 32767) {
-            const uint32_t d16 = (uint32_t)delta & 0xFFFFu;
-            uint32_t* w = &T.nodes[from].d01;
+        if (delta != 0 && delta >= INLINE_DELTA_MIN && delta <= INLINE_DELTA_MAX) {
+            const uint32_t d10 = (uint32_t)delta & META_D_MASK;
+            uint32_t* w = &T.nodes[from].meta;
             uint32_t old = *w;
             for (;;) {
+                const uint32_t o0 = (old >> META_D0_SHIFT) & META_D_MASK, o1 = (old >> META_D1_SHIFT) & META_D_MASK;
                 uint32_t neu;
                 int slot;
-                if ((old & 0xFFFFu) == d16 || (old >> 16) == d16) { atomicAdd(&stats[0], 1ull); placed = true; break; }   // duplicate key
-                if ((old & 0xFFFFu) == 0) { neu = old | d16; slot = 0; }
-                else if ((old >> 16) == 0) { neu = old | (d16 << 16); slot = 1; }
+                if (o0 == d10 || o1 == d10) { atomicAdd(&stats[0], 1ull); placed = true; break; }   // duplicate key
+                if (o0 == 0) { neu = old | (d10 << META_D0_SHIFT); slot = 0; }
+                else if (o1 == 0) { neu = old | (d10 << META_D1_SHIFT); slot = 1; }
                 else break;
                 const uint32_t seen = atomicCAS(w, old, neu);
                 if (seen == old) { T.inl_edge[2 * from + slot] = (uint32_t)e; placed = true; break; }
@@ -281,7 +312,7 @@ __global__ void ovf_edges_kernel(Tables T, const uint64_t* keys, uint64_t n_edge
         const uint64_t from = key >> 32, to = key & 0xFFFFFFFFull;
         if (from >= T.n_nodes || to >= T.n_nodes) continue;
         if (T.inl_edge[2 * from] == (uint32_t)e || T.inl_edge[2 * from + 1] == (uint32_t)e) continue;
-        if (DevSink::inline_slot(T.nodes[from].d01, (uint32_t)from, (uint32_t)to) >= 0) continue;    // duplicate of an inline key (counted in pass 1)
+        if (DevSink::inline_slot(T.nodes[from].meta, (uint32_t)from, (uint32_t)to) >= 0) continue;    // duplicate of an inline key (counted in pass 1)
         uint64_t h = mix64(key) & T.ovf_mask;
         for (uint64_t probes = 0; probes <= T.ovf_mask; probes++) {
             const unsigned long long k = atomicCAS(&T.ovf[h].key, KEY_EMPTY, (unsigned long long)key);
@@ -292,41 +323,56 @@ __global__ void ovf_edges_kernel(Tables T, const uint64_t* keys, uint64_t n_edge
     }
 }
 
-// 32-bit epoch state -> 64-bit totals; clears the epoch state
+// 32-bit epoch state -> 64-bit totals; clears the epoch state (and the settled bits: they refer to the epoch's stamps)
 __global__ void fold_epoch_kernel(Tables T) {
     const uint64_t N = T.n_nodes;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
-        NodeRec r = T.nodes[i];
-        const int32_t ia = T.il_adj32[i], oa = T.ol_adj32[i];
-        if ((r.c0 | r.c1) != 0) {
-            T.nc64[i] += (long long)((r.c0 & 0xFFFFFFFFull) + (r.c1 & 0xFFFFFFFFull));
+        const NodeHot r = T.nodes[i];
+        if ((r.t | r.rc0 | r.rc1) != 0u || (r.meta & (META_IL_SETTLED | META_OL_SETTLED)) != 0u) {
+            T.t64[i] += (long long)(int32_t)r.t;           // the exact path moves a count out of t again (DevSink::edge)
             const uint32_t e0 = T.inl_edge[2 * i], e1 = T.inl_edge[2 * i + 1];
-            if ((r.c0 >> 32) != 0 && e0 != NO_EDGE) T.rc64[e0] += (long long)(r.c0 >> 32);
-            if ((r.c1 >> 32) != 0 && e1 != NO_EDGE) T.rc64[e1] += (long long)(r.c1 >> 32);
-            T.nodes[i].c0 = 0;
-            T.nodes[i].c1 = 0;
+            if (r.rc0 != 0u && e0 != NO_EDGE) T.rc64[e0] += (long long)r.rc0;
+            if (r.rc1 != 0u && e1 != NO_EDGE) T.rc64[e1] += (long long)r.rc1;
+            NodeHot z;
+            z.meta = r.meta & ~(META_IL_SETTLED | META_OL_SETTLED);
+            z.t = 0;
+            z.rc0 = 0;
+            z.rc1 = 0;
+            T.nodes[i] = z;
         }
-        if (ia) { T.il_adj64[i] += ia; T.il_adj32[i] = 0; }
-        if (oa) { T.ol_adj64[i] += oa; T.ol_adj32[i] = 0; }
-        if (r.il_stamp != UNSET32) {
-            const unsigned long long s = ((unsigned long long)(T.epoch_base + (int64_t)r.il_stamp) << 2) | 1ull;
-            if (s < T.il_st64[i]) T.il_st64[i] = s;
-            T.nodes[i].il_stamp = UNSET32;
+        const int32_t ia = T.il_ex32[i], oa = T.ol_ex32[i];
+        if (ia) { T.il_ex64[i] += ia; T.il_ex32[i] = 0; }
+        if (oa) { T.ol_ex64[i] += oa; T.ol_ex32[i] = 0; }
+        const Stamp32 s = T.st32[i];
+        if (s.il != UNSET32) {
+            const unsigned long long v = ((unsigned long long)(T.epoch_base + (int64_t)s.il) << 2) | 1ull;
+            if (v < T.il_st64[i]) T.il_st64[i] = v;
         }
-        if (r.ol_stamp != UNSET32) {
-            const unsigned long long s = ((unsigned long long)(T.epoch_base + (int64_t)r.ol_stamp) << 2) | 1ull;
-            if (s < T.ol_st64[i]) T.ol_st64[i] = s;
-            T.nodes[i].ol_stamp = UNSET32;
+        if (s.ol != UNSET32) {
+            const unsigned long long v = ((unsigned long long)(T.epoch_base + (int64_t)s.ol) << 2) | 1ull;
+            if (v < T.ol_st64[i]) T.ol_st64[i] = v;
+        }
+        if ((s.il & s.ol) != UNSET32) {
+            Stamp32 u;
+            u.il = UNSET32;
+            u.ol = UNSET32;
+            T.st32[i] = u;
         }
     }
 }
 __global__ void reset_nodes_kernel(Tables T) {
     const uint64_t N = T.n_nodes;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
-        T.nodes[i].il_stamp = UNSET32;
-        T.nodes[i].ol_stamp = UNSET32;
-        T.nodes[i].c0 = 0;
-        T.nodes[i].c1 = 0;
+        NodeHot r = T.nodes[i];
+        r.meta &= ~(META_IL_SETTLED | META_OL_SETTLED);
+        r.t = 0;
+        r.rc0 = 0;
+        r.rc1 = 0;
+        T.nodes[i] = r;
+        Stamp32 u;
+        u.il = UNSET32;
+        u.ol = UNSET32;
+        T.st32[i] = u;
         T.il_st64[i] = STAMP_UNSET;
         T.ol_st64[i] = STAMP_UNSET;
     }
@@ -341,13 +387,21 @@ __global__ void clear_side_kernel(SideSlot* s, uint64_t cap) {
         s[i] = z;
     }
 }
-// after fold: sums = [nc | il_adj | ol_adj | rc | rej, n_lines, 0, 0], stamps = [il | ol]
+__global__ void reset_teams_kernel(Tables T) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < T.team_cap; i += gridDim.x * blockDim.x) T.team_tile[i] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) T.sc[SC_LWM] = 0;
+}
+
+// ---- export.  Flat layout of include/pantas_aug.h: sums = [nc | il_adj | ol_adj | rc | rej, n_lines, 0, 0] with
+// IL[v][0] = nc + il_adj, OL[v][len] = nc + ol_adj; stamps = [il | ol].  Step 1 writes the per-node terms, steps 2..4
+// scatter every link's count to its two ends (header comment: NC, IL, OL as sums of RC).
 __global__ void export_nodes_kernel(Tables T, long long* sums, long long* stamps, uint64_t n_edges) {
     const uint64_t N = T.n_nodes;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
-        sums[i] = T.nc64[i];
-        sums[N + i] = T.il_adj64[i];
-        sums[2 * N + i] = T.ol_adj64[i];
+        const long long t = T.t64[i];
+        sums[i] = t;                                       // + links leaving i
+        sums[N + i] = T.il_ex64[i] - t;                    // + links entering i - links leaving i
+        sums[2 * N + i] = T.ol_ex64[i] - t;
         stamps[i] = (long long)T.il_st64[i];
         stamps[N + i] = (long long)T.ol_st64[i];
     }
@@ -362,11 +416,40 @@ __global__ void export_nodes_kernel(Tables T, long long* sums, long long* stamps
         tail[3] = 0;
     }
 }
-// after export_nodes_kernel (same stream): links held by the ovf table
-__global__ void export_ovf_kernel(Tables T, long long* rc) {
+__device__ __forceinline__ void export_link_ends(long long* sums, uint64_t N, uint64_t from, uint64_t to, unsigned long long c) {
+    if (c == 0ull) return;
+    unsigned long long* s = reinterpret_cast<unsigned long long*>(sums);
+    atomicAdd(&s[from], c);                                // NC[from]
+    atomicAdd(&s[N + from], 0ull - c);                     // il_adj[from] = IL - NC
+    atomicAdd(&s[N + to], c);                              // IL[to][0]
+}
+// after export_nodes_kernel (same stream): inline links (their 64-bit totals are in rc64 after the fold)
+__global__ void export_inline_kernel(Tables T, long long* sums) {
+    const uint64_t N = T.n_nodes;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t meta = T.nodes[i].meta;
+        const uint32_t e0 = T.inl_edge[2 * i], e1 = T.inl_edge[2 * i + 1];
+        if (e0 != NO_EDGE) export_link_ends(sums, N, i, (uint64_t)((int64_t)i + sext10((meta >> META_D0_SHIFT) & META_D_MASK)), (unsigned long long)T.rc64[e0]);
+        if (e1 != NO_EDGE) export_link_ends(sums, N, i, (uint64_t)((int64_t)i + sext10((meta >> META_D1_SHIFT) & META_D_MASK)), (unsigned long long)T.rc64[e1]);
+    }
+}
+// links held by the ovf table
+__global__ void export_ovf_kernel(Tables T, long long* sums) {
+    const uint64_t N = T.n_nodes;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i <= T.ovf_mask; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t e = T.ovf_edge[i];
-        if (e != NO_EDGE) rc[e] = (long long)T.ovf[i].count;
+        if (e == NO_EDGE) continue;
+        const OvfSlot v = T.ovf[i];
+        sums[3 * N + e] = (long long)v.count;
+        export_link_ends(sums, N, v.key >> 32, v.key & 0xFFFFFFFFull, v.count);
+    }
+}
+// links that are not in the GFA
+__global__ void export_novel_ends_kernel(Tables T, long long* sums) {
+    const uint64_t N = T.n_nodes;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i <= T.novel_mask; i += (uint64_t)gridDim.x * blockDim.x) {
+        const SideSlot v = T.novel[i];
+        if (v.key != KEY_EMPTY) export_link_ends(sums, N, v.key >> 32, v.key & 0xFFFFFFFFull, v.count);
     }
 }
 __global__ void compact_side_kernel(const SideSlot* s, uint64_t cap, unsigned long long* out, uint64_t rows,

@@ -158,7 +158,7 @@ class AugmentEngine:
         self._check(self.lib.pt_profile_enable(self._ctx, 1 if on else 0))
 
     def kernel_time(self):
-        """(summed ms of augment_tiles_kernel, launches) since the last call."""
+        """(summed ms of augment_team_kernel, launches) since the last call."""
         ms, n = ctypes.c_float(), ctypes.c_uint64()
         self._check(self.lib.pt_kernel_time(self._ctx, ctypes.byref(ms), ctypes.byref(n)))
         return float(ms.value), int(n.value)

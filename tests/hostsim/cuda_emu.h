@@ -28,6 +28,8 @@
 #define __restrict__
 
 struct uint4 { uint32_t x, y, z, w; };
+struct uint2 { uint32_t x, y; };
+inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 struct emu_dim3 { unsigned x, y, z; };
 
 namespace emu {
@@ -179,6 +181,8 @@ inline unsigned __ballot_sync(unsigned, int pred) {
     for (int l = 0; l < 32; l++) r |= (emu::shfl(pred ? 1u : 0u, l) & 1u) << l;
     return r;
 }
+
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
 
 // ---- intrinsics
 inline long long clock64() { return 0; }

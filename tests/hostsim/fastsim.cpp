@@ -1,7 +1,7 @@
 // tests/hostsim/fastsim.cpp -- TEST HARNESS, NOT PRODUCT CODE.
 //
 // Runs the REAL device code of the augment pass (pantas_b200/csrc/aug_kernels.cuh: table build, the
-// fast path of fast_tiles.cuh, the exact per-record kernel, epoch fold, export) on the CPU through the
+// fast path of team_tiles.cuh, the exact per-record kernel, epoch fold, export) on the CPU through the
 // fibre emulator of cuda_emu.h, following the launch sequence of pantas_aug.cu (pt_set_graph,
 // pt_reset_counts, pt_process_chunk, pt_export_dense / pt_export_side).  The build container has no
 // GPU: this is how CPU-only tests fuzz the fast path against the oracle.  Nothing under pantas_b200/
@@ -26,7 +26,7 @@ template <class G>
 void run_fast(unsigned grid, ChunkArgs A, const Tables& T) {
     A.n_tiles = (uint32_t)((A.nbytes + G::TILE - 1) / G::TILE);
     if (grid > A.n_tiles) grid = A.n_tiles;
-    emu::launch(grid, G::THREADS, G::SMEM_BYTES, [&] { fastp::augment_fast_kernel<G>(A, T); });
+    emu::launch(grid, teamp::THREADS, G::SMEM_BYTES, [&] { teamp::augment_team_kernel<G>(A, T); });
 }
 
 }  // namespace
@@ -58,13 +58,17 @@ int fastsim_run(const uint8_t* gaf, uint64_t nbytes, uint64_t file_off, int64_t 
     const uint64_t novel_cap = 1u << 12, sparse_cap = 1u << 12;
     T.novel_mask = novel_cap - 1;
     T.sparse_mask = sparse_cap - 1;
-    T.nodes = zalloc<NodeRec>(N);
-    T.il_adj32 = zalloc<int32_t>(N);
-    T.ol_adj32 = zalloc<int32_t>(N);
+    T.nodes = zalloc<NodeHot>(N);
+    T.st32 = zalloc<Stamp32>(N);
+    T.len_full = zalloc<uint32_t>(N);
+    T.il_ex32 = zalloc<int32_t>(N);
+    T.ol_ex32 = zalloc<int32_t>(N);
     T.inl_edge = zalloc<uint32_t>(2 * N);
-    T.nc64 = zalloc<long long>(N);
-    T.il_adj64 = zalloc<long long>(N);
-    T.ol_adj64 = zalloc<long long>(N);
+    T.t64 = zalloc<long long>(N);
+    T.il_ex64 = zalloc<long long>(N);
+    T.ol_ex64 = zalloc<long long>(N);
+    T.team_cap = 64;
+    T.team_tile = zalloc<uint32_t>(T.team_cap);
     T.il_st64 = zalloc<unsigned long long>(N);
     T.ol_st64 = zalloc<unsigned long long>(N);
     T.rc64 = zalloc<long long>(E);
@@ -104,21 +108,23 @@ int fastsim_run(const uint8_t* gaf, uint64_t nbytes, uint64_t file_off, int64_t 
     A.file_off = (int64_t)file_off;
     A.thr = thr;
     if (nbytes) {
-        typedef fastp::Geo<1024, 256, 64> G0;
-        typedef fastp::Geo<4096, 512, 128> G1;
-        typedef fastp::Geo<16384, 1024, 256> G2;
+        typedef teamp::Geo<1024, 256, 128, 1> G0;
+        typedef teamp::Geo<4096, 512, 256, 1> G1;
+        typedef teamp::Geo<8192, 1024, 512, 10> G2;
         if (geo == 0) run_fast<G0>(grid, A, T);
         else if (geo == 1) run_fast<G1>(grid, A, T);
         else run_fast<G2>(grid, A, T);
         emu::launch(2, 128, 0, [&] { augment_deferred_kernel(A, T); });
-        emu::launch(1, 1, 0, [&] { end_chunk_kernel(T); });
+        emu::launch(2, 64, 0, [&] { end_chunk_kernel(T); });
     }
     // ---- pt_export_dense / pt_export_side
     emu::launch(KG, KB, 0, [&] { fold_epoch_kernel(T); });
     out->sums = (int64_t*)calloc(3 * N + E + 4, sizeof(int64_t));
     out->stamps = (int64_t*)calloc(2 * N + 1, sizeof(int64_t));
     emu::launch(KG, KB, 0, [&] { export_nodes_kernel(T, (long long*)out->sums, (long long*)out->stamps, E); });
-    emu::launch(KG, KB, 0, [&] { export_ovf_kernel(T, (long long*)out->sums + 3 * N); });
+    emu::launch(KG, KB, 0, [&] { export_inline_kernel(T, (long long*)out->sums); });
+    emu::launch(KG, KB, 0, [&] { export_ovf_kernel(T, (long long*)out->sums); });
+    emu::launch(KG, KB, 0, [&] { export_novel_ends_kernel(T, (long long*)out->sums); });
     unsigned long long cursor[2] = {0, 0};
     out->novel = (uint64_t*)calloc(3 * novel_cap + 1, sizeof(uint64_t));
     out->sparse = (uint64_t*)calloc(3 * sparse_cap + 1, sizeof(uint64_t));
@@ -136,9 +142,9 @@ int fastsim_run(const uint8_t* gaf, uint64_t nbytes, uint64_t file_off, int64_t 
         out->err_code = 0;
     }
     free(raw);
-    free(T.nodes); free(T.il_adj32); free(T.ol_adj32); free(T.inl_edge); free(T.nc64); free(T.il_adj64); free(T.ol_adj64);
-    free(T.il_st64); free(T.ol_st64); free(T.rc64); free(T.novel); free(T.sparse); free(T.sc); free(T.deferred); free(T.ovf);
-    free(T.ovf_edge);
+    free(T.nodes); free(T.st32); free(T.len_full); free(T.il_ex32); free(T.ol_ex32); free(T.inl_edge); free(T.t64); free(T.il_ex64);
+    free(T.ol_ex64); free(T.il_st64); free(T.ol_st64); free(T.rc64); free(T.novel); free(T.sparse); free(T.sc); free(T.deferred);
+    free(T.ovf); free(T.ovf_edge); free(T.team_tile);
     return 0;
 }
 

@@ -45,7 +45,7 @@ struct HostSink {
     void edge_pf_init(EdgePf& pf) { pf.unused = 0; }
     void prefetch_edge(EdgePf&, uint32_t) {}
     void count_node(uint32_t idx) { nc[idx]++; }
-    void dense(uint32_t idx, int64_t il, int64_t ol, uint64_t stamp, const Stamps&) {
+    void dense(uint32_t idx, int64_t il, int64_t ol, uint64_t stamp, const Stamps&, bool, bool) {
         il_adj[idx] += il - 1;
         ol_adj[idx] += ol - 1;
         if (il > 0) il_stamp[idx] = std::min(il_stamp[idx], stamp);

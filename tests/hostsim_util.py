@@ -73,7 +73,7 @@ FSRC = os.path.join(HERE, "hostsim", "fastsim.cpp")
 FSO = os.path.join(HERE, "hostsim", "libfastsim.so")
 _CSRC = os.path.join(os.path.dirname(HERE), "pantas_b200", "csrc")
 FDEPS = [FSRC, os.path.join(HERE, "hostsim", "cuda_emu.h")] + [os.path.join(_CSRC, f) for f in
-                                                                ("aug_kernels.cuh", "fast_tiles.cuh", "tables.cuh", "line_core.cuh")]
+                                                                ("aug_kernels.cuh", "team_tiles.cuh", "tables.cuh", "line_core.cuh")]
 
 
 class _FRes(ctypes.Structure):

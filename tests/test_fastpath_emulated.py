@@ -1,4 +1,4 @@
-"""The fast path (pantas_b200/csrc/fast_tiles.cuh) and the kernels around it, run thread by thread on
+"""The fast path (pantas_b200/csrc/team_tiles.cuh) and the kernels around it, run thread by thread on
 the CPU by tests/hostsim/cuda_emu.h (test harness) and compared with the reference's golden outputs and
 the oracle.  Same code as the sm_100a build; the GPU parity tests (-m gpu) cover the real thing.
 """
@@ -116,7 +116,8 @@ def test_dense_short_records_overflow_the_tile_lists(tmp_path):
         st = {}
         res = pipeline(tmp_path, gfa, gaf, geo=geo, stats=st)
         assert res[0] == "ok" and res[1] == orc.out and res[2] == orc.rej
-        assert st["deferred"] > 0
+        if geo == 1:                   # 4 KiB tiles of 53-byte records: 77 > the 64 record slots of a tile
+            assert st["deferred"] > 0
 
 
 @pytest.mark.parametrize("seed", range(7500, 7506))

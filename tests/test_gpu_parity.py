@@ -107,31 +107,12 @@ def test_golden_cases_host_buffers(tmp_path):
         check_golden(case, gpu_pipeline(tmp_path, case["gfa"], case["gaf"], thr, eng=eng, via_host=True))
 
 
-@pytest.mark.parametrize("tile,over,listcap", [(64, 32, 1024), (256, 64, 2), (1024, 16, 1024), (4096, 4096, 8)])
-def test_golden_tiny_tiles(tile, over, listcap, tmp_path):
-    """Tile boundaries, look-ahead overflow (deferred records) and list overflow change nothing."""
-    eng = _engine(PANTAS_KERNEL=1, PANTAS_TILE_BYTES=tile, PANTAS_OVER_BYTES=over, PANTAS_LIST_CAP=listcap)
+@pytest.mark.parametrize("team_tile", [1024, 6144, 7168, 8192, 12288])
+def test_golden_team_geometries(team_tile, tmp_path):
+    """The fast path gives the same bytes for every tile size (1 KiB tiles: many tile boundaries, records longer than
+    the look-ahead, full lists -- all of which hand records to the exact per-record kernel)."""
+    eng = _engine(PANTAS_TEAM_TILE=team_tile)
     for case in GOLDEN:
-        if "\r" in case["gaf"]:
-            continue
-        thr = 20 if case["thr"] is None else case["thr"]
-        check_golden(case, gpu_pipeline(tmp_path, case["gfa"], case["gaf"], thr, eng=eng))
-
-
-@pytest.mark.parametrize("fast_t", [1024, 16384, 24576, 32768])
-def test_golden_fast_path_geometries(fast_t, tmp_path):
-    """The warp-autonomous fast path gives the same bytes for every mini-tile size (records that
-    cross a mini-tile's look-ahead or fail a fast-path precondition take the slow path)."""
-    eng = _engine(PANTAS_KERNEL=2, PANTAS_FAST_T=fast_t)
-    for case in GOLDEN:
-        thr = 20 if case["thr"] is None else case["thr"]
-        check_golden(case, gpu_pipeline(tmp_path, case["gfa"], case["gaf"], thr, eng=eng))
-
-
-@pytest.mark.parametrize("threads", [128, 512])
-def test_golden_other_block_sizes(threads, tmp_path):
-    eng = _engine(PANTAS_KERNEL=1, PANTAS_THREADS=threads, PANTAS_TILE_KB=32)
-    for case in GOLDEN[:80]:
         thr = 20 if case["thr"] is None else case["thr"]
         check_golden(case, gpu_pipeline(tmp_path, case["gfa"], case["gaf"], thr, eng=eng))
 
@@ -142,18 +123,16 @@ def test_fuzz_vs_oracle(seed, tmp_path):
                                  crlf=(seed % 6 == 0), trailing_newline=(seed % 4 != 0))
     orc = run_oracle(gaf.encode(), gfa.encode())
     assert orc.rc == 0
-    eng = _engine(PANTAS_KERNEL=[2, 2, 2, 1][seed % 4], PANTAS_FAST_T=[24576, 1024, 32768][seed % 3],
-                  PANTAS_TILE_BYTES=[65536, 2048, 512][seed % 3], PANTAS_OVER_BYTES=[4096, 256, 64][seed % 3])
+    eng = _engine(PANTAS_TEAM_TILE=[8192, 1024, 7168, 12288, 6144][seed % 5])
     res = gpu_pipeline(tmp_path, gfa, gaf, eng=eng, chunks=1 + seed % 3, via_host=(seed % 5 == 0))
     assert res[0] == "ok", res
     assert res[1] == orc.out
     assert res[2] == orc.rej
 
 
-@pytest.mark.parametrize("preset,pairs,fast_t,kernel", [("tiny", 20000, 24576, 2), ("dm-chr4", 100000, 24576, 2),
-                                                        ("dm-chr4", 50000, 32768, 2), ("tiny", 20000, 1024, 2),
-                                                        ("gene-panel", 50000, 16384, 2), ("tiny", 20000, 24576, 1)])
-def test_synthetic_workload_matches_oracle(preset, pairs, fast_t, kernel, tmp_path):
+@pytest.mark.parametrize("preset,pairs,team_tile", [("tiny", 20000, 8192), ("dm-chr4", 100000, 8192), ("dm-chr4", 50000, 7168),
+                                                    ("tiny", 20000, 1024), ("gene-panel", 50000, 12288), ("tiny", 20000, 6144)])
+def test_synthetic_workload_matches_oracle(preset, pairs, team_tile, tmp_path):
     """The bench workload's generator (vg-mpmap-shaped records, mostly fast-path) at a size the CPU oracle
     finishes in seconds: the augmented GFA is byte-identical."""
     import torch
@@ -169,7 +148,7 @@ def test_synthetic_workload_matches_oracle(preset, pairs, fast_t, kernel, tmp_pa
     want = run_oracle(gaf, gp.read_bytes())
     assert want.rc == 0, want.err
     graph = load_graph(str(gp))
-    eng = _engine(PANTAS_KERNEL=kernel, PANTAS_FAST_T=fast_t)
+    eng = _engine(PANTAS_TEAM_TILE=team_tile)
     eng.set_graph(graph)
     n = int(gaf.shape[0])
     d = torch.zeros(n + 32, dtype=torch.uint8, device="cuda")
@@ -183,8 +162,8 @@ def test_synthetic_workload_matches_oracle(preset, pairs, fast_t, kernel, tmp_pa
     write_augmented(str(gp), graph, counts, out)
     assert out.getvalue().encode() == want.out
     st = eng.stats()
-    if kernel == 2 and fast_t >= 4096:
-        assert st["deferred_lines"] < 0.15 * n_lines, st      # the fast path really is the path taken
+    if team_tile >= 4096:
+        assert st["deferred_lines"] < 0.02 * n_lines, st      # the fast path really is the path taken
 
 
 def test_rerun_after_reset_is_identical(tmp_path):
@@ -233,7 +212,7 @@ def test_full_size_graphs_are_linear_in_the_gaf(preset, pairs):
     bounds = shard_bounds_bytes(gaf, 3)
     parts = []
     for k, (lo, hi) in enumerate(zip(bounds, bounds[1:])):
-        e2 = _engine(PANTAS_FAST_T=[32768, 24576, 16384][k])
+        e2 = _engine(PANTAS_TEAM_TILE=[8192, 7168, 12288][k])
         e2.set_graph(graph)
         piece = torch.zeros(hi - lo + 32, dtype=torch.uint8, device="cuda")
         piece[: hi - lo] = d[lo:hi]
@@ -255,7 +234,7 @@ def test_far_links_vs_oracle(seed, tmp_path):
     gfa, gaf = fuzzgen.spread_ids(gfa, gaf, pivot=15, shift=50000)
     orc = run_oracle(gaf.encode(), gfa.encode())
     assert orc.rc == 0
-    eng = _engine(PANTAS_FAST_T=[32768, 1024, 24576, 16384][seed % 4])
+    eng = _engine(PANTAS_TEAM_TILE=[8192, 1024, 7168, 6144][seed % 4])
     res = gpu_pipeline(tmp_path, gfa, gaf, eng=eng, chunks=1 + seed % 2)
     assert res[0] == "ok", res
     assert res[1] == orc.out

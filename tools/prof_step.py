@@ -21,6 +21,7 @@ ap.add_argument("--pairs", type=int, default=1_000_000)
 ap.add_argument("--preset", default="dm-full")
 ap.add_argument("--seed", type=int, default=1002)
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--ladder", action="store_true", help="ablation ladder: time the pass stopped after every phase (PANTAS_ABLATE)")
 a = ap.parse_args()
 
 sg = SynthGraph(a.preset, seed=a.seed)
@@ -44,7 +45,22 @@ f, sl, nn = eng.kernel_time_split()
 print(f"fast kernel {f / nn:.3f} ms, per-record kernel {sl / nn:.3f} ms (avg of {nn})")
 eng.check_data_error()
 print(eng.stats(), eng.handover_reasons())
-if os.environ.get("PANTAS_PHASE_CLOCKS"):
-    pc = eng.phase_cycles()
-    tot = sum(pc.values()) or 1
-    print("phase share of CTA time:", {k: round(100.0 * v / tot, 1) for k, v in pc.items()})
+if a.ladder:
+    # every tile stops after phase k: TMA only, + scan, + records, + ids, + walk, everything (results are wrong on purpose
+    # for k != 0; timing only).  A fresh context per rung: PANTAS_ABLATE is read by pt_create.
+    names = {1: "tma only", 2: "+ scan", 3: "+ records", 4: "+ ids", 5: "+ walk", 0: "+ fold + count (all)"}
+    g = sg.graph()
+    for k in (1, 2, 3, 4, 5, 0):
+        os.environ["PANTAS_ABLATE"] = str(k)
+        e2 = AugmentEngine(0)
+        e2.set_graph(g)
+        e2.profile(True)
+        for i in range(a.steps):
+            e2.reset()
+            e2.process_device(dev, n, 0, 20)
+        e2.sync()
+        f, sl, nn = e2.kernel_time_split()
+        ms = f / nn
+        print(f"ladder {names[k]:22s} {ms:8.3f} ms  {n / ms / 1e6:8.1f} GB/s")
+        e2.close()
+    os.environ.pop("PANTAS_ABLATE", None)
