@@ -50,6 +50,8 @@ __device__ __forceinline__ void tma_load_1d_stream(void* dst_smem, const void* s
                  : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// named barrier `id` (1..15) for `count` threads of the CTA (SASS: BAR.SYNC id, count)
+__device__ __forceinline__ void named_barrier(uint32_t id, uint32_t count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 #else   // ---- test harness: the bulk copy is a memcpy that has completed when it returns
 #define PT_DYNAMIC_SMEM(name) uint8_t* const name = emu::S().dyn
 // (*bar = number of completed phases; a waiter yields until the phase with its parity is complete)
@@ -62,6 +64,7 @@ inline void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, ui
 }
 inline void tma_load_1d_stream(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) { tma_load_1d(dst_smem, src_gmem, bytes, bar); }
 inline void fence_async_smem() {}
+inline void named_barrier(uint32_t id, uint32_t count) { emu_named_barrier(id, count); }
 #endif
 
 struct ChunkArgs {
@@ -71,17 +74,22 @@ struct ChunkArgs {
     int64_t thr;
     uint32_t n_tiles;
     uint32_t stream_hint;   // bit 0: load the GAF with an L2 evict-first policy
+    uint32_t loose;         // 1: team-level barriers inside a tile, one CTA-wide barrier per tile (PANTAS_LOOSE)
     uint32_t ablate;        // diagnostics (PANTAS_ABLATE): 0 = the whole pass, k = every tile stops after phase k (timing only)
 };
 
 // why a record is handed to the slow path (pt_debug_counters)
 enum { WHY_LONG = 0, WHY_COLUMNS, WHY_INTS, WHY_TAGS, WHY_CS, WHY_PATH, WHY_STEPS_FULL, WHY_WALK, WHY_LINES_FULL, WHY_V1 };
 
+__device__ __noinline__ void defer_line_impl(unsigned long long* sc, uint32_t* deferred, uint64_t deferred_cap, uint64_t chunk_pos,
+                                            int64_t file_off, int why) {
+    atomicAdd(&sc[SC_WHY + why], 1ull);
+    const unsigned long long j = atomicAdd(&sc[SC_NDEFER], 1ull);
+    if (j < deferred_cap) deferred[j] = (uint32_t)chunk_pos;
+    else report_error_sc(sc, pt::PT_X_DEFER_FULL, file_off + (int64_t)chunk_pos);
+}
 __device__ __forceinline__ void defer_line(const Tables& T, uint64_t chunk_pos, int64_t file_off, int why = WHY_V1) {
-    atomicAdd(&T.sc[SC_WHY + why], 1ull);
-    const unsigned long long j = atomicAdd(&T.sc[SC_NDEFER], 1ull);
-    if (j < T.deferred_cap) T.deferred[j] = (uint32_t)chunk_pos;
-    else report_error(T, pt::PT_X_DEFER_FULL, file_off + (int64_t)chunk_pos);
+    defer_line_impl(T.sc, T.deferred, T.deferred_cap, chunk_pos, file_off, why);
 }
 
 #include "team_tiles.cuh"

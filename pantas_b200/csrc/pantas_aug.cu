@@ -24,6 +24,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "../../include/pantas_aug.h"
 #include "line_core.cuh"
 
@@ -143,32 +145,35 @@ static int fold_epoch(pt_ctx* ctx) {
     return 0;
 }
 
-// the fast path's geometries: Geo<tile, look-ahead, step-list entries, teams per SM>
-typedef teamp::Geo<8192, 1024, 512, 10> GeoP;        // production
-typedef teamp::Geo<7168, 1024, 448, 11> GeoQ;
-typedef teamp::Geo<6144, 1024, 384, 12> GeoR;
-typedef teamp::Geo<12288, 1024, 768, 7> GeoS;
-typedef teamp::Geo<1024, 256, 128, 1> GeoT;          // tests: many tile boundaries, records longer than the look-ahead
+// the fast path's geometries: Geo<tile, look-ahead, step-list entries, teams per CTA, CTAs per SM>
+typedef teamp::Geo<8192, 1024, 512, 5, 2> GeoP;      // production
+typedef teamp::Geo<7168, 1024, 448, 5, 2> GeoQ;
+typedef teamp::Geo<6144, 1024, 384, 6, 2> GeoR;
+typedef teamp::Geo<12288, 1024, 768, 7, 1> GeoS;
+typedef teamp::Geo<8192, 1024, 512, 10, 1> GeoU;     // one CTA of ten teams per SM
+typedef teamp::Geo<1024, 256, 96, 2, 1> GeoT;        // tests: many tile boundaries, records longer than the look-ahead
 
 template <class G>
 static int launch_team(pt_ctx* ctx, ChunkArgs A, const Tables& T) {
     void (*kern)(ChunkArgs, Tables) = teamp::augment_team_kernel<G>;
+    const size_t smem = (size_t)G::SMEM_BYTES * G::NT;
+    const int threads = (int)teamp::THREADS * G::NT;
     if (ctx->teams_per_sm == 0) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES));
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (int)teamp::THREADS, (size_t)G::SMEM_BYTES));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
         if (occ < 1) return fail_msg(ctx, PT_ERR_ARG, "fast path does not fit shared memory");
-        const uint32_t want = env_u32("PANTAS_TEAMS_PER_SM", 0);
+        const uint32_t want = env_u32("PANTAS_CTAS_PER_SM", 0);
         if (want && (int)want < occ) occ = (int)want;
-        ctx->teams_per_sm = occ;
+        ctx->teams_per_sm = occ;                           // CTAs of G::NT teams
     }
     const uint64_t nt = (A.nbytes + G::TILE - 1) / G::TILE;
     if (nt > 0xFFFFFFF0ull) return fail_msg(ctx, PT_ERR_ARG, "chunk too large");
     A.n_tiles = (uint32_t)nt;
     uint64_t g = (uint64_t)ctx->sm_count * ctx->teams_per_sm;
-    if (g > nt) g = nt;
-    if (g > T.team_cap) g = T.team_cap;
-    kern<<<(unsigned)g, teamp::THREADS, (size_t)G::SMEM_BYTES, ctx->stream>>>(A, T);
+    if (g * G::NT > nt) g = (nt + G::NT - 1) / G::NT;
+    if (g * G::NT > T.team_cap) g = T.team_cap / G::NT;
+    kern<<<(unsigned)g, threads, smem, ctx->stream>>>(A, T);
     return 0;
 }
 
@@ -438,6 +443,7 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
     A.file_off = (int64_t)file_offset;
     A.thr = thr;
     A.ablate = ctx->ablate;
+    A.loose = env_u32("PANTAS_LOOSE", 0);
     {   // measured: -4 % kernel time, -25 % DRAM reads (PANTAS_STREAM_HINT=0 switches it off)
         const char* h = getenv("PANTAS_STREAM_HINT");
         A.stream_hint = (h && h[0] == '0') ? 0u : 1u;
@@ -459,6 +465,7 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
         case 7168: rc = launch_team<GeoQ>(ctx, A, T); break;
         case 6144: rc = launch_team<GeoR>(ctx, A, T); break;
         case 12288: rc = launch_team<GeoS>(ctx, A, T); break;
+        case 8193: rc = launch_team<GeoU>(ctx, A, T); break;
         default: rc = launch_team<GeoP>(ctx, A, T); break;
     }
     if (rc) return rc;

@@ -111,13 +111,17 @@ __device__ __forceinline__ uint64_t mix64(uint64_t h) {
     return h;
 }
 
-__device__ __forceinline__ void report_error(const Tables& T, int code, int64_t off) {
-    atomicMin(&T.sc[SC_ERR], ((unsigned long long)off << 8) | (unsigned long long)code);
+// (out-of-line helpers take plain pointers: a reference to the kernel's parameter struct would force a local copy of it
+// and turn every table access into a generic-address one)
+__device__ __noinline__ void report_error_sc(unsigned long long* sc, int code, int64_t off) {
+    atomicMin(&sc[SC_ERR], ((unsigned long long)off << 8) | (unsigned long long)code);
 }
+__device__ __forceinline__ void report_error(const Tables& T, int code, int64_t off) { report_error_sc(T.sc, code, off); }
 
-// insert-or-increment in a 64-bit-key open-addressing table (linear probing, CAS claim)
-__device__ __forceinline__ void side_add(SideSlot* tab, uint64_t mask, unsigned long long* used, uint64_t key,
-                                         uint64_t stamp, const Tables& T, int full_code) {
+// insert-or-increment in a 64-bit-key open-addressing table (linear probing, CAS claim); out of line: rare, and the hot
+// loops stay small
+__device__ __noinline__ void side_add(SideSlot* tab, uint64_t mask, unsigned long long* used, uint64_t key,
+                                      uint64_t stamp, unsigned long long* sc, int full_code) {
     uint64_t h = mix64(key) & mask;
     for (uint64_t probes = 0; probes <= mask; probes++) {
         unsigned long long k = *(volatile unsigned long long*)&tab[h].key;
@@ -125,7 +129,7 @@ __device__ __forceinline__ void side_add(SideSlot* tab, uint64_t mask, unsigned 
             k = atomicCAS(&tab[h].key, KEY_EMPTY, (unsigned long long)key);
             if (k == KEY_EMPTY) {
                 unsigned long long n = atomicAdd(used, 1ull);
-                if (n * 4 >= (mask + 1) * 3) report_error(T, full_code, (int64_t)(stamp >> 2));
+                if (n * 4 >= (mask + 1) * 3) report_error_sc(sc, full_code, (int64_t)(stamp >> 2));
                 k = key;
             }
         }
@@ -136,7 +140,7 @@ __device__ __forceinline__ void side_add(SideSlot* tab, uint64_t mask, unsigned 
         }
         h = (h + 1) & mask;
     }
-    report_error(T, full_code, (int64_t)(stamp >> 2));
+    report_error_sc(sc, full_code, (int64_t)(stamp >> 2));
 }
 
 __device__ __forceinline__ int32_t sext10(uint32_t v) { return (int32_t)(v << 22) >> 22; }
@@ -198,7 +202,7 @@ struct DevSink {
             if (k == KEY_EMPTY) break;
             h = (h + 1) & T.ovf_mask;
         }
-        side_add(T.novel, T.novel_mask, &T.sc[SC_NOVEL_USED], key, stamp, T, pt::PT_X_NOVEL_FULL);
+        side_add(T.novel, T.novel_mask, &T.sc[SC_NOVEL_USED], key, stamp, T.sc, pt::PT_X_NOVEL_FULL);
     }
     // (counting ops - 1) of a node occurrence that has an in-link (il) / an out-link (ol) in its read
     __device__ __forceinline__ void extras(uint32_t idx, int32_t il_ex, int32_t ol_ex) {
@@ -236,7 +240,7 @@ struct DevSink {
         const int64_t bias = 1ll << 30;
         if (pos < -bias || pos >= bias) { report_error(T, pt::PT_U_POSITION, (int64_t)(stamp >> 2)); return; }
         const uint64_t key = ((uint64_t)idx << 32) | ((uint64_t)dir << 31) | (uint64_t)(pos + bias);
-        side_add(T.sparse, T.sparse_mask, &T.sc[SC_SPARSE_USED], key, stamp, T, pt::PT_X_SPARSE_FULL);
+        side_add(T.sparse, T.sparse_mask, &T.sc[SC_SPARSE_USED], key, stamp, T.sc, pt::PT_X_SPARSE_FULL);
     }
     // count_node(a) was called for this occurrence already: move its 1 from t to the link's counter
     __device__ __forceinline__ void edge(uint32_t a, uint32_t b, uint64_t stamp, const EdgePf& pf) {

@@ -42,7 +42,7 @@ constexpr uint32_t FULL = 0xffffffffu;
 constexpr uint32_t THREADS = 64;
 constexpr int MAX_STEPS = 250;                // longer paths take the exact path
 constexpr int MAX_OPS = 48;                   // more cs ops: exact path
-constexpr int32_t MAX_NTOT = 1 << 22;         // longer cs strings: exact path
+constexpr int32_t MAX_NTOT = 60000;           // longer cs strings: exact path (cs coordinates are kept in 16 bits, saturating)
 constexpr uint32_t SL_BAD = 0xFFFFu;          // sL[] entry: unknown node / share that does not fit 16 bits
 
 enum : uint8_t { ST_FAST = 0, ST_DONE = 1, ST_DEFER = 2 };      // per role; a record's status is the maximum
@@ -51,8 +51,9 @@ enum : uint32_t { OP_MATCH = 0, OP_SUB = 1, OP_DEL = 2, OP_INS = 3, OP_EQ = 4 };
 struct __align__(4) Rec {
     int32_t start;        // int(tokens[7])                                    (role B)
     int32_t end_rel1;     // int(tokens[6]) - int(tokens[8]) - 1               (role B)
-    uint32_t n_tot;       // sum of the cs op lengths                          (role A)
-    int32_t start_add;    // cigar_clipping: start_pos += len of a leading '+' (role A, REF:46-47)
+    uint16_t n_tot;       // sum of the cs op lengths (<= MAX_NTOT)            (role A)
+    uint16_t start_add;   // cigar_clipping: start_pos += len of a leading '+' (role A, REF:46-47)
+    uint32_t sum;         // sum of the node lengths of the record's steps     (role B zeroes, ids adds)
     uint16_t s0;          // first entry of the record in the step list        (role B)
     uint16_t nsteps;      //                                                   (role B)
     uint16_t ls;          // buffer position of the record's first byte        (role B)
@@ -60,11 +61,13 @@ struct __align__(4) Rec {
     uint8_t nops;         //                                                   (role A)
     uint8_t stA, stB;     // ST_* per role; walk raises stB
     uint8_t whyA;         // WHY_* when role A says ST_DEFER
-    uint16_t a_off;       // multi-op records: first entry in the prefix pool  (walk)
+    uint16_t a5r;         // path column starts at buffer position a5r & 0x7FFF; bit 15: it starts with '<' (role B)
     uint8_t whyB;
     uint8_t single;       // 1: one ':' or '=' op -- every node with a positive share survives, one counting op  (role A)
+    uint16_t b5;          // end of the path column                            (role B)
+    uint16_t pad;
 };
-static_assert(sizeof(Rec) == 32 && offsetof(Rec, nops) == 24, "rec_status reads nops / stA / stB / whyA as one word");
+static_assert(sizeof(Rec) == 36 && offsetof(Rec, nops) == 24, "rec_status reads nops / stA / stB / whyA as one word");
 
 // step list entry
 constexpr uint32_t SE_POS_MASK = 0xFFFFu;     // bits 0..15  buffer position of the separator (sentinel: end of the path column)
@@ -75,27 +78,30 @@ constexpr int SE_NCNT_SHIFT = 27;             // bits 27..28 counting ops of the
 constexpr uint32_t SE_NCNT_MASK = 3u << SE_NCNT_SHIFT;
 constexpr uint32_t SE_INVALID = 0xFFFFFFFFu;
 
-template <int TILE_, int OV_, int STEP_CAP_, int MIN_CTAS_>
+template <int TILE_, int OV_, int STEP_CAP_, int NT_, int CTAS_>
 struct Geo {
     static constexpr int TILE = TILE_;
     static constexpr int OV = OV_;
     static constexpr int BUF = 16 + TILE + OV + 16;               // [pre 16][tile][look-ahead][pad 16]
-    static constexpr int NG = (16 + TILE + OV + 63) / 64;         // 64-byte groups = 64-bit mask words
+    static constexpr int NV = ((16 + TILE + OV) / 16 + 14 + 3) & ~3;  // 16-byte vectors = 16-bit mask words (+ the walkers' end marks, padded)
     static constexpr int LINE_CAP = 64;                           // records per tile (slots: 6 bits)
     static constexpr int STEP_CAP = STEP_CAP_;                    // typical: 15 entries per 300-byte record
     static constexpr int OPS_CAP = 192;
-    static constexpr int HEAVY_CAP = 256;                         // steps of multi-op records
+    static constexpr int HEAVY_CAP = 160;                         // steps of multi-op records that an op boundary / mismatch / indel falls into
     static constexpr int FAR_CAP = 48;                            // links that are not inline: typically 1 per record
     static constexpr int DEL_CAP = 24;                            // steps with deletion-derived keys
-    static constexpr int MIN_CTAS = MIN_CTAS_;
+    static constexpr int ITEM_CAP = 224;                          // (record, 32-byte word of its path column) pairs: typically 4-5 per record
+    static constexpr int NT = NT_;                                // teams per CTA: they walk through the phases together (one instruction working set)
+    static constexpr int CTAS = CTAS_;                            // CTAs per SM
     // masks are dead after `records`; sL / prefix pool / heavy list live from `ids` to `fold` in the same bytes
-    static constexpr int MASK_BYTES = 16 * NG;
-    static constexpr int WALK_BYTES = 2 * STEP_CAP + 4 * HEAVY_CAP + 2 * HEAVY_CAP;
-    static constexpr int OFF_WM = (BUF + 127) & ~127;
-    static constexpr int OFF_SM = OFF_WM + 8 * NG;
+    static constexpr int MASK_BYTES = 4 * NV;
+    static constexpr int WALK_BYTES = 2 * STEP_CAP + 2 * STEP_CAP + 2 * HEAVY_CAP;
+    static constexpr int OFF_CTL = (BUF + 15) & ~15;              // TeamCtl
+    static constexpr int OFF_WM = (OFF_CTL + 64 + 127) & ~127;
+    static constexpr int OFF_SM = OFF_WM + 2 * NV;
     static constexpr int OFF_SL = OFF_WM;
-    static constexpr int OFF_SA = OFF_SL + 2 * STEP_CAP;
-    static constexpr int OFF_HEAVY = OFF_SA + 4 * HEAVY_CAP;
+    static constexpr int OFF_SR = OFF_SL + 2 * STEP_CAP;
+    static constexpr int OFF_HEAVY = OFF_SR + 2 * STEP_CAP;
     static constexpr int OFF_STEP = (OFF_WM + (MASK_BYTES > WALK_BYTES ? MASK_BYTES : WALK_BYTES) + 15) & ~15;
     static constexpr int OFF_SIDX = OFF_STEP + 4 * (STEP_CAP + 4);
     static constexpr int OFF_SMETA = OFF_SIDX + 4 * STEP_CAP;
@@ -104,22 +110,29 @@ struct Geo {
     static constexpr int OFF_DEL = OFF_FAR + 12 * FAR_CAP;
     static constexpr int OFF_REC = (OFF_DEL + 12 * DEL_CAP + 7) & ~7;
     static constexpr int OFF_LINES = OFF_REC + (int)sizeof(Rec) * LINE_CAP;
-    static constexpr int SMEM_BYTES = (OFF_LINES + 2 * LINE_CAP + 127) & ~127;
+    static constexpr int OFF_ITEMS = (OFF_LINES + 2 * LINE_CAP + 3) & ~3;
+    static constexpr int SMEM_BYTES = (OFF_ITEMS + 4 * ITEM_CAP + 127) & ~127;
     static_assert(BUF <= 65536, "step entries hold 16-bit positions");
+    static_assert(2 * STEP_CAP <= 2 * NV, "`ids` writes sL while it still reads the separator masks: sL must stay inside the whitespace masks");
     static_assert(LINE_CAP <= 64, "step entries hold 6-bit record slots");
     static_assert(STEP_CAP < 65536 && OPS_CAP < 65536 && HEAVY_CAP < 65536, "records hold 16-bit list offsets");
-    static_assert((SMEM_BYTES + 1024 + 64) * MIN_CTAS <= 227 * 1024, "MIN_CTAS teams must fit one SM's shared memory");
+    static_assert((SMEM_BYTES * NT + 1024 + 64) * CTAS <= 227 * 1024, "CTAS x NT teams must fit one SM's shared memory");
 };
 
-// 0x80 flags at bits 7/15/23/31 -> 4-bit mask in the top nibble (no carries: the partial products
-// of 2^21 + 2^14 + 2^7 + 1 land on distinct bits)
-__device__ __forceinline__ uint32_t gather_top(uint32_t f) { return f * 0x00204081u; }
-__device__ __forceinline__ uint32_t mask16(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
-    uint32_t m = gather_top(f3) >> 28;
-    m = __funnelshift_l(gather_top(f2), m, 4);
-    m = __funnelshift_l(gather_top(f1), m, 4);
-    m = __funnelshift_l(gather_top(f0), m, 4);
-    return m;
+// one LOP3 for any three-input bitwise function (LUT = f(0xF0, 0xCC, 0xAA)); written out because the compiler spends two
+// instructions on an expression with two different constants
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+#ifndef PT_EMU
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+#else
+    uint32_t d = 0;
+    for (int k = 0; k < 8; k++)
+        if ((LUT >> k) & 1) d |= ((k & 4) ? a : ~a) & ((k & 2) ? b : ~b) & ((k & 1) ? c : ~c);
+    return d;
+#endif
 }
 
 // no "s:" / "v:" byte pair inside: neither regex of REF:154-156,172-174 can start in this token
@@ -211,17 +224,16 @@ __device__ __forceinline__ bool small_uint(const uint8_t* s, uint32_t a, uint32_
     return true;
 }
 
-// The walkers read the 64-bit mask words as 32-bit halves (one FLO / POPC per step instead of two).
-// next whitespace bit at or after the walker's position (32 bytes of the tile per half word);
-// false: ran off the end of the loaded bytes
-__device__ __forceinline__ bool next_ws(const uint32_t* wm32, uint32_t nhalf, uint32_t& wi, uint32_t& m, uint32_t& pos) {
-    while (m == 0u) {
-        if (++wi >= nhalf) return false;
-        m = wm32[wi];
-    }
+// The walkers read the mask arrays as 32-bit words (32 bytes of the tile each).
+// Next whitespace bit at or after the walker's position.  No bounds checks: the scan leaves four zero words and then two
+// all-ones words behind the data, so a walker that runs off the record's end finds positions >= lim (checked once by the
+// caller).  Up to two empty words (a read name, a long tag) are skipped without a loop: the lanes of a role warp stay together.
+__device__ __forceinline__ void next_ws(const uint32_t* wm32, uint32_t& wi, uint32_t& m, uint32_t& pos) {
+    if (m == 0u) m = wm32[++wi];
+    if (m == 0u) m = wm32[++wi];
+    while (m == 0u) m = wm32[++wi];
     pos = 32u * wi + (uint32_t)(__ffs((int)m) - 1);
     m &= m - 1u;
-    return true;
 }
 
 // separator bits of half word w that lie in buffer positions [a, b)
@@ -252,22 +264,36 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane, ui
     return incl - v;
 }
 
-template <class G>
-__global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(ChunkArgs A, Tables T) {
-    PT_DYNAMIC_SMEM(smem);
-    __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t s_cnt[2];                // record starts found by each warp
-    __shared__ uint32_t s_nent, s_nheavy, s_nfar, s_ndel, s_far_take, s_lwm;
+// per-team control block (shared memory)
+struct __align__(8) TeamCtl {
+    uint64_t mbar;               // the tile's TMA copy has landed
+    uint32_t cnt[2];             // record starts found by each warp
+    uint32_t nent, nitems, nheavy, nfar, ndel, far_take, lwm;
+};
+static_assert(sizeof(TeamCtl) <= 64, "OFF_WM leaves 64 bytes for the control block");
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+template <class G>
+__global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(ChunkArgs A, Tables T) {
+    PT_DYNAMIC_SMEM(smem_cta);
+    // The CTA is G::NT independent teams that only share the barriers: all teams of an SM are then in (nearly) the same
+    // phase, so the SM's instruction caches hold one or two phases instead of all of them.
+    const uint32_t team = threadIdx.x / THREADS, tid = threadIdx.x % THREADS, lane = tid & 31u, warp = tid >> 5;
+    uint8_t* const smem = smem_cta + team * (uint32_t)G::SMEM_BYTES;
+    TeamCtl& C = *reinterpret_cast<TeamCtl*>(smem + G::OFF_CTL);
+    uint64_t& mbar = C.mbar;
+    uint32_t* const s_cnt = C.cnt;
+    uint32_t &s_nent = C.nent, &s_nitems = C.nitems, &s_nheavy = C.nheavy, &s_nfar = C.nfar, &s_ndel = C.ndel, &s_far_take = C.far_take, &s_lwm = C.lwm;
+    const uint32_t gteam = blockIdx.x * (uint32_t)G::NT + team, nteams = gridDim.x * (uint32_t)G::NT;
+    // inside a tile the phases only need the team's own two warps; the CTA-wide barrier after `scan` re-aligns the teams
+    auto team_sync = [&]() { if (A.loose) named_barrier(team + 1u, THREADS); else __syncthreads(); };
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint8_t* const buf = smem;
-    unsigned long long* const wm64 = reinterpret_cast<unsigned long long*>(smem + G::OFF_WM);
-    unsigned long long* const sm64 = reinterpret_cast<unsigned long long*>(smem + G::OFF_SM);
+    uint16_t* const wm16 = reinterpret_cast<uint16_t*>(smem + G::OFF_WM);      // whitespace mask, 16 bits per 16-byte vector
+    uint16_t* const sm16 = reinterpret_cast<uint16_t*>(smem + G::OFF_SM);      // separators + non-tab whitespace
     const uint32_t* const wm32 = reinterpret_cast<const uint32_t*>(smem + G::OFF_WM);   // the same masks, as half words
     const uint32_t* const sm32 = reinterpret_cast<const uint32_t*>(smem + G::OFF_SM);
     uint16_t* const sL = reinterpret_cast<uint16_t*>(smem + G::OFF_SL);        // share of the query per step (REF:215-218), SL_BAD
-    uint32_t* const sA = reinterpret_cast<uint32_t*>(smem + G::OFF_SA);        // multi-op records: cs coordinate where the step's node starts
+    uint16_t* const sR = reinterpret_cast<uint16_t*>(smem + G::OFF_SR);        // cs coordinate where the step's node starts (saturating)
     uint16_t* const heavy = reinterpret_cast<uint16_t*>(smem + G::OFF_HEAVY);  // steps of multi-op records
     uint32_t* const steps = reinterpret_cast<uint32_t*>(smem + G::OFF_STEP);
     uint32_t* const sidx = reinterpret_cast<uint32_t*>(smem + G::OFF_SIDX);
@@ -276,6 +302,7 @@ __global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(Chun
     uint32_t* const far = reinterpret_cast<uint32_t*>(smem + G::OFF_FAR);      // {from, to, separator position}: filled by `count`, drained during the next tile's `walk`
     uint32_t* const dels = reinterpret_cast<uint32_t*>(smem + G::OFF_DEL);     // {step, first del, last del}
     Rec* const recs = reinterpret_cast<Rec*>(smem + G::OFF_REC);
+    uint32_t* const items = reinterpret_cast<uint32_t*>(smem + G::OFF_ITEMS);  // record slot | word << 6 | steps of the record before this word << 15
     uint16_t* const lines = reinterpret_cast<uint16_t*>(smem + G::OFF_LINES);  // record starts: warp 0 fills the list from the front, warp 1 from the back
 
     if (tid == 0) {
@@ -292,7 +319,8 @@ __global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(Chun
     const uint32_t ablate = A.ablate;            // diagnostics: 0 = everything, k = stop every tile after phase k (profiles/ ablation ladder)
     const uint64_t nbytes16 = (A.nbytes + 15ull) & ~15ull;
     uint32_t parity = 0;
-    unsigned long long my_lines = 0, my_tiles = 0;
+    unsigned long long my_tiles = 0;
+    uint32_t my_real = 0;                        // records this thread has listed
     int64_t far_base = 0;                        // file offset of buf[0] of the tile that filled the far-link list
 
     auto issue_load = [&](uint32_t tile) {
@@ -315,26 +343,33 @@ __global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(Chun
         }
     };
 
-    uint32_t tile = blockIdx.x;
-    if (tile < A.n_tiles && tid == 0) issue_load(tile);
+    if (gteam < A.n_tiles && tid == 0) issue_load(gteam);
 
-    for (; tile < A.n_tiles; tile += gridDim.x) {
+    // every team of the CTA makes the same number of rounds (the barriers are CTA-wide); a team without a tile idles through
+    const uint32_t rounds = (A.n_tiles + nteams - 1u) / nteams;
+    for (uint32_t round = 0; round < rounds; round++) {
+        const uint32_t tile = gteam + round * nteams;
+        const bool active = tile < A.n_tiles;
         const uint64_t t0 = (uint64_t)tile * G::TILE;
-        const uint32_t owned = (uint32_t)min((uint64_t)G::TILE, A.nbytes - t0);
+        const uint32_t owned = active ? (uint32_t)min((uint64_t)G::TILE, A.nbytes - t0) : 0u;
         const uint64_t hi = min(t0 + G::TILE + G::OV, nbytes16);
-        const uint32_t lim = 16u + (uint32_t)(min(hi, A.nbytes) - t0);     // data ends here in the buffer
+        const uint32_t lim = active ? 16u + (uint32_t)(min(hi, A.nbytes) - t0) : 0u;     // data ends here in the buffer
         const int64_t base_off = A.file_off + (int64_t)t0 - 16;            // file offset of buf[0]
-        const uint32_t own_end = 16u + owned;                               // records starting before this are ours
-        const uint32_t nwords = (lim + 63u) >> 6;
-        const uint32_t nxt_tile = tile + gridDim.x;
-        if (tid == 0) {
+        const uint32_t own_end = active ? 16u + owned : 0u;                 // records starting before this are ours
+        const uint32_t nvec = (lim + 15u) >> 4;                             // vectors holding data
+        const uint32_t nvec2 = (nvec + 1u) & ~1u;                           // whole 32-bit mask words
+        const uint32_t nhalf = nvec2 >> 1;
+        const uint32_t nxt_tile = tile + nteams;
+        if (tid == 0 && active) {
             // low-water mark of the running kernel (tables.cuh): every tile below it is complete
             const unsigned long long lw = *(volatile unsigned long long*)&T.sc[SC_LWM];
             const int64_t rel = A.file_off - T.epoch_base + (int64_t)(lw * (unsigned long long)G::TILE);
             s_lwm = rel <= 0 ? 0u : (rel > 0xFFFFFFF0ll ? 0xFFFFFFF0u : (uint32_t)rel);
         }
-        mbar_wait(&mbar, parity);
-        parity ^= 1;
+        if (active) {
+            mbar_wait(&mbar, parity);
+            parity ^= 1;
+        }
         if (ablate == 1u) {                                                 // TMA only
             __syncthreads();
             if (tid == 0 && nxt_tile < A.n_tiles) issue_load(nxt_tile);
@@ -342,92 +377,111 @@ __global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(Chun
         }
 
         // ================= scan: whitespace / separator masks, record starts =================
-        uint32_t my_cnt = 0;                                                // warp-uniform: record starts this warp has listed
-        if (tile == 0 && warp == 0 && owned > 0u) {                         // the chunk starts at a record start
-            if (lane == 0) lines[0] = 16;
-            my_cnt = 1;
-        }
-        for (uint32_t g0 = 0; g0 < nwords; g0 += THREADS) {
-            const uint32_t g = g0 + tid;
-            unsigned long long cand = 0;
-            if (g < nwords) {
-                unsigned long long wm = 0, sm = 0;
-                uint32_t hib = 0;
-                // the four vectors of the group in a lane-dependent order: a quarter warp's eight LDS.128 then fall into
-                // eight different 16-byte bank groups (lane stride 64 bytes alone would put them into two)
-                const uint32_t rot = (lane >> 1) & 3u;
-                uint4 q[4];
+        // A warp iteration covers 2 KiB: lane L takes the 16-byte vectors L, L + 64, L + 128, L + 192 of the team's 4 KiB
+        // (consecutive lanes, consecutive vectors: no bank conflicts) and stores one 16-bit mask pair per vector; the
+        // walkers read the mask arrays as 32-bit words (32 bytes of the tile each).
+        {
+            auto scan_vec = [&](uint32_t v, uint32_t& hib, auto tail) {
+                const uint4 q = *reinterpret_cast<const uint4*>(buf + 16u * v);
+                const uint32_t x4[4] = {q.x, q.y, q.z, q.w};
+                uint32_t bw[4], sv[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) q[u] = *reinterpret_cast<const uint4*>(buf + 64u * g + 16u * ((u + rot) & 3u));
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t x = x4[k];
+                    // exact for ASCII bytes; a byte >= 0x80 is a fatal PT_U_NON_ASCII error anyway
+                    bw[k] = x + 0x5F5F5F5Fu;                                      // bit 7 clear: x <= 0x20
+                    const uint32_t ts = lop3<0x56>(x, 0x02020202u, 0x3E3E3E3Eu) + 0x7F7F7F7Fu;   // (x | 2) ^ '>': bit 7 clear: '>' or '<'
+                    const uint32_t t = x + 0x76767676u;                           // bit 7 set: x >= 0x0A
+                    sv[k] = lop3<0x2F>(ts, bw[k], t);                             // bit 7: separator, or whitespace that is not a tab
+                }
+                // two words per multiply: flags of word 2k+1 at bit 7, of word 2k at bit 3 of every byte -> the top byte of
+                // the product holds the eight flags in byte order (partial products land on distinct bits: no carries)
+                const uint32_t w01 = ~lop3<0xCA>(0x80808080u, bw[1], bw[0] >> 4) & 0x88888888u;
+                const uint32_t w23 = ~lop3<0xCA>(0x80808080u, bw[3], bw[2] >> 4) & 0x88888888u;
+                const uint32_t s01 = lop3<0xCA>(0x80808080u, sv[1], sv[0] >> 4) & 0x88888888u;
+                const uint32_t s23 = lop3<0xCA>(0x80808080u, sv[3], sv[2] >> 4) & 0x88888888u;
+                uint32_t wm = __byte_perm(w01 * 0x00204081u, w23 * 0x00204081u, 0x4473);   // byte 3 of each product -> 16-bit mask
+                uint32_t sm = __byte_perm(s01 * 0x00204081u, s23 * 0x00204081u, 0x4473);
+                if (decltype(tail)::value) {                                // the last vectors: nothing past the data
+                    const uint32_t room = lim > 16u * v ? lim - 16u * v : 0u;
+                    const uint32_t keep = room < 16u ? ~(~0u << room) : 0xFFFFu;
+                    wm &= keep;
+                    sm &= keep;
+                }
+                wm16[v] = (uint16_t)wm;
+                sm16[v] = (uint16_t)sm;
+                hib |= (q.x | q.y) | (q.z | q.w);
+            };
+            const uint32_t nfull = nvec > 2u ? (nvec - 2u) / (4u * THREADS) : 0u;     // rounds in which every vector is whole
+            uint32_t hib = 0;
+            for (uint32_t r = 0; r < nfull; r++) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) scan_vec(4u * THREADS * r + THREADS * u + tid, hib, std::false_type());
+            }
+            for (uint32_t v0 = 4u * THREADS * nfull; v0 < nvec2; v0 += 4u * THREADS) {
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const uint32_t sh = 16u * ((u + rot) & 3u);
-                    uint32_t wf[4], sf[4];
-                    const uint32_t x4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const uint32_t x = x4[k];
-                        // exact for ASCII bytes; a byte >= 0x80 is a fatal PT_U_NON_ASCII error anyway
-                        const uint32_t b = (x | 0x80808080u) - 0x21212121u;          // bit 7 clear: x <= 0x20
-                        const uint32_t ts = ((x | 0x02020202u) ^ 0x3E3E3E3Eu) + 0x7F7F7F7Fu;   // bit 7 clear: '>' or '<'
-                        const uint32_t t = x + 0x76767676u;                          // bit 7 set: x >= 0x0A
-                        wf[k] = ~b & 0x80808080u;
-                        sf[k] = (~ts & 0x80808080u) | (wf[k] & t);                   // separators, and whitespace that is not a tab
-                        hib |= x;
-                    }
-                    wm |= (unsigned long long)mask16(wf[0], wf[1], wf[2], wf[3]) << sh;
-                    sm |= (unsigned long long)mask16(sf[0], sf[1], sf[2], sf[3]) << sh;
-                }
-                const uint32_t room = lim > 64u * g ? lim - 64u * g : 0u;   // loaded bytes in this group
-                unsigned long long keep = room < 64u ? ~(~0ull << room) : ~0ull;
-                cand = wm & sm & keep;                                      // '\n' (record end), '\r', other odd whitespace
-                if (g == 0) {
-                    keep &= ~0xFFFFull;                                     // positions 0..15 are before the tile ...
-                    cand &= tile != 0 ? ~0x7FFFull : ~0xFFFFull;            // ... but is the byte before the tile a newline?
-                }
-                wm64[g] = wm & keep;
-                sm64[g] = sm & keep;
-                if ((hib & 0x80808080u) != 0u) {                            // non-ASCII byte: not modelled
-                    for (uint32_t p = max(64u * g, 16u); p < min(64u * g + 64u, min(lim, own_end)); p++)
-                        if (buf[p] >= 0x80u) { report_error(T, pt::PT_U_NON_ASCII, base_off + (int64_t)p); break; }
+                    const uint32_t v = v0 + THREADS * u + tid;
+                    if (v < nvec2) scan_vec(v, hib, std::true_type());
                 }
             }
-            // record starts: one candidate per lane and round (a second round only when a 64-byte group holds two)
-            while (__any_sync(FULL, cand != 0ull)) {
-                bool is_start = false;
-                uint32_t p = 0;
-                if (cand != 0ull) {
-                    p = 64u * g + (uint32_t)(__ffsll((long long)cand) - 1);
-                    cand &= cand - 1ull;
-                    const uint32_t c = buf[p];
-                    if (c == '\n') {
-                        is_start = p + 1u < own_end;
-                    } else if (c == '\r' && p >= 16u && p < own_end) {      // lone '\r': a line break for the reference's text mode
+            if ((hib & 0x80808080u) != 0u) {                                // non-ASCII byte: not modelled.  (Rare: look again.)
+                for (uint32_t v = tid; v < nvec; v += THREADS)
+                    for (uint32_t p = max(16u * v, 16u); p < min(16u * v + 16u, min(lim, own_end)); p++)
+                        if (buf[p] >= 0x80u) { report_error(T, pt::PT_U_NON_ASCII, base_off + (int64_t)p); break; }
+            }
+        }
+        __syncwarp();
+        // ---- record starts.  A warp reads back the mask words it wrote itself (16 words of every 32): whitespace that is
+        // not a tab (sep & ws) is a '\n' (record end), a '\r' or something odd; ranked by one warp scan, no atomics.
+        uint32_t my_cnt = 0;                                                // warp-uniform: list slots this warp has handed out
+        {
+            const uint32_t p_min = tile ? 15u : 16u;                        // is the byte before the tile a newline? (tile 0: nothing there)
+            const uint32_t w_end = (own_end + 31u) >> 5;                    // record starts are ours up to own_end
+            const uint32_t w_first = 32u * (lane >> 4) + 16u * warp + (lane & 15u);
+            uint32_t cnt = 0;
+            for (uint32_t w = w_first; w < w_end; w += 64u) cnt += (uint32_t)__popc(wm32[w] & sm32[w]);
+            uint32_t total;
+            uint32_t j = warp_excl_scan(cnt, lane, total);
+            if (active && tile == 0 && warp == 0 && owned > 0u) {           // the chunk starts at a record start
+                if (lane == 0) lines[0] = 16;
+                j += 1u;
+                total += 1u;
+                my_real += lane == 0 ? 1u : 0u;
+            }
+            my_cnt = total;
+            for (uint32_t w = w_first; w < w_end && cnt != 0u; w += 64u) {
+                uint32_t c = wm32[w] & sm32[w];
+                while (c) {
+                    const uint32_t p = 32u * w + (uint32_t)(__ffs((int)c) - 1);
+                    c &= c - 1u;
+                    cnt--;
+                    const uint32_t ch = buf[p];
+                    const bool is_start = ch == '\n' && p + 1u < own_end && p >= p_min;
+                    if (ch == '\r' && p >= 16u && p < own_end) {            // lone '\r': a line break for the reference's text mode
                         const uint64_t abs_pos = t0 + p - 16u;
                         if (abs_pos + 1 < A.nbytes && buf[p + 1] != '\n') report_error(T, pt::PT_U_BARE_CR, base_off + (int64_t)p);
                     }
+                    // (a candidate that is no record start keeps its slot: 0 = no record)
+                    if (j < (uint32_t)G::LINE_CAP) lines[warp ? (uint32_t)G::LINE_CAP - 1u - j : j] = is_start ? (uint16_t)(p + 1u) : (uint16_t)0;
+                    j++;
+                    my_real += is_start ? 1u : 0u;
                 }
-                const uint32_t bal = __ballot_sync(FULL, is_start);
-                if (is_start) {
-                    const uint32_t j = my_cnt + (uint32_t)__popc(bal & lt_mask);
-                    if (j < (uint32_t)G::LINE_CAP) lines[warp ? (uint32_t)G::LINE_CAP - 1u - j : j] = (uint16_t)(p + 1u);
-                }
-                my_cnt += (uint32_t)__popc(bal);
             }
         }
+        if (tid < 12u) wm16[nvec2 + tid] = tid < 8u ? 0u : 0xFFFFu;         // end marks for the walkers (next_ws)
         if (lane == 0) s_cnt[warp] = my_cnt;
         __syncthreads();                                                    // ---- B1: masks + record lists complete; everyone is through the previous tile
         const uint32_t n0 = s_cnt[0], n1 = s_cnt[1];
         const uint32_t lwm_rel = s_lwm;
-        if (tid == 0) {
-            my_lines += n0 + n1;
+        if (tid == 0 && active) {
             my_tiles++;
-            *(volatile uint32_t*)&T.team_tile[blockIdx.x] = tile;           // my tiles before this one are complete
+            *(volatile uint32_t*)&T.team_tile[gteam] = tile;                // my tiles before this one are complete
         }
-        if (blockIdx.x == 0 && warp == 1) {
+        if (gteam == 0 && warp == 1) {
             // one team keeps the kernel's low-water mark: the smallest tile any team is still working on
             uint32_t m = 0xFFFFFFFFu;
-            for (uint32_t i = lane; i < gridDim.x; i += 32u) m = min(m, *(volatile uint32_t*)&T.team_tile[i]);
+            for (uint32_t i = lane; i < nteams; i += 32u) m = min(m, *(volatile uint32_t*)&T.team_tile[i]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(FULL, m, o));
             if (lane == 0 && m != 0xFFFFFFFFu) atomicMax(&T.sc[SC_LWM], (unsigned long long)m);
@@ -438,60 +492,48 @@ __global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(Chun
             continue;
         }
 
-        if (n0 + n1 > (uint32_t)G::LINE_CAP) {
-            // more records than the lists hold (pathological input): all of them take the exact path
+        uint32_t n_lines = n0 + n1;
+        if (n_lines > (uint32_t)G::LINE_CAP) {
+            // more records than the list holds (pathological input): all of them take the exact path
             for (uint32_t p = 15u + tid; p + 1u < own_end; p += THREADS) {
                 const bool nl = p == 15u ? (tile == 0 || buf[p] == '\n') : buf[p] == '\n';
                 if (nl) defer_line(T, t0 + p + 1u - 16u, A.file_off, WHY_LINES_FULL);
             }
-            if (warp == 1) drain_far();                                    // the previous tile's far links (normally done in `walk`)
-            __syncthreads();
-            if (tid == 0) {
-                s_nfar = 0;
-                s_far_take = 0;
-                if (nxt_tile < A.n_tiles) issue_load(nxt_tile);
-            }
-            __syncthreads();
-            continue;
+            n_lines = 0;
         }
-        const uint32_t n_lines = n0 + n1;
 
         // ================= records: warp 0 = role B, warp 1 = role A, one thread per record =================
         if (warp == 0) {
-            uint32_t step_base = 0;                                         // warp-uniform: entries handed out so far
+            uint32_t step_base = 0, item_base = 0;                          // warp-uniform: step entries / items handed out so far
             for (uint32_t l0 = 0; l0 < n_lines; l0 += 32u) {
                 const uint32_t l = l0 + lane;
                 const bool have = l < n_lines;
-                uint32_t st = ST_DONE, ns = 0, a5 = 0, b5 = 0, ls = 0;
+                uint32_t st = ST_DONE, ns = 0, nw = 0, a5 = 0, b5 = 0, ls = 0;
                 int why = WHY_LONG;
                 int32_t plen = 0, start = 0, pend = 0;
                 if (have) {
                     // ---------------- role B: columns, filters, coordinates
                     ls = lines[l < n0 ? l : (uint32_t)G::LINE_CAP - 1u - (l - n0)];
+                }
+                if (have && ls != 0u) {
                     uint32_t wi = ls >> 5;
                     uint32_t wmk = wm32[wi] & (~0u << (ls & 31u));
                     uint32_t e[13];
                     e[0] = ls - 1u;
-                    bool ran_off = false, gaps_ok = true;
-                    uint32_t tabs = 0xFFFFFFFFu;              // AND of (byte == '\t') over the first 11 boundaries
+                    uint32_t gaps_ok = 1u, tabs = 1u;         // AND over the boundaries: no empty column / a tab (the first 11)
 #pragma unroll
                     for (int j = 1; j <= 12; j++) {
-                        e[j] = 0;
-                        if (!ran_off) {
-                            if (!next_ws(wm32, 2u * nwords, wi, wmk, e[j])) ran_off = true;   // record runs past the look-ahead
-                            else {
-                                gaps_ok &= e[j] - e[j - 1] >= 2u;                        // no empty column
-                                if (j < 12) tabs &= buf[e[j]] == '\t' ? 0xFFFFFFFFu : 0u;
-                            }
-                        }
+                        next_ws(wm32, wi, wmk, e[j]);
+                        gaps_ok &= e[j] - e[j - 1] >= 2u ? 1u : 0u;
+                        if (j < 12) tabs &= buf[e[j]] == '\t' ? 1u : 0u;
                     }
-                    bool slow = ran_off, done = false, no_tags = false;
+                    bool slow = e[12] >= lim, done = false, no_tags = false;      // record runs past the look-ahead
                     int32_t mapq = 0;
                     if (!slow) {
                         // 11 single tabs, then a tab (tags follow) or the end of a 12-column record
                         const uint32_t c12 = buf[e[12]];
                         no_tags = c12 == '\n';
-                        if (!gaps_ok || tabs == 0u || (c12 != '\t' && !no_tags)) { slow = true; why = WHY_COLUMNS; }
+                        if ((gaps_ok & tabs) == 0u || (c12 != '\t' && !no_tags)) { slow = true; why = WHY_COLUMNS; }
                     }
                     if (!slow) {
                         why = WHY_INTS;
@@ -505,56 +547,66 @@ __global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(Chun
                         slow = !small_uint(buf, e[6] + 1u, e[7], plen) || !small_uint(buf, e[7] + 1u, e[8], start) ||
                                !small_uint(buf, e[8] + 1u, e[9], pend);
                     if (!slow && !done && no_tags) { slow = true; why = WHY_TAGS; }   // no dv tag: ValueError (REF:179), the exact path reports
-                    // ---- path column (REF:185-197): it must start with a separator; count the steps
+                    // ---- path column (REF:185-197): it must start with a separator
                     if (!slow && !done) {
                         why = WHY_PATH;
                         a5 = e[5] + 1u;
                         b5 = e[6];
-                        for (uint32_t w = a5 >> 5; w <= ((b5 - 1u) >> 5); w++) ns += (uint32_t)__popc(sep_word(sm32, w, a5, b5));
-                        if (ns == 0u || ns > (uint32_t)MAX_STEPS || !((sm32[a5 >> 5] >> (a5 & 31u)) & 1u)) slow = true;
+                        nw = ((b5 - 1u) >> 5) - (a5 >> 5) + 1u;
+                        if (!((sm32[a5 >> 5] >> (a5 & 31u)) & 1u)) slow = true;
                     }
                     st = slow ? ST_DEFER : (done ? ST_DONE : ST_FAST);
+                    if (st != ST_FAST) nw = 0;
+                }
+                // ---- one item per 32-byte word of the path column: `ids` turns its separator bits into steps
+                uint32_t total;
+                const uint32_t it0 = item_base + warp_excl_scan(nw, lane, total);
+                item_base += total;
+                if (st == ST_FAST) {
+                    if (it0 + nw > (uint32_t)G::ITEM_CAP) {                 // list full: exact path
+                        st = ST_DEFER;
+                        why = WHY_STEPS_FULL;
+                        for (uint32_t i = it0; i < (uint32_t)G::ITEM_CAP; i++) items[i] = 0xFFFFFFFFu;
+                    } else {
+                        const uint32_t w0 = a5 >> 5;
+                        for (uint32_t k = 0; k < nw; k++) {
+                            items[it0 + k] = l | ((w0 + k) << 6) | (ns << 15);
+                            ns += (uint32_t)__popc(sep_word(sm32, w0 + k, a5, b5));
+                        }
+                        if (ns > (uint32_t)MAX_STEPS) { st = ST_DEFER; ns = 0; }     // (ns >= 1: the column starts with a separator)
+                    }
                     if (st != ST_FAST) ns = 0;
                 }
-                // ---- list space for the steps of the warp's records (+ one sentinel each)
-                uint32_t total;
-                uint32_t off = step_base + warp_excl_scan(st == ST_FAST ? ns + 1u : 0u, lane, total);
+                // ---- list space for the steps of the warp's records
+                const uint32_t off = step_base + warp_excl_scan(ns, lane, total);
                 step_base += total;
                 if (have) {
                     Rec& R = recs[l];
-                    if (st == ST_FAST && off + ns + 1u > (uint32_t)G::STEP_CAP) {      // list full: exact path
+                    if (st == ST_FAST && off + ns > (uint32_t)G::STEP_CAP) {          // list full: exact path
                         st = ST_DEFER;
                         why = WHY_STEPS_FULL;
-                        for (uint32_t i = off; i < (uint32_t)G::STEP_CAP; i++) steps[i] = SE_INVALID;
+                        for (uint32_t i = off; i < (uint32_t)G::STEP_CAP; i++) steps[i] = SE_INVALID;   // (`ids` will not write these)
                     }
                     R.ls = (uint16_t)ls;
                     R.stB = (uint8_t)st;
                     R.whyB = (uint8_t)why;
                     R.nsteps = 0;
                     R.s0 = 0;
+                    R.sum = 0;
                     if (st == ST_FAST) {
                         R.start = start;
                         R.end_rel1 = plen - pend - 1;
                         R.s0 = (uint16_t)off;
                         R.nsteps = (uint16_t)ns;
-                        // ---- one entry per path step, then the sentinel (end of the column)
-                        const uint32_t common = (l << SE_SLOT_SHIFT) | (buf[a5] == '<' ? SE_REV : 0u) | (1u << SE_NCNT_SHIFT);
-                        uint32_t i = off;
-                        for (uint32_t w = a5 >> 5; w <= ((b5 - 1u) >> 5); w++) {
-                            uint32_t m = sep_word(sm32, w, a5, b5);
-                            const uint32_t wb = (32u * w) | common;
-                            while (m) {
-                                steps[i++] = wb + (uint32_t)(__ffs((int)m) - 1);
-                                m &= m - 1u;
-                            }
-                        }
-                        steps[off] |= SE_FIRST;
-                        steps[off + ns - 1u] |= SE_LAST;
-                        steps[off + ns] = b5 | (l << SE_SLOT_SHIFT) | SE_SENT;
+                        R.a5r = (uint16_t)(a5 | (buf[a5] == '<' ? 0x8000u : 0u));
+                        R.b5 = (uint16_t)b5;
                     }
                 }
             }
-            if (lane == 0) s_nent = step_base;
+            if (lane == 0) {
+                s_nent = min(step_base, (uint32_t)G::STEP_CAP);
+                s_nitems = min(item_base, (uint32_t)G::ITEM_CAP);
+            }
         } else {
             uint32_t ops_base = 0;                                          // warp-uniform: op-pool words handed out so far
             for (uint32_t l0 = 0; l0 < n_lines; l0 += 32u) {
@@ -565,8 +617,8 @@ __global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(Chun
                 int why = WHY_LONG;
                 bool idle = true, slow = false, done = false, perfect = false;
                 uint32_t cs_a = 0, cs_b = 0, room = 0, q = 0, n_tot = 0;
-                if (have) {
-                    const uint32_t ls = lines[l < n0 ? l : (uint32_t)G::LINE_CAP - 1u - (l - n0)];
+                const uint32_t ls = have ? lines[l < n0 ? l : (uint32_t)G::LINE_CAP - 1u - (l - n0)] : 0u;
+                if (ls != 0u) {                                             // (0: a candidate that was no record start)
                     uint32_t wi = ls >> 5;
                     uint32_t wmk = wm32[wi] & (~0u << (ls & 31u));
                     uint32_t e11 = 0, e12 = 0;
@@ -577,12 +629,15 @@ __global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(Chun
                         const uint32_t c = (uint32_t)__popc(wmk);
                         if (c > skip) break;
                         skip -= c;
-                        if (++wi >= 2u * nwords) { ran_off = true; break; }
+                        if (++wi >= nhalf) { ran_off = true; break; }
                         wmk = wm32[wi];
                     }
                     for (; skip != 0u && !ran_off; skip--) wmk &= wmk - 1u;
-                    if (!ran_off && !next_ws(wm32, 2u * nwords, wi, wmk, e11)) ran_off = true;
-                    if (!ran_off && !next_ws(wm32, 2u * nwords, wi, wmk, e12)) ran_off = true;
+                    if (!ran_off) {
+                        next_ws(wm32, wi, wmk, e11);
+                        next_ws(wm32, wi, wmk, e12);
+                        ran_off = e12 >= lim;
+                    }
                     // role B decides about everything up to column 12; here: is there anything left to do?
                     int32_t mapq = 0;
                     idle = ran_off || buf[e12] != '\t' || !small_uint(buf, e11 + 1u, e12, mapq) || (int64_t)mapq < A.thr;
@@ -592,7 +647,8 @@ __global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(Chun
                         // ---- tags: [inert]* cs [inert]* dv in any order, within the first few tags
                         why = WHY_TAGS;
                         uint32_t a = e12 + 1u, b = 0;
-                        if (!next_ws(wm32, 2u * nwords, wi, wmk, b)) slow = true;
+                        next_ws(wm32, wi, wmk, b);
+                        if (b >= lim) slow = true;
                         for (int j = 13; !slow; j++) {
                             const unsigned long long t8 = ld8(buf, a);          // the token's first eight bytes
                             if (!cs_b && b - a >= 3u && (t8 & 0xFFFFFFull) == TAG_CS3) {
@@ -615,7 +671,8 @@ __global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(Chun
                             if (cs_b && dv_b) break;
                             if (buf[b] == '\n' || j >= 18) { slow = true; break; }      // end of the record: a tag is missing
                             a = b + 1u;
-                            if (!next_ws(wm32, 2u * nwords, wi, wmk, b)) { slow = true; break; }
+                            next_ws(wm32, wi, wmk, b);
+                            if (b >= lim) { slow = true; break; }
                         }
                         // ---- dv filter (REF:172-180).  The reference parses cs first, but that has no side effects and
                         //      cannot raise, so a record that dv filters out needs no cs class
@@ -716,9 +773,9 @@ __global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(Chun
                         }
                         if (!slow) {
                             const uint32_t k0 = ops[op_off] & 7u;
-                            R.n_tot = n_tot;
+                            R.n_tot = (uint16_t)n_tot;
                             R.op_off = (uint16_t)op_off;
-                            R.start_add = start_add;
+                            R.start_add = (uint16_t)start_add;
                             R.single = (uint8_t)((nops == 1u && (k0 == OP_MATCH || k0 == OP_EQ)) ? 1 : 0);
                         }
                     }
@@ -735,125 +792,190 @@ __global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(Chun
                 }
             }
         }
-        __syncthreads();                                                    // ---- B2: records, ops, step list complete
-        const uint32_t n_ent = min(s_nent, (uint32_t)G::STEP_CAP);         // step entries incl. sentinels
+        team_sync();                                                          // ---- B2: records, ops, step list complete
+        const uint32_t n_ent = s_nent;                                      // step entries
         if (ablate == 3u) {
             __syncthreads();
             if (tid == 0 && nxt_tile < A.n_tiles) issue_load(nxt_tile);
             continue;
         }
 
-        // ================= ids: one thread per path step: id -> node index -> the node's hot record =================
-        // UI steps per thread and iteration: their 16-byte loads are all in flight before the first is used.
+        // ================= ids: one thread per item (a 32-byte word of a path column) =================
+        // Every separator bit of the word is a path step: SWAR decimal parse of the id that follows it -> node index -> ONE
+        // 16-byte load of the node's hot record, up to UI of them in flight per thread.  Writes the step list (entry, node
+        // index, meta word, node length) and collects what `walk` needs per record: the sum of the node lengths, and
+        // whether two consecutive ids are equal (REF:188 collapses those: the exact path redoes such a record).
         {
             constexpr int UI = 4;
-            for (uint32_t s00 = 0; s00 < n_ent; s00 += THREADS * UI) {
-                uint32_t idx_[UI], se_[UI];
-                uint4 hot_[UI];
+            const uint32_t n_items = s_nitems;
+            for (uint32_t it = tid; it < n_items; it += THREADS) {
+                const uint32_t item = items[it];
+                if (item == 0xFFFFFFFFu) continue;                          // (list overflow: that record went to the exact path)
+                const uint32_t l = item & 63u, w = (item >> 6) & 511u;
+                Rec& R = recs[l];
+                if (R.nsteps == 0u) continue;                               // (role B handed the record over after listing the item)
+                const uint32_t a5 = R.a5r & 0x7FFFu, rev = R.a5r >> 15, b5 = R.b5, s0 = R.s0, s_last = s0 + R.nsteps - 1u;
+                const uint32_t sepc = rev ? '<' : '>';
+                uint32_t m = sep_word(sm32, w, a5, b5);
+                uint32_t s = s0 + (item >> 15);
+                uint32_t prev = NONE32;                                     // node of the step before, inside this word
+                bool hand_over = false;
+                uint32_t sum = 0;
+                while (m) {
+                    uint32_t p_[UI], idx_[UI];
+                    uint4 hot_[UI];
 #pragma unroll
-                for (int u = 0; u < UI; u++) {
-                    const uint32_t s = s00 + THREADS * u + tid;
-                    uint32_t idx = NONE32, se = SE_INVALID;
-                    if (s < n_ent) {
-                        se = steps[s];
-                        if (se != SE_INVALID && !(se & SE_SENT)) {
-                            const uint32_t p = se & SE_POS_MASK;
-                            const uint32_t end = steps[s + 1u] & SE_POS_MASK;       // next separator, or the sentinel
+                    for (int u = 0; u < UI; u++) {
+                        p_[u] = NONE32;
+                        idx_[u] = NONE32;
+                        hot_[u] = make_uint4(0u, 0u, 0u, 0u);
+                        if (m) {
+                            const uint32_t p = 32u * w + (uint32_t)(__ffs((int)m) - 1);
+                            m &= m - 1u;
+                            // the id ends at the next separator -- in this word, in the next one -- or with the column
+                            uint32_t end = b5;
+                            if (m) end = 32u * w + (uint32_t)(__ffs((int)m) - 1);
+                            else if (32u * (w + 1u) < b5) {
+                                const uint32_t mn = sep_word(sm32, w + 1u, a5, b5);
+                                if (mn) end = 32u * (w + 1u) + (uint32_t)(__ffs((int)mn) - 1);
+                            }
+                            const uint32_t nd = end - p - 1u;
                             uint64_t id;
                             uint32_t ix;
                             // the separator the path began with (REF:186-194: a mixed path is a KeyError)
-                            if (buf[p] == ((se & SE_REV) ? '<' : '>') && step_id(buf, p + 1u, end - p - 1u, id) && sink.id_to_idx(id, ix)) idx = ix;
-                        }
-                    }
-                    idx_[u] = idx;                                          // NONE32: KeyError in the reference, `walk` hands the record over
-                    se_[u] = se;
-                    hot_[u] = make_uint4(0u, 0u, 0u, 0u);
-                    if (idx != NONE32) hot_[u] = sink.load_hot(idx);        // issued at once: in flight while the next id is parsed
-                }
-#pragma unroll
-                for (int u = 0; u < UI; u++) {
-                    const uint32_t s = s00 + THREADS * u + tid;
-                    if (s < n_ent) {
-                        const uint32_t se = se_[u], meta = hot_[u].x, len = meta & META_LEN_MASK;
-                        uint32_t share = SL_BAD;                            // absent node, >= 1023 bases, unknown id: exact path
-                        if (idx_[u] != NONE32 && len - 1u < META_LEN_ESC - 1u) {
-                            int32_t L = (int32_t)len;
-                            if (se & (SE_FIRST | SE_LAST)) {
-                                const Rec& R = recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK];
-                                int64_t L64 = L;
-                                if (se & SE_FIRST) L64 -= (int64_t)R.start + R.start_add;           // REF:215-216
-                                if (se & SE_LAST) L64 -= R.end_rel1;                                // REF:217-218
-                                L = L64 <= 0 ? 0 : (L64 >= (int64_t)SL_BAD ? (int32_t)SL_BAD : (int32_t)L64);
+                            if (buf[p] == sepc && step_id(buf, p + 1u, nd, id) && sink.id_to_idx(id, ix)) {
+                                idx_[u] = ix;
+                                hot_[u] = sink.load_hot(ix);                // issued at once: in flight while the next id is parsed
+                                if (prev == NONE32 && p != a5) {
+                                    // first step of the word: is the id before it spelled the same?
+                                    if (nd < p - a5 && buf[p - nd - 1u] == sepc) {
+                                        const uint32_t n8 = min(nd, 8u);
+                                        bool same = ((ld8(buf, p + 1u) ^ ld8(buf, p - nd)) << (8u * (8u - n8))) == 0ull;
+                                        if (nd > 8u) same = same && buf[p - nd + 8u] == buf[p + 9u] && (nd < 10u || buf[p - 1u] == buf[p + 10u]);
+                                        hand_over |= same;
+                                    }
+                                }
+                                hand_over |= ix == prev;
+                                prev = ix;
                             }
-                            share = (uint32_t)L;
+                            p_[u] = p;
                         }
-                        sidx[s] = idx_[u];
-                        smeta[s] = meta;
-                        sL[s] = (uint16_t)share;
                     }
+#pragma unroll
+                    for (int u = 0; u < UI; u++) {
+                        if (p_[u] != NONE32) {
+                            const uint32_t meta = hot_[u].x, len = meta & META_LEN_MASK;
+                            const bool ok = idx_[u] != NONE32 && len - 1u < META_LEN_ESC - 1u;   // absent node, >= 1023 bases, unknown id: exact path
+                            if (s < (uint32_t)G::STEP_CAP) {
+                                steps[s] = p_[u] | (l << SE_SLOT_SHIFT) | (rev ? SE_REV : 0u) | (1u << SE_NCNT_SHIFT) | (s == s0 ? SE_FIRST : 0u) |
+                                           (s == s_last ? SE_LAST : 0u);
+                                sidx[s] = idx_[u];
+                                smeta[s] = meta;
+                                sL[s] = (uint16_t)(ok ? len : SL_BAD);
+                            }
+                            hand_over |= !ok;
+                            sum += len;
+                            s++;
+                        }
+                    }
+                }
+                if (hand_over) {
+                    R.stB = ST_DEFER;
+                    R.whyB = WHY_WALK;
+                } else {
+                    atomicAdd(&R.sum, sum);
                 }
             }
         }
-        __syncthreads();                                                    // ---- B3: node indices complete; the bytes and the masks are dead
+        team_sync();                                                          // ---- B3: node indices complete; the bytes and the masks are dead
         if (tid == 0 && nxt_tile < A.n_tiles) issue_load(nxt_tile);        // overlaps walk + fold + count
         if (ablate == 4u) continue;
 
-        // ================= walk: warp 0, one thread per record; warp 1 drains the previous tile's far links =================
+        // ================= walk: warp 0; warp 1 drains the previous tile's far links =================
+        // (a) One thread per record, no loop: the two ends of the path are shortened (REF:215-218); every other node keeps its
+        //     whole length, so the record's sum of shares follows from the sum `ids` collected, and with it the one check the
+        //     merge walk needs for a single-op record: a node with bases left but no cs left is an IndexError (REF:227).
+        // (b) Records whose cs string has several ops, one at a time, one lane per step: prefix sum of the shares = the cs
+        //     coordinate of every node (REF:205-255); a node inside one ':' / '=' op has one counting op like every node of a
+        //     single-op record, the nodes an op boundary or a mismatch / indel falls into are listed for `fold`.
         if (warp == 0) {
-            uint32_t hbase = 0;                                             // warp-uniform: prefix-pool entries handed out
+            uint32_t n_heavy_w = 0;                                         // warp-uniform: entries of the fold list
             for (uint32_t l0 = 0; l0 < n_lines; l0 += 32u) {
                 const uint32_t l = l0 + lane;
-                bool fast = false, multi = false;
-                uint32_t ns = 0, s0 = 0;
+                bool multi = false;
                 if (l < n_lines) {
-                    const Rec& R = recs[l];
-                    fast = rec_status(R) == ST_FAST;
-                    if (fast) {
-                        ns = R.nsteps;
-                        s0 = R.s0;
-                        multi = R.single == 0;
+                    Rec& R = recs[l];
+                    if (rec_status(R) == ST_FAST) {
+                        const uint32_t ns = R.nsteps, s0 = R.s0, sl = s0 + ns - 1u, n_tot = R.n_tot;
+                        const uint32_t raw0 = sL[s0], raw1 = sL[sl];        // (not SL_BAD: `ids` would have handed the record over)
+                        // first node: L -= start_pos (REF:215-216); last node: L = L - end_pos_rel + 1 (REF:217-218)
+                        int64_t L0 = (int64_t)raw0 - ((int64_t)R.start + R.start_add), L1 = (int64_t)raw1 - R.end_rel1;
+                        if (ns == 1u) { L0 -= R.end_rel1; L1 = L0; }
+                        const uint32_t v0 = (uint32_t)(L0 <= 0 ? 0 : (L0 >= (int64_t)SL_BAD ? (int64_t)SL_BAD : L0));
+                        const uint32_t v1 = (uint32_t)(L1 <= 0 ? 0 : (L1 >= (int64_t)SL_BAD ? (int64_t)SL_BAD : L1));
+                        bool bad = v0 == SL_BAD || v1 == SL_BAD;
+                        // shares: v0, the interior nodes' whole lengths, v1; the last node with bases left starts at a_last
+                        const uint32_t total = ns == 1u ? v0 : R.sum - raw0 - raw1 + v0 + v1;
+                        uint32_t a_last = 0;
+                        if (ns > 1u) a_last = v1 ? total - v1 : (ns > 2u ? total - sL[sl - 1u] : 0u);
+                        if (total != 0u && a_last >= n_tot) bad = true;    // IndexError (REF:227): the exact path reports it
+                        if (bad) {
+                            R.stB = ST_DEFER;
+                            R.whyB = WHY_WALK;
+                        } else {
+                            sL[s0] = (uint16_t)v0;
+                            sL[sl] = (uint16_t)v1;
+                            // a node is not in `align` iff no bases are left for it: only the two ends can run out
+                            if (v0 == 0u) steps[s0] |= SE_DROPPED;
+                            if (v1 == 0u) steps[sl] |= SE_DROPPED;
+                            multi = R.single == 0;
+                        }
                     }
                 }
-                uint32_t total;
-                const uint32_t a_off = hbase + warp_excl_scan(multi ? ns : 0u, lane, total);
-                hbase += total;
-                if (fast) {
-                    Rec& R = recs[l];
-                    bool bad = false;
-                    if (multi && a_off + ns > (uint32_t)G::HEAVY_CAP) {         // prefix pool full: exact path
-                        for (uint32_t h = a_off; h < (uint32_t)G::HEAVY_CAP; h++) heavy[h] = 0xFFFFu;
-                        bad = true;
-                        multi = false;
-                        ns = 0;
-                    }
-                    uint32_t run = 0, a_last = 0, prev = NONE32;
-                    bool any = false;
-                    for (uint32_t k = 0; k < ns; k++) {
-                        const uint32_t v = sL[s0 + k], i = sidx[s0 + k];
-                        // unknown id: KeyError (REF:214); collapsible duplicate (REF:188): the exact path redoes the record
-                        bad |= v == SL_BAD || i == prev;
-                        prev = i;
-                        if (multi) {
-                            sA[a_off + k] = run;
-                            heavy[a_off + k] = (uint16_t)(s0 + k);
+                // ---- (b) the multi-op records of this batch, one after the other, the warp's lanes on the record's steps
+                uint32_t todo = __ballot_sync(FULL, multi);
+                while (todo) {
+                    const uint32_t lr = l0 + (uint32_t)(__ffs((int)todo) - 1);
+                    todo &= todo - 1u;
+                    Rec& R = recs[lr];
+                    const uint32_t ns = R.nsteps, s0 = R.s0, n_tot = R.n_tot;
+                    const uint32_t* op = ops + R.op_off;
+                    uint32_t carry = 0;
+                    bool full = false;
+                    for (uint32_t k0 = 0; k0 < ns; k0 += 32u) {
+                        const uint32_t k = k0 + lane;
+                        const uint32_t v = k < ns ? sL[s0 + k] : 0u;
+                        uint32_t incl = v;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t y = __shfl_up_sync(FULL, incl, o);
+                            if (lane >= (uint32_t)o) incl += y;
                         }
-                        if (v != 0u) { a_last = run; any = true; }
-                        run += v;
+                        const uint32_t run = carry + incl - v;              // cs coordinate where this node starts
+                        carry += __shfl_sync(FULL, incl, 31);
+                        bool list = false;
+                        if (k < ns && v != 0u && run < n_tot) {             // (run >= n_tot with bases left: excluded in (a))
+                            uint32_t j = 0, o_end = op[0] >> 3;
+                            while (o_end <= run) o_end += op[++j] >> 3;     // (run < n_tot = sum of the op lengths)
+                            const uint32_t kind = op[j] & 7u;
+                            list = min(run + v, n_tot) > o_end || (kind != OP_MATCH && kind != OP_EQ);
+                            sR[s0 + k] = (uint16_t)run;
+                        }
+                        const uint32_t bal = __ballot_sync(FULL, list);
+                        if (list) {
+                            const uint32_t h = n_heavy_w + (uint32_t)__popc(bal & lt_mask);
+                            if (h < (uint32_t)G::HEAVY_CAP) heavy[h] = (uint16_t)(s0 + k);
+                        }
+                        n_heavy_w += (uint32_t)__popc(bal);
+                        full |= n_heavy_w > (uint32_t)G::HEAVY_CAP;
                     }
-                    // a node with bases left but no cs left: IndexError (REF:227); the last such node starts furthest right
-                    if (any && a_last >= R.n_tot) bad = true;
-                    if (bad) {
+                    if (full && lane == 0) {                                // list full: exact path (nothing counted yet)
                         R.stB = ST_DEFER;
                         R.whyB = WHY_WALK;
-                    } else if (!multi && ns) {
-                        // one ':' / '=' op: a node is not in `align` iff no bases are left for it -- only the two ends can be
-                        if (sL[s0] == 0u) steps[s0] |= SE_DROPPED;
-                        if (sL[s0 + ns - 1u] == 0u) steps[s0 + ns - 1u] |= SE_DROPPED;
                     }
-                    R.a_off = (uint16_t)a_off;
                 }
             }
-            if (lane == 0) s_nheavy = min(hbase, (uint32_t)G::HEAVY_CAP);
+            if (lane == 0) s_nheavy = n_heavy_w;
         } else {
             drain_far();
             __syncwarp();
@@ -863,25 +985,20 @@ __global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(Chun
                 s_ndel = 0;
             }
         }
-        far_base = base_off;                                                // the list `count` fills below belongs to this tile
-        __syncthreads();                                                    // ---- B4: hand-over decisions of `walk`, prefix pool, heavy list
+        if (active) far_base = base_off;                                    // the list `count` fills below belongs to this tile
+        team_sync();                                                          // ---- B4: hand-over decisions of `walk`, prefix pool, heavy list
         if (ablate == 5u) continue;
 
         // ================= fold: every step of a multi-op record folds the cs ops that overlap its node =================
-        const uint32_t n_heavy = s_nheavy;
-        if (n_heavy != 0u) {
+        const uint32_t n_heavy = min(s_nheavy, (uint32_t)G::HEAVY_CAP);
+        {
             for (uint32_t h = tid; h < n_heavy; h += THREADS) {
                 const uint32_t s = heavy[h];
-                if (s == 0xFFFFu) continue;                                 // (pool overflow: that record went to the exact path)
                 const uint32_t se = steps[s];
                 Rec& R = recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK];
                 if (rec_status(R) != ST_FAST) continue;
-                const uint32_t Lk = sL[s];
-                if (Lk == 0u) {                                             // no bases left for this node: it is not in `align`
-                    steps[s] = se | SE_DROPPED;
-                    continue;
-                }
-                const uint32_t Ak = sA[h], n_tot = R.n_tot;                 // Ak < n_tot (walk)
+                const uint32_t Lk = sL[s];                                  // > 0 (walk)
+                const uint32_t Ak = sR[s], n_tot = R.n_tot;                 // Ak < n_tot (walk)
                 const uint32_t* op = ops + R.op_off;
                 const uint32_t nops = R.nops;
                 const uint32_t Bk = min(Ak + Lk, n_tot);
@@ -939,7 +1056,7 @@ __global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(Chun
                     }
                 }
             }
-            __syncthreads();                                                // ---- B5: every hand-over decision is made; nothing counted so far
+            team_sync();                                                      // ---- B5: every hand-over decision is made; nothing counted so far
         }
         for (uint32_t l = tid; l < n_lines; l += THREADS) {
             const Rec& R = recs[l];
@@ -947,19 +1064,19 @@ __global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(Chun
         }
 
         // surviving neighbours of step s inside its record (dropped nodes are skipped)
-        auto prev_survivor = [&](uint32_t s) -> uint32_t {                  // NONE32: s is the first survivor
-            uint32_t t = s;
-            while (!(steps[t] & SE_FIRST)) {
-                t--;
-                if (!(steps[t] & SE_DROPPED)) return t;
+        auto prev_survivor = [&](uint32_t s, uint32_t se) -> uint32_t {     // NONE32: s is the first survivor (se = steps[s])
+            uint32_t t = s, e = se;
+            while (!(e & SE_FIRST)) {
+                e = steps[--t];
+                if (!(e & SE_DROPPED)) return t;
             }
             return NONE32;
         };
-        auto next_survivor = [&](uint32_t s) -> uint32_t {                  // NONE32: s is the last survivor
-            uint32_t t = s;
-            while (!(steps[t] & SE_LAST)) {
-                t++;
-                if (!(steps[t] & SE_DROPPED)) return t;
+        auto next_survivor = [&](uint32_t s, uint32_t se) -> uint32_t {     // NONE32: s is the last survivor
+            uint32_t t = s, e = se;
+            while (!(e & SE_LAST)) {
+                e = steps[++t];
+                if (!(e & SE_DROPPED)) return t;
             }
             return NONE32;
         };
@@ -971,7 +1088,7 @@ __global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(Chun
             if (se == SE_INVALID || (se & (SE_SENT | SE_DROPPED)) || rec_status(recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK]) != ST_FAST) continue;
             const uint32_t idx = sidx[s], meta = smeta[s];
             const bool rev = (se & SE_REV) != 0u;
-            const uint32_t ps = prev_survivor(s), nx = next_survivor(s);
+            const uint32_t ps = prev_survivor(s, se), nx = next_survivor(s, se);
             const bool first = ps == NONE32, last = nx == NONE32;           // among the surviving nodes (REF:276-353: i == 0, i == last)
             const uint32_t n_count = (se >> SE_NCNT_SHIFT) & 3u;
             // this step owns the link that LEAVES its node (REF:357-359): to the next survivor forward, to the previous one reverse;
@@ -1014,7 +1131,7 @@ __global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(Chun
                 const uint32_t idx = sidx[s];
                 const int64_t len = (int64_t)(smeta[s] & META_LEN_MASK);
                 const bool rev = (se & SE_REV) != 0u;
-                const bool not_first = prev_survivor(s) != NONE32, not_last = next_survivor(s) != NONE32;
+                const bool not_first = prev_survivor(s, se) != NONE32, not_last = next_survivor(s, se) != NONE32;
                 const bool first_del = (f >> 31) != 0u, last_del = (g >> 31) != 0u;
                 const int64_t first_len = f & 0x7FFFFFFFu, last_len = g & 0x7FFFFFFFu;     // >= 1: no op is empty here
                 const uint64_t stamp = (uint64_t)(base_off + (int64_t)(se & SE_POS_MASK) + 1) << 2;
@@ -1034,15 +1151,18 @@ __global__ void __launch_bounds__(THREADS, G::MIN_CTAS) augment_team_kernel(Chun
     __syncthreads();                                                        // the last tile's far-link list is complete
 
     drain_far();
-    if (tid == 0) *(volatile uint32_t*)&T.team_tile[blockIdx.x] = 0xFFFFFFFFu;   // nothing of mine is pending any more
+    if (tid == 0) *(volatile uint32_t*)&T.team_tile[gteam] = 0xFFFFFFFFu;   // nothing of mine is pending any more
 
     // rejected-record count: warp reduce, one RED per warp
     uint32_t r = sink.rej;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
     if (lane == 0u && r) atomicAdd(&T.sc[SC_REJ], (unsigned long long)r);
+    uint32_t nl = my_real;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nl += __shfl_xor_sync(FULL, nl, o);
+    if (lane == 0u && nl) atomicAdd(&T.sc[SC_LINES], (unsigned long long)nl);
     if (tid == 0) {
-        if (my_lines) atomicAdd(&T.sc[SC_LINES], my_lines);
         if (my_tiles) atomicAdd(&T.sc[SC_TILES], my_tiles);
     }
 }

@@ -22,6 +22,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__ inline
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static
@@ -53,6 +54,7 @@ struct State {
     std::vector<Fibre> fib;
     std::vector<Warp> warps;
     uint32_t live = 0, bar_arrived = 0, bar_gen = 0;
+    uint32_t named_arrived[16] = {0}, named_gen[16] = {0};
     int cur = -1;
     const std::function<void()>* body = nullptr;
 };
@@ -90,6 +92,7 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::
         s.warps.assign((block + 31) / 32, Warp());
         s.live = block;
         s.bar_arrived = 0;
+        for (int k = 0; k < 16; k++) { s.named_arrived[k] = 0; s.named_gen[k] = 0; }
         for (unsigned t = 0; t < block; t++) {
             Fibre& f = s.fib[t];
             f.done = false;
@@ -161,6 +164,21 @@ inline void __syncthreads() {
         emu::yield();
     }
 }
+// bar.sync id, count: `count` threads of the block meet at named barrier `id` (1..15)
+inline void emu_named_barrier(unsigned id, unsigned count) {
+    emu::State& s = emu::S();
+    s.named_arrived[id]++;
+    const uint32_t gen = s.named_gen[id];
+    while (s.named_gen[id] == gen) {
+        if (s.named_arrived[id] >= count) {
+            s.named_arrived[id] = 0;
+            s.named_gen[id]++;
+            s.bar_gen++;                     // (progress marker for the deadlock detector)
+            break;
+        }
+        emu::yield();
+    }
+}
 inline void __syncwarp(unsigned = 0xffffffffu) { (void)emu::shfl(0, 0); }
 
 inline uint32_t __shfl_sync(unsigned, uint32_t v, int src) { return emu::shfl(v, src & 31); }
@@ -199,6 +217,12 @@ inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t sh) {
 inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
     const uint64_t v = ((uint64_t)hi << 32) | lo;
     return (uint32_t)(v >> (sh & 31u));
+}
+inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t sel) {
+    const uint64_t v = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+    return r;
 }
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T __ldcg(const T* p) { return *p; }

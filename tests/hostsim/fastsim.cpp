@@ -26,7 +26,8 @@ template <class G>
 void run_fast(unsigned grid, ChunkArgs A, const Tables& T) {
     A.n_tiles = (uint32_t)((A.nbytes + G::TILE - 1) / G::TILE);
     if (grid > A.n_tiles) grid = A.n_tiles;
-    emu::launch(grid, teamp::THREADS, G::SMEM_BYTES, [&] { teamp::augment_team_kernel<G>(A, T); });
+    const unsigned ctas = (grid + G::NT - 1) / G::NT;           // `grid` counts teams
+    emu::launch(ctas, teamp::THREADS * G::NT, (size_t)G::SMEM_BYTES * G::NT, [&] { teamp::augment_team_kernel<G>(A, T); });
 }
 
 }  // namespace
@@ -108,9 +109,9 @@ int fastsim_run(const uint8_t* gaf, uint64_t nbytes, uint64_t file_off, int64_t 
     A.file_off = (int64_t)file_off;
     A.thr = thr;
     if (nbytes) {
-        typedef teamp::Geo<1024, 256, 128, 1> G0;
-        typedef teamp::Geo<4096, 512, 256, 1> G1;
-        typedef teamp::Geo<8192, 1024, 512, 10> G2;
+        typedef teamp::Geo<1024, 256, 96, 2, 1> G0;
+        typedef teamp::Geo<4096, 512, 256, 3, 1> G1;
+        typedef teamp::Geo<8192, 1024, 512, 5, 2> G2;
         if (geo == 0) run_fast<G0>(grid, A, T);
         else if (geo == 1) run_fast<G1>(grid, A, T);
         else run_fast<G2>(grid, A, T);

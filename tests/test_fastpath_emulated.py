@@ -143,3 +143,52 @@ def test_far_links_are_counted_one_tile_later(seed, tmp_path):
     assert res[0] == "ok", res
     assert res[1] == orc.out
     assert res[2] == orc.rej
+
+
+def test_long_paths_duplicates_and_multi_op_records(tmp_path):
+    """Paths of 40+ steps (a multi-op record spans more than one 32-lane batch of `walk`), consecutive duplicate ids
+    (REF:188 collapses them) at every alignment relative to the 32-byte mask words, mismatches / indels on short nodes."""
+    import random
+
+    rng = random.Random(5)
+    n = 70
+    gfa = ["H\tVN:Z:1.1"] + [f"S\t{i}\t{'ACGT'[i % 4] * 2}" for i in range(1, n + 1)]
+    gfa += [f"L\t{i}\t+\t{i + 1}\t+\t*" for i in range(1, n)] + [f"L\t{i}\t+\t{i + 2}\t+\t*" for i in range(1, n - 1, 7)]
+    recs = []
+    for r in range(160):
+        a = rng.randrange(1, 20)
+        k = rng.randrange(2, 48) if r % 5 == 0 else rng.randrange(2, 24)
+        ids = list(range(a, a + k))
+        if r % 3 == 0:                                   # a consecutive duplicate somewhere
+            j = rng.randrange(0, k)
+            ids.insert(j, ids[j])
+        rev = r % 2 == 1
+        path = "".join(("<" if rev else ">") + str(i) for i in (reversed(ids) if rev else ids))
+        nuniq = k
+        plen = 2 * len(ids)
+        qlen = 2 * nuniq
+        kind = r % 4
+        if kind == 0:
+            cs = f":{qlen}"
+        elif kind == 1:
+            x = rng.randrange(1, qlen - 1)
+            cs = f":{x}*ag:{qlen - x - 1}"
+        elif kind == 2:
+            x = rng.randrange(1, qlen - 2)
+            cs = f":{x}-ac:{qlen - x - 2}"
+        else:
+            x = rng.randrange(1, qlen - 1)
+            cs = f":{x}+t:{qlen - x - 1}"
+        name = "r" * (200 + r % 37)                 # long names: few records per tile, so that most of them stay on the fast path
+        recs.append(f"{name}\t{qlen}\t0\t{qlen}\t+\t{path}\t{plen}\t0\t{plen}\t{qlen}\t{qlen}\t60\tAS:i:1\tcs:Z:{cs}\tdv:f:0.01")
+    gfa_s, gaf_s = "\n".join(gfa) + "\n", "\n".join(recs) + "\n"
+    orc = run_oracle(gaf_s.encode(), gfa_s.encode())
+    assert orc.rc == 0, orc.err
+    for geo in (0, 1, 2):
+        st = {}
+        res = pipeline(tmp_path, gfa_s, gaf_s, geo=geo, grid=2, stats=st)
+        assert res[0] == "ok", res
+        assert res[1] == orc.out
+        assert res[2] == orc.rej
+        if geo:
+            assert st["deferred"] < 90, st                 # the 54 records with a duplicate id + a few list overflows

@@ -46,7 +46,7 @@ print(f"fast kernel {f / nn:.3f} ms, per-record kernel {sl / nn:.3f} ms (avg of 
 eng.check_data_error()
 print(eng.stats(), eng.handover_reasons())
 if a.ladder:
-    # every tile stops after phase k: TMA only, + scan, + records, + ids, + walk, everything (results are wrong on purpose
+    # every tile stops after phase k: TMA only, + scan, + records, + ids, + walk 1, + walk 2, everything (results are wrong on purpose
     # for k != 0; timing only).  A fresh context per rung: PANTAS_ABLATE is read by pt_create.
     names = {1: "tma only", 2: "+ scan", 3: "+ records", 4: "+ ids", 5: "+ walk", 0: "+ fold + count (all)"}
     g = sg.graph()
