@@ -146,11 +146,11 @@ static int fold_epoch(pt_ctx* ctx) {
 }
 
 // the fast path's geometries: Geo<tile, look-ahead, step-list entries, teams per CTA, CTAs per SM>
-typedef teamp::Geo<8192, 1024, 512, 5, 2> GeoP;      // production
+typedef teamp::Geo<8192, 1024, 512, 10, 1> GeoP;     // production: one CTA of ten teams per SM (measured best, profiles/r02_geometry_sweep.txt)
 typedef teamp::Geo<7168, 1024, 448, 5, 2> GeoQ;
 typedef teamp::Geo<6144, 1024, 384, 6, 2> GeoR;
 typedef teamp::Geo<12288, 1024, 768, 7, 1> GeoS;
-typedef teamp::Geo<8192, 1024, 512, 10, 1> GeoU;     // one CTA of ten teams per SM
+typedef teamp::Geo<8192, 1024, 512, 5, 2> GeoU;      // two CTAs of five teams per SM
 typedef teamp::Geo<1024, 256, 96, 2, 1> GeoT;        // tests: many tile boundaries, records longer than the look-ahead
 
 template <class G>
@@ -443,7 +443,7 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
     A.file_off = (int64_t)file_offset;
     A.thr = thr;
     A.ablate = ctx->ablate;
-    A.loose = env_u32("PANTAS_LOOSE", 0);
+    A.loose = env_u32("PANTAS_LOOSE", 1);
     {   // measured: -4 % kernel time, -25 % DRAM reads (PANTAS_STREAM_HINT=0 switches it off)
         const char* h = getenv("PANTAS_STREAM_HINT");
         A.stream_hint = (h && h[0] == '0') ? 0u : 1u;

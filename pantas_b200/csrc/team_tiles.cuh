@@ -61,13 +61,11 @@ struct __align__(4) Rec {
     uint8_t nops;         //                                                   (role A)
     uint8_t stA, stB;     // ST_* per role; walk raises stB
     uint8_t whyA;         // WHY_* when role A says ST_DEFER
-    uint16_t a5r;         // path column starts at buffer position a5r & 0x7FFF; bit 15: it starts with '<' (role B)
+    uint16_t spare;
     uint8_t whyB;
     uint8_t single;       // 1: one ':' or '=' op -- every node with a positive share survives, one counting op  (role A)
-    uint16_t b5;          // end of the path column                            (role B)
-    uint16_t pad;
 };
-static_assert(sizeof(Rec) == 36 && offsetof(Rec, nops) == 24, "rec_status reads nops / stA / stB / whyA as one word");
+static_assert(sizeof(Rec) == 32 && offsetof(Rec, nops) == 24, "rec_status reads nops / stA / stB / whyA as one word");
 
 // step list entry
 constexpr uint32_t SE_POS_MASK = 0xFFFFu;     // bits 0..15  buffer position of the separator (sentinel: end of the path column)
@@ -90,7 +88,6 @@ struct Geo {
     static constexpr int HEAVY_CAP = 160;                         // steps of multi-op records that an op boundary / mismatch / indel falls into
     static constexpr int FAR_CAP = 48;                            // links that are not inline: typically 1 per record
     static constexpr int DEL_CAP = 24;                            // steps with deletion-derived keys
-    static constexpr int ITEM_CAP = 224;                          // (record, 32-byte word of its path column) pairs: typically 4-5 per record
     static constexpr int NT = NT_;                                // teams per CTA: they walk through the phases together (one instruction working set)
     static constexpr int CTAS = CTAS_;                            // CTAs per SM
     // masks are dead after `records`; sL / prefix pool / heavy list live from `ids` to `fold` in the same bytes
@@ -110,8 +107,7 @@ struct Geo {
     static constexpr int OFF_DEL = OFF_FAR + 12 * FAR_CAP;
     static constexpr int OFF_REC = (OFF_DEL + 12 * DEL_CAP + 7) & ~7;
     static constexpr int OFF_LINES = OFF_REC + (int)sizeof(Rec) * LINE_CAP;
-    static constexpr int OFF_ITEMS = (OFF_LINES + 2 * LINE_CAP + 3) & ~3;
-    static constexpr int SMEM_BYTES = (OFF_ITEMS + 4 * ITEM_CAP + 127) & ~127;
+    static constexpr int SMEM_BYTES = (OFF_LINES + 2 * LINE_CAP + 127) & ~127;
     static_assert(BUF <= 65536, "step entries hold 16-bit positions");
     static_assert(2 * STEP_CAP <= 2 * NV, "`ids` writes sL while it still reads the separator masks: sL must stay inside the whitespace masks");
     static_assert(LINE_CAP <= 64, "step entries hold 6-bit record slots");
@@ -268,7 +264,7 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane, ui
 struct __align__(8) TeamCtl {
     uint64_t mbar;               // the tile's TMA copy has landed
     uint32_t cnt[2];             // record starts found by each warp
-    uint32_t nent, nitems, nheavy, nfar, ndel, far_take, lwm;
+    uint32_t nent, nheavy[2], nfar, ndel, far_take, lwm;
 };
 static_assert(sizeof(TeamCtl) <= 64, "OFF_WM leaves 64 bytes for the control block");
 
@@ -282,7 +278,8 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
     TeamCtl& C = *reinterpret_cast<TeamCtl*>(smem + G::OFF_CTL);
     uint64_t& mbar = C.mbar;
     uint32_t* const s_cnt = C.cnt;
-    uint32_t &s_nent = C.nent, &s_nitems = C.nitems, &s_nheavy = C.nheavy, &s_nfar = C.nfar, &s_ndel = C.ndel, &s_far_take = C.far_take, &s_lwm = C.lwm;
+    uint32_t* const s_nheavy2 = C.nheavy;
+    uint32_t &s_nent = C.nent, &s_nfar = C.nfar, &s_ndel = C.ndel, &s_far_take = C.far_take, &s_lwm = C.lwm;
     const uint32_t gteam = blockIdx.x * (uint32_t)G::NT + team, nteams = gridDim.x * (uint32_t)G::NT;
     // inside a tile the phases only need the team's own two warps; the CTA-wide barrier after `scan` re-aligns the teams
     auto team_sync = [&]() { if (A.loose) named_barrier(team + 1u, THREADS); else __syncthreads(); };
@@ -302,7 +299,6 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
     uint32_t* const far = reinterpret_cast<uint32_t*>(smem + G::OFF_FAR);      // {from, to, separator position}: filled by `count`, drained during the next tile's `walk`
     uint32_t* const dels = reinterpret_cast<uint32_t*>(smem + G::OFF_DEL);     // {step, first del, last del}
     Rec* const recs = reinterpret_cast<Rec*>(smem + G::OFF_REC);
-    uint32_t* const items = reinterpret_cast<uint32_t*>(smem + G::OFF_ITEMS);  // record slot | word << 6 | steps of the record before this word << 15
     uint16_t* const lines = reinterpret_cast<uint16_t*>(smem + G::OFF_LINES);  // record starts: warp 0 fills the list from the front, warp 1 from the back
 
     if (tid == 0) {
@@ -310,7 +306,8 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
         s_nfar = 0;
         s_ndel = 0;
         s_far_take = 0;
-        s_nheavy = 0;
+        s_nheavy2[0] = 0;
+        s_nheavy2[1] = 0;
         s_nent = 0;
     }
     __syncthreads();
@@ -402,7 +399,8 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
                 const uint32_t s23 = lop3<0xCA>(0x80808080u, sv[3], sv[2] >> 4) & 0x88888888u;
                 uint32_t wm = __byte_perm(w01 * 0x00204081u, w23 * 0x00204081u, 0x4473);   // byte 3 of each product -> 16-bit mask
                 uint32_t sm = __byte_perm(s01 * 0x00204081u, s23 * 0x00204081u, 0x4473);
-                if (decltype(tail)::value) {                                // the last vectors: nothing past the data
+                const bool last = decltype(tail)::value && v + 2u >= nvec;   // the last vectors: nothing past the data
+                if (last) {
                     const uint32_t room = lim > 16u * v ? lim - 16u * v : 0u;
                     const uint32_t keep = room < 16u ? ~(~0u << room) : 0xFFFFu;
                     wm &= keep;
@@ -410,7 +408,12 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
                 }
                 wm16[v] = (uint16_t)wm;
                 sm16[v] = (uint16_t)sm;
-                hib |= (q.x | q.y) | (q.z | q.w);
+                if (last) {                                                 // (bytes past the data are whatever the buffer held before)
+                    for (uint32_t p = max(16u * v, 16u); p < min(16u * v + 16u, min(lim, own_end)); p++)
+                        if (buf[p] >= 0x80u) hib |= 0x80u;
+                } else {
+                    hib |= (q.x | q.y) | (q.z | q.w);
+                }
             };
             const uint32_t nfull = nvec > 2u ? (nvec - 2u) / (4u * THREADS) : 0u;     // rounds in which every vector is whole
             uint32_t hib = 0;
@@ -504,11 +507,11 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
 
         // ================= records: warp 0 = role B, warp 1 = role A, one thread per record =================
         if (warp == 0) {
-            uint32_t step_base = 0, item_base = 0;                          // warp-uniform: step entries / items handed out so far
+            uint32_t step_base = 0;                                         // warp-uniform: entries handed out so far
             for (uint32_t l0 = 0; l0 < n_lines; l0 += 32u) {
                 const uint32_t l = l0 + lane;
                 const bool have = l < n_lines;
-                uint32_t st = ST_DONE, ns = 0, nw = 0, a5 = 0, b5 = 0, ls = 0;
+                uint32_t st = ST_DONE, ns = 0, a5 = 0, b5 = 0, ls = 0;
                 int why = WHY_LONG;
                 int32_t plen = 0, start = 0, pend = 0;
                 if (have) {
@@ -547,45 +550,27 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
                         slow = !small_uint(buf, e[6] + 1u, e[7], plen) || !small_uint(buf, e[7] + 1u, e[8], start) ||
                                !small_uint(buf, e[8] + 1u, e[9], pend);
                     if (!slow && !done && no_tags) { slow = true; why = WHY_TAGS; }   // no dv tag: ValueError (REF:179), the exact path reports
-                    // ---- path column (REF:185-197): it must start with a separator
+                    // ---- path column (REF:185-197): it must start with a separator; count the steps
                     if (!slow && !done) {
                         why = WHY_PATH;
                         a5 = e[5] + 1u;
                         b5 = e[6];
-                        nw = ((b5 - 1u) >> 5) - (a5 >> 5) + 1u;
-                        if (!((sm32[a5 >> 5] >> (a5 & 31u)) & 1u)) slow = true;
+                        for (uint32_t w = a5 >> 5; w <= ((b5 - 1u) >> 5); w++) ns += (uint32_t)__popc(sep_word(sm32, w, a5, b5));
+                        if (ns == 0u || ns > (uint32_t)MAX_STEPS || !((sm32[a5 >> 5] >> (a5 & 31u)) & 1u)) slow = true;
                     }
                     st = slow ? ST_DEFER : (done ? ST_DONE : ST_FAST);
-                    if (st != ST_FAST) nw = 0;
-                }
-                // ---- one item per 32-byte word of the path column: `ids` turns its separator bits into steps
-                uint32_t total;
-                const uint32_t it0 = item_base + warp_excl_scan(nw, lane, total);
-                item_base += total;
-                if (st == ST_FAST) {
-                    if (it0 + nw > (uint32_t)G::ITEM_CAP) {                 // list full: exact path
-                        st = ST_DEFER;
-                        why = WHY_STEPS_FULL;
-                        for (uint32_t i = it0; i < (uint32_t)G::ITEM_CAP; i++) items[i] = 0xFFFFFFFFu;
-                    } else {
-                        const uint32_t w0 = a5 >> 5;
-                        for (uint32_t k = 0; k < nw; k++) {
-                            items[it0 + k] = l | ((w0 + k) << 6) | (ns << 15);
-                            ns += (uint32_t)__popc(sep_word(sm32, w0 + k, a5, b5));
-                        }
-                        if (ns > (uint32_t)MAX_STEPS) { st = ST_DEFER; ns = 0; }     // (ns >= 1: the column starts with a separator)
-                    }
                     if (st != ST_FAST) ns = 0;
                 }
-                // ---- list space for the steps of the warp's records
-                const uint32_t off = step_base + warp_excl_scan(ns, lane, total);
+                // ---- list space for the steps of the warp's records (+ one sentinel each)
+                uint32_t total;
+                uint32_t off = step_base + warp_excl_scan(st == ST_FAST ? ns + 1u : 0u, lane, total);
                 step_base += total;
                 if (have) {
                     Rec& R = recs[l];
-                    if (st == ST_FAST && off + ns > (uint32_t)G::STEP_CAP) {          // list full: exact path
+                    if (st == ST_FAST && off + ns + 1u > (uint32_t)G::STEP_CAP) {      // list full: exact path
                         st = ST_DEFER;
                         why = WHY_STEPS_FULL;
-                        for (uint32_t i = off; i < (uint32_t)G::STEP_CAP; i++) steps[i] = SE_INVALID;   // (`ids` will not write these)
+                        for (uint32_t i = off; i < (uint32_t)G::STEP_CAP; i++) steps[i] = SE_INVALID;
                     }
                     R.ls = (uint16_t)ls;
                     R.stB = (uint8_t)st;
@@ -598,15 +583,24 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
                         R.end_rel1 = plen - pend - 1;
                         R.s0 = (uint16_t)off;
                         R.nsteps = (uint16_t)ns;
-                        R.a5r = (uint16_t)(a5 | (buf[a5] == '<' ? 0x8000u : 0u));
-                        R.b5 = (uint16_t)b5;
+                        // ---- one entry per path step, then the sentinel (end of the column)
+                        const uint32_t common = (l << SE_SLOT_SHIFT) | (buf[a5] == '<' ? SE_REV : 0u) | (1u << SE_NCNT_SHIFT);
+                        uint32_t i = off;
+                        for (uint32_t w = a5 >> 5; w <= ((b5 - 1u) >> 5); w++) {
+                            uint32_t m = sep_word(sm32, w, a5, b5);
+                            const uint32_t wb = (32u * w) | common;
+                            while (m) {
+                                steps[i++] = wb + (uint32_t)(__ffs((int)m) - 1);
+                                m &= m - 1u;
+                            }
+                        }
+                        steps[off] |= SE_FIRST;
+                        steps[off + ns - 1u] |= SE_LAST;
+                        steps[off + ns] = b5 | (l << SE_SLOT_SHIFT) | SE_SENT;
                     }
                 }
             }
-            if (lane == 0) {
-                s_nent = min(step_base, (uint32_t)G::STEP_CAP);
-                s_nitems = min(item_base, (uint32_t)G::ITEM_CAP);
-            }
+            if (lane == 0) s_nent = min(step_base, (uint32_t)G::STEP_CAP);
         } else {
             uint32_t ops_base = 0;                                          // warp-uniform: op-pool words handed out so far
             for (uint32_t l0 = 0; l0 < n_lines; l0 += 32u) {
@@ -793,97 +787,64 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
             }
         }
         team_sync();                                                          // ---- B2: records, ops, step list complete
-        const uint32_t n_ent = s_nent;                                      // step entries
+        const uint32_t n_ent = s_nent;                                      // step entries incl. sentinels
         if (ablate == 3u) {
             __syncthreads();
             if (tid == 0 && nxt_tile < A.n_tiles) issue_load(nxt_tile);
             continue;
         }
 
-        // ================= ids: one thread per item (a 32-byte word of a path column) =================
-        // Every separator bit of the word is a path step: SWAR decimal parse of the id that follows it -> node index -> ONE
-        // 16-byte load of the node's hot record, up to UI of them in flight per thread.  Writes the step list (entry, node
-        // index, meta word, node length) and collects what `walk` needs per record: the sum of the node lengths, and
-        // whether two consecutive ids are equal (REF:188 collapses those: the exact path redoes such a record).
+        // ================= ids: one thread per path step: id -> node index -> the node's hot record =================
+        // UI steps per thread and iteration: their 16-byte loads are all in flight before the first is used.  A warp holds 32
+        // consecutive entries, so the collapsible duplicates of REF:188 show up in a shuffle; the record's sum of node lengths
+        // is collected on the way.
         {
             constexpr int UI = 4;
-            const uint32_t n_items = s_nitems;
-            for (uint32_t it = tid; it < n_items; it += THREADS) {
-                const uint32_t item = items[it];
-                if (item == 0xFFFFFFFFu) continue;                          // (list overflow: that record went to the exact path)
-                const uint32_t l = item & 63u, w = (item >> 6) & 511u;
-                Rec& R = recs[l];
-                if (R.nsteps == 0u) continue;                               // (role B handed the record over after listing the item)
-                const uint32_t a5 = R.a5r & 0x7FFFu, rev = R.a5r >> 15, b5 = R.b5, s0 = R.s0, s_last = s0 + R.nsteps - 1u;
-                const uint32_t sepc = rev ? '<' : '>';
-                uint32_t m = sep_word(sm32, w, a5, b5);
-                uint32_t s = s0 + (item >> 15);
-                uint32_t prev = NONE32;                                     // node of the step before, inside this word
-                bool hand_over = false;
-                uint32_t sum = 0;
-                while (m) {
-                    uint32_t p_[UI], idx_[UI];
-                    uint4 hot_[UI];
+            for (uint32_t s00 = 0; s00 < n_ent; s00 += THREADS * UI) {
+                uint32_t idx_[UI], se_[UI];
+                uint4 hot_[UI];
 #pragma unroll
-                    for (int u = 0; u < UI; u++) {
-                        p_[u] = NONE32;
-                        idx_[u] = NONE32;
-                        hot_[u] = make_uint4(0u, 0u, 0u, 0u);
-                        if (m) {
-                            const uint32_t p = 32u * w + (uint32_t)(__ffs((int)m) - 1);
-                            m &= m - 1u;
-                            // the id ends at the next separator -- in this word, in the next one -- or with the column
-                            uint32_t end = b5;
-                            if (m) end = 32u * w + (uint32_t)(__ffs((int)m) - 1);
-                            else if (32u * (w + 1u) < b5) {
-                                const uint32_t mn = sep_word(sm32, w + 1u, a5, b5);
-                                if (mn) end = 32u * (w + 1u) + (uint32_t)(__ffs((int)mn) - 1);
-                            }
-                            const uint32_t nd = end - p - 1u;
+                for (int u = 0; u < UI; u++) {
+                    const uint32_t s = s00 + THREADS * u + tid;
+                    uint32_t idx = NONE32, se = SE_INVALID;
+                    if (s < n_ent) {
+                        se = steps[s];
+                        if (se != SE_INVALID && !(se & SE_SENT)) {
+                            const uint32_t p = se & SE_POS_MASK;
+                            const uint32_t end = steps[s + 1u] & SE_POS_MASK;       // next separator, or the sentinel
                             uint64_t id;
                             uint32_t ix;
                             // the separator the path began with (REF:186-194: a mixed path is a KeyError)
-                            if (buf[p] == sepc && step_id(buf, p + 1u, nd, id) && sink.id_to_idx(id, ix)) {
-                                idx_[u] = ix;
-                                hot_[u] = sink.load_hot(ix);                // issued at once: in flight while the next id is parsed
-                                if (prev == NONE32 && p != a5) {
-                                    // first step of the word: is the id before it spelled the same?
-                                    if (nd < p - a5 && buf[p - nd - 1u] == sepc) {
-                                        const uint32_t n8 = min(nd, 8u);
-                                        bool same = ((ld8(buf, p + 1u) ^ ld8(buf, p - nd)) << (8u * (8u - n8))) == 0ull;
-                                        if (nd > 8u) same = same && buf[p - nd + 8u] == buf[p + 9u] && (nd < 10u || buf[p - 1u] == buf[p + 10u]);
-                                        hand_over |= same;
-                                    }
-                                }
-                                hand_over |= ix == prev;
-                                prev = ix;
-                            }
-                            p_[u] = p;
+                            if (buf[p] == ((se & SE_REV) ? '<' : '>') && step_id(buf, p + 1u, end - p - 1u, id) && sink.id_to_idx(id, ix)) idx = ix;
                         }
                     }
-#pragma unroll
-                    for (int u = 0; u < UI; u++) {
-                        if (p_[u] != NONE32) {
-                            const uint32_t meta = hot_[u].x, len = meta & META_LEN_MASK;
-                            const bool ok = idx_[u] != NONE32 && len - 1u < META_LEN_ESC - 1u;   // absent node, >= 1023 bases, unknown id: exact path
-                            if (s < (uint32_t)G::STEP_CAP) {
-                                steps[s] = p_[u] | (l << SE_SLOT_SHIFT) | (rev ? SE_REV : 0u) | (1u << SE_NCNT_SHIFT) | (s == s0 ? SE_FIRST : 0u) |
-                                           (s == s_last ? SE_LAST : 0u);
-                                sidx[s] = idx_[u];
-                                smeta[s] = meta;
-                                sL[s] = (uint16_t)(ok ? len : SL_BAD);
-                            }
-                            hand_over |= !ok;
-                            sum += len;
-                            s++;
-                        }
-                    }
+                    idx_[u] = idx;                                          // NONE32: KeyError in the reference, the exact path reports it
+                    se_[u] = se;
+                    hot_[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if (idx != NONE32) hot_[u] = sink.load_hot(idx);        // issued at once: in flight while the next id is parsed
                 }
-                if (hand_over) {
-                    R.stB = ST_DEFER;
-                    R.whyB = WHY_WALK;
-                } else {
-                    atomicAdd(&R.sum, sum);
+#pragma unroll
+                for (int u = 0; u < UI; u++) {
+                    const uint32_t s = s00 + THREADS * u + tid;
+                    const uint32_t se = se_[u];
+                    const uint32_t prev = __shfl_up_sync(FULL, idx_[u], 1);  // (lane 0's predecessor sits in the other warp: `walk` checks those pairs)
+                    if (s < n_ent) {
+                        const uint32_t meta = hot_[u].x, len = meta & META_LEN_MASK;
+                        const bool step = se != SE_INVALID && !(se & SE_SENT);
+                        const bool ok = idx_[u] != NONE32 && len - 1u < META_LEN_ESC - 1u;   // absent node, >= 1023 bases, unknown id: exact path
+                        sidx[s] = idx_[u];
+                        smeta[s] = meta;
+                        sL[s] = (uint16_t)(ok ? len : SL_BAD);
+                        if (step) {
+                            Rec& R = recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK];
+                            if (!ok || (lane != 0u && !(se & SE_FIRST) && idx_[u] == prev)) {
+                                R.stB = ST_DEFER;                           // (a FAST record: role B listed the step)
+                                R.whyB = WHY_WALK;
+                            } else {
+                                atomicAdd(&R.sum, len);
+                            }
+                        }
+                    }
                 }
             }
         }
@@ -891,17 +852,27 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
         if (tid == 0 && nxt_tile < A.n_tiles) issue_load(nxt_tile);        // overlaps walk + fold + count
         if (ablate == 4u) continue;
 
-        // ================= walk: warp 0; warp 1 drains the previous tile's far links =================
+        // ================= walk: warp 0 the even records, warp 1 the previous tile's far links and the odd records =================
         // (a) One thread per record, no loop: the two ends of the path are shortened (REF:215-218); every other node keeps its
         //     whole length, so the record's sum of shares follows from the sum `ids` collected, and with it the one check the
         //     merge walk needs for a single-op record: a node with bases left but no cs left is an IndexError (REF:227).
         // (b) Records whose cs string has several ops, one at a time, one lane per step: prefix sum of the shares = the cs
         //     coordinate of every node (REF:205-255); a node inside one ':' / '=' op has one counting op like every node of a
         //     single-op record, the nodes an op boundary or a mismatch / indel falls into are listed for `fold`.
-        if (warp == 0) {
-            uint32_t n_heavy_w = 0;                                         // warp-uniform: entries of the fold list
-            for (uint32_t l0 = 0; l0 < n_lines; l0 += 32u) {
-                const uint32_t l = l0 + lane;
+        if (warp == 1) {
+            drain_far();
+            __syncwarp();
+            if (lane == 0) {
+                s_nfar = 0;
+                s_far_take = 0;
+                s_ndel = 0;
+            }
+        }
+        {
+            constexpr uint32_t HALF = (uint32_t)G::HEAVY_CAP / 2u;          // every warp lists into its own half
+            uint32_t n_heavy_w = 0;                                         // warp-uniform: entries of this warp's fold list
+            for (uint32_t l0 = 0; 2u * l0 < n_lines; l0 += 32u) {
+                const uint32_t l = 2u * (l0 + lane) + warp;
                 bool multi = false;
                 if (l < n_lines) {
                     Rec& R = recs[l];
@@ -913,7 +884,9 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
                         if (ns == 1u) { L0 -= R.end_rel1; L1 = L0; }
                         const uint32_t v0 = (uint32_t)(L0 <= 0 ? 0 : (L0 >= (int64_t)SL_BAD ? (int64_t)SL_BAD : L0));
                         const uint32_t v1 = (uint32_t)(L1 <= 0 ? 0 : (L1 >= (int64_t)SL_BAD ? (int64_t)SL_BAD : L1));
+                        // pairs of steps that `ids` could not compare by shuffle (the later one sits in lane 0 of its warp)
                         bool bad = v0 == SL_BAD || v1 == SL_BAD;
+                        for (uint32_t q = (s0 + 32u) & ~31u; q <= sl; q += 32u) bad |= sidx[q] == sidx[q - 1u];
                         // shares: v0, the interior nodes' whole lengths, v1; the last node with bases left starts at a_last
                         const uint32_t total = ns == 1u ? v0 : R.sum - raw0 - raw1 + v0 + v1;
                         uint32_t a_last = 0;
@@ -935,7 +908,7 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
                 // ---- (b) the multi-op records of this batch, one after the other, the warp's lanes on the record's steps
                 uint32_t todo = __ballot_sync(FULL, multi);
                 while (todo) {
-                    const uint32_t lr = l0 + (uint32_t)(__ffs((int)todo) - 1);
+                    const uint32_t lr = 2u * (l0 + (uint32_t)(__ffs((int)todo) - 1)) + warp;
                     todo &= todo - 1u;
                     Rec& R = recs[lr];
                     const uint32_t ns = R.nsteps, s0 = R.s0, n_tot = R.n_tot;
@@ -964,10 +937,10 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
                         const uint32_t bal = __ballot_sync(FULL, list);
                         if (list) {
                             const uint32_t h = n_heavy_w + (uint32_t)__popc(bal & lt_mask);
-                            if (h < (uint32_t)G::HEAVY_CAP) heavy[h] = (uint16_t)(s0 + k);
+                            if (h < HALF) heavy[warp * HALF + h] = (uint16_t)(s0 + k);
                         }
                         n_heavy_w += (uint32_t)__popc(bal);
-                        full |= n_heavy_w > (uint32_t)G::HEAVY_CAP;
+                        full |= n_heavy_w > HALF;
                     }
                     if (full && lane == 0) {                                // list full: exact path (nothing counted yet)
                         R.stB = ST_DEFER;
@@ -975,25 +948,17 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
                     }
                 }
             }
-            if (lane == 0) s_nheavy = n_heavy_w;
-        } else {
-            drain_far();
-            __syncwarp();
-            if (lane == 0) {
-                s_nfar = 0;
-                s_far_take = 0;
-                s_ndel = 0;
-            }
+            if (lane == 0) s_nheavy2[warp] = min(n_heavy_w, HALF);
         }
         if (active) far_base = base_off;                                    // the list `count` fills below belongs to this tile
         team_sync();                                                          // ---- B4: hand-over decisions of `walk`, prefix pool, heavy list
         if (ablate == 5u) continue;
 
         // ================= fold: every step of a multi-op record folds the cs ops that overlap its node =================
-        const uint32_t n_heavy = min(s_nheavy, (uint32_t)G::HEAVY_CAP);
+        const uint32_t nh0 = s_nheavy2[0], n_heavy = nh0 + s_nheavy2[1];
         {
             for (uint32_t h = tid; h < n_heavy; h += THREADS) {
-                const uint32_t s = heavy[h];
+                const uint32_t s = heavy[h < nh0 ? h : (uint32_t)G::HEAVY_CAP / 2u + (h - nh0)];
                 const uint32_t se = steps[s];
                 Rec& R = recs[(se >> SE_SLOT_SHIFT) & SE_SLOT_MASK];
                 if (rec_status(R) != ST_FAST) continue;

@@ -55,6 +55,8 @@ struct State {
     std::vector<Warp> warps;
     uint32_t live = 0, bar_arrived = 0, bar_gen = 0;
     uint32_t named_arrived[16] = {0}, named_gen[16] = {0};
+    uint64_t progress = 0;
+    std::vector<int> where;        // what every fibre is waiting in (1 block barrier, 2 shuffle, 100 + id named barrier): deadlock report
     int cur = -1;
     const std::function<void()>* body = nullptr;
 };
@@ -84,6 +86,7 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::
     s.bdim = {block, 1, 1};
     s.body = &body;
     if (s.fib.size() < block) s.fib.resize(block);
+    s.where.assign(block, 0);
     for (unsigned t = 0; t < block; t++)
         if (!s.fib[t].stack) s.fib[t].stack = (char*)malloc(STACK_BYTES);
     for (unsigned b = 0; b < grid; b++) {
@@ -105,15 +108,18 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::
         uint64_t idle_passes = 0;
         while (s.live > 0) {
             const uint32_t live_before = s.live, gen_before = s.bar_gen;
+            const uint64_t prog_before = s.progress;
             for (unsigned t = 0; t < block; t++) {
                 if (s.fib[t].done) continue;
                 s.cur = (int)t;
                 s.tidx = {t, 0, 0};
                 swapcontext(&s.sched, &s.fib[t].ctx);
             }
-            if (s.live == live_before && s.bar_gen == gen_before) {
+            if (s.live == live_before && s.bar_gen == gen_before && s.progress == prog_before) {
                 if (++idle_passes > 1000000) {
                     fprintf(stderr, "cuda_emu: deadlock (barrier / shuffle that not every thread reaches)\n");
+                    for (unsigned t = 0; t < block; t++)
+                        if (!s.fib[t].done) fprintf(stderr, "  thread %u waits in %d\n", t, s.where[t]);
                     abort();
                 }
             } else {
@@ -129,6 +135,7 @@ inline uint32_t shfl(uint32_t v, int src_lane) {
     Warp& w = s.warps[s.cur >> 5];
     const uint32_t lane = (uint32_t)s.cur & 31u;
     const uint32_t width = s.bdim.x - ((uint32_t)s.cur & ~31u) < 32u ? s.bdim.x - ((uint32_t)s.cur & ~31u) : 32u;
+    s.where[s.cur] = 2;
     w.val[lane] = v;
     w.arrived++;
     const uint32_t gen = w.gen;
@@ -153,6 +160,7 @@ inline uint32_t shfl(uint32_t v, int src_lane) {
 
 inline void __syncthreads() {
     emu::State& s = emu::S();
+    s.where[s.cur] = 1;
     s.bar_arrived++;
     const uint32_t gen = s.bar_gen;
     while (s.bar_gen == gen) {
@@ -167,13 +175,14 @@ inline void __syncthreads() {
 // bar.sync id, count: `count` threads of the block meet at named barrier `id` (1..15)
 inline void emu_named_barrier(unsigned id, unsigned count) {
     emu::State& s = emu::S();
+    s.where[s.cur] = 100 + (int)id;
     s.named_arrived[id]++;
     const uint32_t gen = s.named_gen[id];
     while (s.named_gen[id] == gen) {
         if (s.named_arrived[id] >= count) {
             s.named_arrived[id] = 0;
             s.named_gen[id]++;
-            s.bar_gen++;                     // (progress marker for the deadlock detector)
+            s.progress++;                    // (for the deadlock detector)
             break;
         }
         emu::yield();

@@ -104,6 +104,8 @@ int fastsim_run(const uint8_t* gaf, uint64_t nbytes, uint64_t file_off, int64_t 
     if (nbytes) memcpy(dev, gaf, nbytes);
     ChunkArgs A;
     memset(&A, 0, sizeof A);
+    A.loose = (geo + grid) & 1u;      // both barrier modes get exercised
+    if (getenv("FASTSIM_ABLATE")) A.ablate = (uint32_t)atoi(getenv("FASTSIM_ABLATE"));
     A.gaf = dev;
     A.nbytes = nbytes;
     A.file_off = (int64_t)file_off;
@@ -111,7 +113,7 @@ int fastsim_run(const uint8_t* gaf, uint64_t nbytes, uint64_t file_off, int64_t 
     if (nbytes) {
         typedef teamp::Geo<1024, 256, 96, 2, 1> G0;
         typedef teamp::Geo<4096, 512, 256, 3, 1> G1;
-        typedef teamp::Geo<8192, 1024, 512, 5, 2> G2;
+        typedef teamp::Geo<8192, 1024, 512, 10, 1> G2;
         if (geo == 0) run_fast<G0>(grid, A, T);
         else if (geo == 1) run_fast<G1>(grid, A, T);
         else run_fast<G2>(grid, A, T);
