@@ -121,14 +121,55 @@ int pt_export_side(pt_ctx* ctx, uint64_t* novel_dev, uint64_t novel_rows, uint64
 int pt_timer_start(pt_ctx* ctx);
 int pt_timer_stop(pt_ctx* ctx, float* ms);     /* synchronises on the stop event */
 
-/* Timing of the augment pass alone (augment_tiles_kernel + the second-pass
- * kernel for records with a non-trivial cs string): when enabled, every chunk
+/* Timing of the augment pass alone (augment_team_kernel + the exact per-record
+ * kernel for the records it hands over): when enabled, every chunk
  * records a CUDA event pair around those launches on the context's stream.  pt_kernel_time() synchronises and returns the summed
  * duration and the number of launches since the last call (then clears them). */
 int pt_profile_enable(pt_ctx* ctx, int on);
 int pt_kernel_time(pt_ctx* ctx, float* ms_total, uint64_t* launches);
 /* Same, split into the fast-path kernel and the exact per-record kernel (+ the chunk epilogue). */
 int pt_kernel_time_split(pt_ctx* ctx, float* ms_fast, float* ms_slow, uint64_t* launches);
+
+/* ---- The two GFA passes on the device.
+ * Replaces REF:121-126 (pass 1: nodes_info) and REF:377-424 (pass 2: the writer); the caller (pantas_b200/gfa_device.py)
+ * supplies the line index and does the prefix sums / key de-duplication with device-side index ops.
+ *
+ * pt_gfa_parse: one GFA line per thread.  start[i] / end[i] = byte range of line i's text (without its line break) in
+ * gfa_dev.  Outputs per line: a_rel / slen = the stripped text (str.strip()), kind = flags (1: raw line starts with 'S',
+ * 2: stripped line starts with 'S', 4: stripped line starts with 'L', bits 4..6: tokens of str.split(), capped at 4),
+ * v1 = token 1 as a canonical decimal id (0xFFFFFFFF: any other spelling), v2 = len(token 2) for S lines, token 3 as an id
+ * for L lines.  *err_dev (initialise to ~0) receives min(line << 8 | code): 1 S line with < 3 fields (reference:
+ * IndexError), 2 S id spelling not supported, 3 sequence of >= 2^30 bases. */
+int pt_gfa_parse(pt_ctx* ctx, const uint8_t* gfa_dev, const int64_t* start_dev, const int64_t* end_dev, uint64_t n_lines,
+                 uint32_t* a_rel_dev, uint32_t* slen_dev, uint32_t* kind_dev, uint32_t* v1_dev, uint32_t* v2_dev, uint64_t* err_dev);
+
+/* Inputs of the writer, all device pointers.  link_edge[i] = index (into the RC block of `sums`) of the count L line i
+ * prints, -1 if it prints 0 (REF:421: weights.pop -- only the first L line of a key gets the count).  sums = what
+ * pt_export_dense wrote (after the cross-rank reduction, if any).  Nodes with deletion-derived IL/OL keys print
+ * sp_text[sp_off[k] .. sp_off[k+1]) with k = sp_slot[idx] >= 0 (the caller orders those few by first-touch stamp). */
+typedef struct pt_gfa_writer {
+    const uint8_t* gfa;
+    const int64_t* start;
+    const uint32_t* a_rel;
+    const uint32_t* slen;
+    const uint32_t* kind;
+    const uint32_t* v1;
+    const int32_t* link_edge;
+    const uint32_t* node_len;
+    const int64_t* sums;
+    const int32_t* sp_slot;
+    const int64_t* sp_off;
+    const uint8_t* sp_text;
+    uint64_t n_nodes;
+    uint64_t n_lines;
+    uint32_t min_id;
+} pt_gfa_writer;
+
+/* out_len[i] = bytes line i prints (REF:377-424; 0 for dropped lines).  Errors in *err_dev: 4 stripped S line without an
+ * id (IndexError), 5 S id not in the node table (KeyError), 6 L line with < 4 fields (IndexError). */
+int pt_gfa_measure(pt_ctx* ctx, const pt_gfa_writer* w, int64_t* out_len_dev, uint64_t* err_dev);
+/* out_off = exclusive prefix sum of out_len; writes every line with its NC / IL / OL / RC tags at out_dev + out_off[i]. */
+int pt_gfa_format(pt_ctx* ctx, const pt_gfa_writer* w, const int64_t* out_off_dev, uint8_t* out_dev, uint64_t* err_dev);
 
 /* Counters for reports: kernel launches since create, records that took the
  * long-line path, tiles processed. */

@@ -41,7 +41,17 @@ SIGNATURES = {
     "pt_kernel_time_split": (ctypes.c_int, [c_ctx, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(u64)]),
     "pt_debug_counters": (ctypes.c_int, [c_ctx, ctypes.POINTER(u64), ctypes.c_int]),
     "pt_stats": (ctypes.c_int, [c_ctx, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(u64)]),
+    "pt_gfa_parse": (ctypes.c_int, [c_ctx, vp, vp, vp, u64, vp, vp, vp, vp, vp, vp]),
+    "pt_gfa_measure": (ctypes.c_int, [c_ctx, vp, vp, vp]),
+    "pt_gfa_format": (ctypes.c_int, [c_ctx, vp, vp, vp, vp]),
 }
+
+
+class GfaWriterArgs(ctypes.Structure):
+    """struct pt_gfa_writer of include/pantas_aug.h"""
+    _fields_ = [("gfa", vp), ("start", vp), ("a_rel", vp), ("slen", vp), ("kind", vp), ("v1", vp), ("link_edge", vp),
+                ("node_len", vp), ("sums", vp), ("sp_slot", vp), ("sp_off", vp), ("sp_text", vp),
+                ("n_nodes", u64), ("n_lines", u64), ("min_id", ctypes.c_uint32)]
 
 _lib = None
 

@@ -111,24 +111,14 @@ def main(argv, out=None, err=None) -> int:
     gfa_file = argv[1]
     thr = int(argv[2]) if len(argv) > 2 else 20           # REF:113
     world, rank, local_rank = _distributed_env()
-
-    print("Read GFA", file=err) if rank == 0 else None    # REF:120
-    graph = load_graph(gfa_file)
-    print("Augmentation by GAF alignments", file=err) if rank == 0 else None   # REF:134
+    host_passes = os.environ.get("PANTAS_GFA_PASSES", "device") == "host"     # the Python GFA passes of gfa.py (cross-check)
 
     from .engine import AugmentEngine
+    from .gfa_device import DeviceGfa
 
-    if world == 1:
-        eng = AugmentEngine(int(os.environ.get("PANTAS_DEVICE", "0")))
-        eng.set_graph(graph)
-        augment_file(graph, gaf_file, thr, engine=eng)
-        eng.check_data_error()
-        flat: FlatResult = eng.export()
-    else:
+    if world > 1:
         import torch
         import torch.distributed as dist
-
-        from .dist import ERR_NONE, allreduce_results, reduce_error
 
         # stdout carries the GFA and nothing else: NCCL prints its version banner on fd 1,
         # so park the real stdout and point fd 1 at stderr until the writer runs
@@ -141,29 +131,62 @@ def main(argv, out=None, err=None) -> int:
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         eng = AugmentEngine(local_rank)
+    else:
+        eng = AugmentEngine(int(os.environ.get("PANTAS_DEVICE", "0")))
+
+    print("Read GFA", file=err) if rank == 0 else None    # REF:120
+    dg = None
+    if host_passes:
+        graph = load_graph(gfa_file)
         eng.set_graph(graph)
-        b = shard_bounds(gaf_file, world)
-        augment_file(graph, gaf_file, thr, engine=eng, lo=b[rank], hi=b[rank + 1])
+    else:
+        dg = DeviceGfa.load(eng, gfa_file)                 # REF:121-126 on the device
+        dg.set_graph()
+        graph = dg.graph
+    print("Augmentation by GAF alignments", file=err) if rank == 0 else None   # REF:134
+
+    if world == 1:
+        augment_file(graph, gaf_file, thr, engine=eng)
+        eng.check_data_error()
+        sums, stamps, novel, sparse = eng.export_device()
+        novel_h = novel.cpu().numpy().view(np.uint64).reshape(-1, 3)
+        sparse_h = sparse.cpu().numpy().view(np.uint64).reshape(-1, 3)
+    else:
+        from .dist import ERR_HOST, ERR_NONE, reduce_error, reduce_results
+
+        # every rank reaches the collectives below, whatever happens to its own share of the GAF
         word = ERR_NONE
         try:
+            b = shard_bounds(gaf_file, world)
+            augment_file(graph, gaf_file, thr, engine=eng, lo=b[rank], hi=b[rank + 1])
             eng.check_data_error()
         except (PantasDataError, UnsupportedInput) as e:
-            word = (e.offset << 8) | e.code
+            word = ((e.offset or 0) << 8) | (e.code or ERR_HOST)
+        except Exception as e:                             # host-side failure on this rank only
+            print(f"rank {rank}: {type(e).__name__}: {e}", file=sys.stderr)
+            word = ERR_HOST
         word = reduce_error(word, eng.tdev)
         if word != ERR_NONE:
             code, off = word & 0xFF, word >> 8
+            if code == ERR_HOST:
+                raise RuntimeError("a rank failed on the host side (see its message above)")
             text = eng.lib.pt_strerror(code).decode()
             exc = PantasDataError if code < 20 else UnsupportedInput
             raise exc(f"GAF byte offset {off}: {text}", code, off)
         sums, stamps, novel, sparse = eng.export_device()
-        flat = allreduce_results(sums, stamps, novel, sparse, graph.n_nodes, graph.n_edges)
+        sums, stamps, novel_h, sparse_h = reduce_results(sums, stamps, novel, sparse, graph.n_nodes, dst=0)
         if rank != 0:
             return 0
 
-    counts = Counts.from_flat(flat)
-    print(f"Rejected alignments: {counts.rej}", file=err)  # REF:375
+    n, e = graph.n_nodes, graph.n_edges
+    rej = int(sums[3 * n + e].item())
+    print(f"Rejected alignments: {rej}", file=err)         # REF:375
     print("Annotating GFA", file=err)                      # REF:376
-    write_augmented(gfa_file, graph, counts, out)
+    if dg is not None:
+        dg.write(sums, stamps, novel_h, sparse_h, out)     # REF:377-427 on the device
+    else:
+        flat = FlatResult(n, e, sums.cpu().numpy(), stamps.cpu().numpy(), novel_h, sparse_h)
+        write_augmented(gfa_file, graph, Counts.from_flat(flat), out)
     out.flush()
     return 0
 
@@ -176,7 +199,9 @@ def cli(argv=None) -> int:
 
         cmd = [sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1",
                "--nnodes=1", f"--nproc-per-node={gpus}", "-m", "pantas_b200.augment"] + list(argv)
-        return subprocess.call(cmd)
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))      # the children import the package from any cwd
+        env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        return subprocess.call(cmd, env=env)
     return main(argv)
 
 

@@ -32,6 +32,7 @@
 namespace {
 
 #include "aug_kernels.cuh"
+#include "gfa_kernels.cuh"
 
 }  // namespace
 
@@ -651,6 +652,70 @@ int pt_debug_counters(pt_ctx* ctx, uint64_t* out, int n) {
     CK(cudaMemcpyAsync(sc, ctx->T.sc, sizeof sc, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (int k = 0; k < n; k++) out[k] = k < 16 ? sc[SC_WHY + k] : 0;      // 16 hand-over reasons
+    return 0;
+}
+
+// ---------------------------------------------------------------- the two GFA passes (gfa_kernels.cuh)
+
+int pt_gfa_parse(pt_ctx* ctx, const uint8_t* gfa_dev, const int64_t* start_dev, const int64_t* end_dev, uint64_t n_lines,
+                 uint32_t* a_rel_dev, uint32_t* slen_dev, uint32_t* kind_dev, uint32_t* v1_dev, uint32_t* v2_dev, uint64_t* err_dev) {
+    if (!ctx || !gfa_dev || !start_dev || !end_dev || !a_rel_dev || !slen_dev || !kind_dev || !v1_dev || !v2_dev || !err_dev)
+        return fail_msg(ctx, PT_ERR_ARG, "pt_gfa_parse: null argument");
+    CK(cudaSetDevice(ctx->device));
+    if (n_lines == 0) return 0;
+    gfa::LineArrays L;
+    L.start = (const long long*)start_dev;
+    L.end = (const long long*)end_dev;
+    L.a_rel = a_rel_dev;
+    L.slen = slen_dev;
+    L.kind = kind_dev;
+    L.v1 = v1_dev;
+    L.v2 = v2_dev;
+    gfa::gfa_parse_kernel<<<grid_for(n_lines, 256, ctx->sm_count * 16), 256, 0, ctx->stream>>>(gfa_dev, L, n_lines, (unsigned long long*)err_dev);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    return 0;
+}
+
+static gfa::WriterArgs writer_args(const pt_gfa_writer* w) {
+    gfa::WriterArgs W;
+    W.s = w->gfa;
+    W.start = (const long long*)w->start;
+    W.a_rel = w->a_rel;
+    W.slen = w->slen;
+    W.kind = w->kind;
+    W.v1 = w->v1;
+    W.link_edge = w->link_edge;
+    W.node_len = w->node_len;
+    W.sums = (const long long*)w->sums;
+    W.sp_slot = w->sp_slot;
+    W.sp_off = (const long long*)w->sp_off;
+    W.sp_text = w->sp_text;
+    W.n_nodes = w->n_nodes;
+    W.n_lines = w->n_lines;
+    W.min_id = w->min_id;
+    return W;
+}
+
+int pt_gfa_measure(pt_ctx* ctx, const pt_gfa_writer* w, int64_t* out_len_dev, uint64_t* err_dev) {
+    if (!ctx || !w || !out_len_dev || !err_dev) return fail_msg(ctx, PT_ERR_ARG, "pt_gfa_measure: null argument");
+    CK(cudaSetDevice(ctx->device));
+    if (w->n_lines == 0) return 0;
+    gfa::gfa_measure_kernel<<<grid_for(w->n_lines, 256, ctx->sm_count * 16), 256, 0, ctx->stream>>>(writer_args(w), (long long*)out_len_dev,
+                                                                                                  (unsigned long long*)err_dev);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    return 0;
+}
+
+int pt_gfa_format(pt_ctx* ctx, const pt_gfa_writer* w, const int64_t* out_off_dev, uint8_t* out_dev, uint64_t* err_dev) {
+    if (!ctx || !w || !out_off_dev || !out_dev || !err_dev) return fail_msg(ctx, PT_ERR_ARG, "pt_gfa_format: null argument");
+    CK(cudaSetDevice(ctx->device));
+    if (w->n_lines == 0) return 0;
+    gfa::gfa_format_kernel<<<grid_for(w->n_lines, 256, ctx->sm_count * 16), 256, 0, ctx->stream>>>(writer_args(w), (const long long*)out_off_dev, out_dev,
+                                                                                                 (unsigned long long*)err_dev);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
     return 0;
 }
 

@@ -13,6 +13,7 @@ import numpy as np
 from .counts import FlatResult, merge_side
 
 ERR_NONE = (1 << 63) - 1
+ERR_HOST = 255          # error word code: a rank failed on the host side (no device error code)
 
 
 def reduce_error(err_word: int, device, group=None) -> int:
@@ -51,3 +52,49 @@ def allreduce_results(sums, stamps, novel, sparse, n_nodes: int, n_edges: int, g
 
     return FlatResult(n_nodes, n_edges, sums.cpu().numpy(), stamps.cpu().numpy(),
                       gather_rows(novel), gather_rows(sparse))
+
+
+def gather_side(rows, group=None) -> np.ndarray:
+    """All ranks' {key, count, stamp} rows, merged by key (counts add, stamps take the minimum), on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rows = rows.reshape(-1, 3).contiguous()
+    n = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(max(sizes), 1)
+    pad = torch.zeros((m, 3), dtype=rows.dtype, device=rows.device)
+    pad[: rows.shape[0]] = rows
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    parts = [b[:s].cpu().numpy().view(np.uint64).reshape(-1, 3) for b, s in zip(bufs, sizes)]
+    return merge_side(parts)
+
+
+def reduce_results(sums, stamps, novel, sparse, n_nodes: int, dst: int = 0, group=None):
+    """The one-shot reduction that ends a multi-GPU job, to rank `dst` only (it alone writes the GFA):
+
+    * the two small side tables are gathered and merged first;
+    * ``reduce(SUM)`` of the counter buffer (not all_reduce: nobody else needs it);
+    * first-touch stamps are only ever read for nodes that also have a deletion-derived key (the writer orders a
+      node's IL / OL entries by them), so only those nodes' stamps are reduced (MIN) -- a few thousand values instead
+      of 2 x n_nodes.
+
+    -> (sums, stamps, novel rows, sparse rows); sums / stamps are valid on `dst` only."""
+    import torch
+    import torch.distributed as dist
+
+    novel_h = gather_side(novel, group)
+    sparse_h = gather_side(sparse, group)
+    dist.reduce(sums, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    if sparse_h.shape[0]:
+        nodes = np.unique((sparse_h[:, 0] >> np.uint64(32)).astype(np.int64))      # the same list on every rank
+        idx = torch.from_numpy(np.concatenate([nodes, nodes + n_nodes])).to(stamps.device)
+        sub = stamps[idx].contiguous()
+        dist.reduce(sub, dst=dst, op=dist.ReduceOp.MIN, group=group)
+        if dist.get_rank(group) == dst:
+            stamps[idx] = sub
+    return sums, stamps, novel_h, sparse_h

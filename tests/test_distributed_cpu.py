@@ -20,12 +20,13 @@ from oracle.oracle import run_oracle
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, gfa_path, gaf_path, out_path):
+def _worker(rank, world, port, gfa_path, gaf_path, out_path, to_root=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from hostsim_util import run_hostsim
     from pantas_b200.counts import Counts
-    from pantas_b200.dist import ERR_NONE, allreduce_results, reduce_error
+    from pantas_b200.counts import FlatResult
+    from pantas_b200.dist import ERR_NONE, allreduce_results, reduce_error, reduce_results
     from pantas_b200.gfa import load_graph, write_augmented
     from pantas_b200.shard import shard_bounds
 
@@ -46,9 +47,13 @@ def _worker(rank, world, port, gfa_path, gaf_path, out_path):
                 f.write(b"ERROR %d" % (word & 0xFF))
         dist.destroy_process_group()
         return
-    res = allreduce_results(torch.from_numpy(flat.sums), torch.from_numpy(flat.stamps),
-                            torch.from_numpy(flat.novel.view(np.int64)), torch.from_numpy(flat.sparse.view(np.int64)),
-                            graph.n_nodes, graph.n_edges)
+    args = (torch.from_numpy(flat.sums), torch.from_numpy(flat.stamps), torch.from_numpy(flat.novel.view(np.int64)),
+            torch.from_numpy(flat.sparse.view(np.int64)))
+    if to_root:        # the product's reduction: to rank 0 only, stamps only where the writer reads them
+        sums, stamps, novel, sparse = reduce_results(*args, graph.n_nodes, dst=0)
+        res = FlatResult(graph.n_nodes, graph.n_edges, sums.numpy(), stamps.numpy(), novel, sparse)
+    else:
+        res = allreduce_results(*args, graph.n_nodes, graph.n_edges)
     if rank == 0:
         out = io.StringIO()
         c = Counts.from_flat(res)
@@ -58,8 +63,8 @@ def _worker(rank, world, port, gfa_path, gaf_path, out_path):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("seed,world", [(8101, 2), (8102, 2), (8103, 3)])
-def test_sharded_reduction_matches_single_run(seed, world, tmp_path):
+@pytest.mark.parametrize("seed,world,to_root", [(8101, 2, False), (8102, 2, True), (8103, 3, True), (8104, 2, True)])
+def test_sharded_reduction_matches_single_run(seed, world, to_root, tmp_path):
     gfa, gaf = fuzzgen.make_case(seed, n_nodes=25, n_reads=300, weird=True)
     want = run_oracle(gaf.encode(), gfa.encode())
     assert want.rc == 0
@@ -67,7 +72,7 @@ def test_sharded_reduction_matches_single_run(seed, world, tmp_path):
     gp.write_bytes(gfa.encode())
     ap.write_bytes(gaf.encode())
     port = 29500 + (os.getpid() + seed) % 2000
-    mp.spawn(_worker, args=(world, port, str(gp), str(ap), str(op)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(gp), str(ap), str(op), to_root), nprocs=world, join=True)
     got = op.read_bytes()
     assert got == want.out + b"\nREJ %d" % want.rej
 

@@ -75,6 +75,44 @@ def gpu_pipeline(tmp_path, gfa: str, gaf: str, thr=20, eng=None, via_host=False,
     return ("ok", out.getvalue().encode(), counts.rej)
 
 
+def gpu_pipeline_device_gfa(gfa: str, gaf: str, thr=20, eng=None):
+    """The same with BOTH GFA passes on the device (pantas_b200/gfa_device.py): what the CLI runs."""
+    import torch
+
+    from pantas_b200.errors import PantasDataError, UnsupportedInput
+    from pantas_b200.gfa_device import DeviceGfa
+
+    eng = eng or _engine()
+    try:
+        dg = DeviceGfa.load_bytes(eng, gfa.encode())
+    except PantasDataError:
+        return ("raise", 0)
+    except UnsupportedInput as e:
+        return ("unsupported", e.code)
+    dg.set_graph()
+    data = np.frombuffer(gaf.encode(), dtype=np.uint8)
+    n = int(data.size)
+    d = torch.zeros(n + 16, dtype=torch.uint8, device="cuda")
+    if n:
+        d[:n] = torch.from_numpy(data.copy()).cuda()
+    eng.process_device(d, n, 0, thr)
+    try:
+        eng.check_data_error()
+    except PantasDataError as e:
+        return ("raise", e.code)
+    except UnsupportedInput as e:
+        return ("unsupported", e.code)
+    sums, stamps, novel, sparse = eng.export_device()
+    g = dg.graph
+    rej = int(sums[3 * g.n_nodes + g.n_edges].item())
+    try:
+        host = dg.render(sums, stamps, novel.cpu().numpy().view(np.uint64).reshape(-1, 3),
+                         sparse.cpu().numpy().view(np.uint64).reshape(-1, 3))
+    except PantasDataError:
+        return ("raise", 0)
+    return ("ok", host.numpy().tobytes(), rej)
+
+
 def check_golden(case, res):
     if case["name"] in UNSUPPORTED_BY_DESIGN:
         assert res[0] == "unsupported", (case["name"], res)
@@ -98,6 +136,62 @@ def test_golden_cases_device_buffers(tmp_path):
     for case in GOLDEN:
         thr = 20 if case["thr"] is None else case["thr"]
         check_golden(case, gpu_pipeline(tmp_path, case["gfa"], case["gaf"], thr, eng=eng))
+
+
+def test_golden_cases_device_gfa_passes():
+    """GFA pass 1 and the writer on the device (REF:121-126, 377-427): same bytes, same failures."""
+    eng = _engine()
+    for case in GOLDEN:
+        thr = 20 if case["thr"] is None else case["thr"]
+        check_golden(case, gpu_pipeline_device_gfa(case["gfa"], case["gaf"], thr, eng=eng))
+
+
+@pytest.mark.parametrize("seed", range(9200, 9212))
+def test_fuzz_device_gfa_passes_vs_oracle(seed):
+    gfa, gaf = fuzzgen.make_case(seed, n_nodes=10 + seed % 40, n_reads=300, weird=(seed % 2 == 0), crlf=(seed % 6 == 0),
+                                 trailing_newline=(seed % 4 != 0))
+    orc = run_oracle(gaf.encode(), gfa.encode())
+    assert orc.rc == 0
+    res = gpu_pipeline_device_gfa(gfa, gaf, eng=_engine(PANTAS_TEAM_TILE=[8192, 1024, 8193][seed % 3]))
+    assert res[0] == "ok", res
+    assert res[1] == orc.out
+    assert res[2] == orc.rej
+
+
+@pytest.mark.parametrize("preset,pairs,seed", [("dm-full", 1_000_000, 1002), ("hs-chr1", 500_000, 1003), ("gene-panel", 1_000_000, 1005)])
+def test_bench_scale_graphs_byte_identical_to_the_oracle(preset, pairs, seed, tmp_path):
+    """The graphs the bench and the scaling runs use, at 1-2 M alignments: the augmented GFA (every NC / IL / OL / RC tag
+    of millions of S and L lines, novel links in first-seen order) is byte-identical to the CPU oracle's."""
+    import torch
+
+    from pantas_b200.gfa_device import DeviceGfa
+    from pantas_b200.synth import SynthGraph
+
+    sg = SynthGraph(preset, seed=seed)
+    gp = tmp_path / "g.gfa"
+    sg.write_gfa(str(gp))
+    gaf, n_lines = sg.gaf(pairs, first_pair=0)
+    gfa_bytes = gp.read_bytes()
+    want = run_oracle(gaf, gfa_bytes)
+    assert want.rc == 0, want.err
+    eng = _engine()
+    dg = DeviceGfa.load(eng, str(gp))
+    dg.set_graph()
+    n = int(gaf.shape[0])
+    d = torch.zeros(n + 32, dtype=torch.uint8, device="cuda")
+    d[:n] = torch.from_numpy(gaf).cuda()
+    eng.process_device(d, n, 0, 20)
+    eng.check_data_error()
+    sums, stamps, novel, sparse = eng.export_device()
+    g = dg.graph
+    assert int(sums[3 * g.n_nodes + g.n_edges].item()) == want.rej
+    assert int(sums[3 * g.n_nodes + g.n_edges + 1].item()) == n_lines == want.n_lines
+    host = dg.render(sums, stamps, novel.cpu().numpy().view(np.uint64).reshape(-1, 3), sparse.cpu().numpy().view(np.uint64).reshape(-1, 3))
+    got = host.numpy()
+    ref = np.frombuffer(want.out, dtype=np.uint8)
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref)
+    assert eng.stats()["deferred_lines"] < 0.02 * n_lines
 
 
 def test_golden_cases_host_buffers(tmp_path):
