@@ -1,24 +1,25 @@
 #!/usr/bin/env python3
 """bench.py -- pantas `augment` hot path on B200: alignments/s and GAF GB/s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A step = one pass of the hot path (GAF records -> NC/RC/IL/OL counters) over one
-synthetic GAF.  At N=1 the workload is BASELINE.json configs[1]: a 10 M-alignment
-GAF over the dm-full synthetic annotated spliced pangenome (no `vg` exists here,
-so graph and reads come from pantas_b200/synth).  At N>1
-each rank parses its own 10 M-alignment byte range of an N x 10 M GAF (weak
-scaling) and the step ends with the one-shot NCCL reduction of the counters.
+A step = one pass of the hot path (GAF records -> NC/RC/IL/OL counters, exported in the C-ABI layout) over one synthetic
+GAF.  At N=1 the workload is BASELINE.json configs[1]: a 10 M-alignment GAF over the dm-full synthetic annotated spliced
+pangenome (no `vg` exists here, so graph and reads come from pantas_b200/synth).  At N>1 each rank
+parses its own 10 M-alignment byte range of an N x 10 M GAF (weak scaling) and the step ends with the one-shot NCCL
+reduction of the counters to rank 0.
 
-  value     alignments/s, whole job, GAF already resident in HBM
-  e2e       same through the host-buffer C-ABI call: pinned host GAF -> H2D ->
-            kernels -> export -> D2H of the reduced counters
-  roofline  augment_team_kernel: GAF bytes parsed / kernel time vs measured HBM copy peak
-  cpu_baseline  the CPU oracle port (oracle/augment_oracle.c) on a bounded sample, 1 core
-`--impl reference` times that CPU port on all host cores instead (the reference
-itself is pure Python and is not present on the GPU box; its measured speed in
-the build container is in BASELINE.md).
+  value         alignments/s, whole job, GAF already resident in HBM (kernels + fold + export [+ reduction])
+  e2e           same through the host-buffer C-ABI call: pinned host GAF -> H2D -> kernels -> export [-> reduction] -> D2H
+  roofline      augment_team_kernel: GAF bytes parsed / kernel time (CUDA events around the kernel) vs measured HBM copy peak
+  parity_checked  the augmented GFA of a prefix of the benchmarked GAF (both GFA passes on the device) is byte-identical
+                  to the CPU oracle's; at N>1: every rank's prefix, reduced, against one oracle run
+  cpu_baseline  the reference script itself (oracle/_ref, 1 core: it is single-threaded) on a bounded sample, with the
+                C port of it (oracle/augment_oracle.c, 1 core) beside it
+  cli           wall time of the drop-in script, file -> stdout, with the GFA passes on the device and in Python
+`--impl reference` times the C port of the reference's loop on all host cores (one shared parse of the GFA, every thread
+its own byte range of a bounded sample) and, when oracle/_ref holds it, the reference script on one core.
 """
 from __future__ import annotations
 
@@ -27,6 +28,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -41,6 +43,7 @@ WORKLOADS = {
     "dm-full-10M": ("dm-full", 5_000_000, 1002),
     "dm-chr4-1M": ("dm-chr4", 500_000, 1001),
     "hs-chr1-10M": ("hs-chr1", 5_000_000, 1003),
+    "hs-chr1-100M-strong": ("hs-chr1", 50_000_000, 1003),       # BASELINE.json configs[2]: 100 M alignments in total, split over the ranks
     "gene-panel-10M": ("gene-panel", 5_000_000, 1005),
     "tiny-20k": ("tiny", 10_000, 7),
 }
@@ -53,16 +56,34 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("PANTAS_BENCH_WORKLOAD", "dm-full-10M"), choices=list(WORKLOADS))
-    ap.add_argument("--cpu-sample-lines", type=int, default=2_000_000)
+    ap.add_argument("--cpu-sample-lines", type=int, default=1_500_000, help="records of the C-port baseline / parity prefix")
+    ap.add_argument("--ref-sample-lines", type=int, default=120_000, help="records the reference script itself is timed on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cli", action="store_true", help="skip the drop-in script wall-time measurement")
+    ap.add_argument("--no-parity", action="store_true")
     return ap.parse_args()
+
+
+def config_of(workload: str, world: int, n_nodes=None, n_links=None, n_lines=None, nbytes=None):
+    """The `config` object: the same keys in both arms."""
+    preset, pairs, seed = WORKLOADS[workload]
+    strong = workload.endswith("-strong")
+    per_gpu = 2 * (pairs // world if strong else pairs)
+    c = {"workload": workload, "graph": preset, "seed": seed, "alignments_per_gpu": per_gpu, "partition": f"byte-range x{world}",
+         "l2": "input (GAF bytes per GPU) is larger than L2; no flush needed",
+         "timing": "per-step CUDA events on the launching stream; counter reset outside the events"}
+    if n_nodes is not None:
+        c.update({"graph_nodes": n_nodes, "graph_links": n_links})
+    if nbytes is not None:
+        c.update({"gaf_bytes_per_gpu": nbytes, "bytes_per_alignment": nbytes / max(n_lines, 1)})
+    return c
 
 
 def measured_traffic(workload: str):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload, or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_roofline_traffic.json")) as f:
             d = json.load(f)
         if d.get("workload") == workload:
             return int(d["dram_bytes_read_per_launch"]) + int(d["dram_bytes_write_per_launch"])
@@ -88,7 +109,6 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.rows = []
         self.proc = None
-        self.gpu = gpu_index
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -129,96 +149,127 @@ class ClockSampler:
             self.proc.terminate()
 
 
-def make_inputs(workload: str, rank: int, world: int):
-    """-> (SynthGraph, pinned uint8 torch tensor with this rank's shard, nbytes, n_lines)"""
-    import torch
-
+def make_inputs(workload: str, rank: int, world: int, pinned: bool = True):
+    """-> (SynthGraph, uint8 GAF of this rank's shard (pinned torch tensor or numpy), nbytes, n_lines)"""
     from pantas_b200.synth import SynthGraph
 
     preset, pairs, seed = WORKLOADS[workload]
+    if workload.endswith("-strong"):
+        pairs //= world
     sg = SynthGraph(preset, seed=seed)
     buf, n_lines = sg.gaf(pairs, first_pair=rank * pairs, threads=max(1, (os.cpu_count() or 8) // max(world, 1)))
     n = int(buf.shape[0])
-    pinned = torch.empty(n + 64, dtype=torch.uint8).pin_memory()
-    pinned[:n] = torch.from_numpy(buf)
-    return sg, pinned, n, n_lines
+    if not pinned:
+        return sg, buf, n, n_lines
+    import torch
+
+    t = torch.empty(n + 64, dtype=torch.uint8).pin_memory()
+    t[:n] = torch.from_numpy(buf)
+    return sg, t, n, n_lines
 
 
-def cpu_baseline(sg, gaf_np: np.ndarray, n_lines_target: int, threads: int):
-    """Time the CPU oracle's GAF loop (REF:138-371 restated in C) on the first ~n_lines_target lines."""
-    import tempfile
-
-    from oracle.oracle import run_oracle
-    from pantas_b200.shard import shard_bounds_bytes
-
-    # cut the sample at a line boundary
-    approx = min(gaf_np.shape[0], int(n_lines_target * 270))
+def cut_lines(gaf_np: np.ndarray, n_lines_target: int):
+    """(end byte, lines) of the longest prefix with at most n_lines_target records."""
+    approx = min(gaf_np.shape[0], int(n_lines_target * 400) + 4096)
     nl = np.flatnonzero(gaf_np[:approx] == 10)
     if nl.size == 0:
-        return None
-    if nl.size > n_lines_target:
-        end = int(nl[n_lines_target - 1]) + 1
-        lines = n_lines_target
-    else:
-        end = int(nl[-1]) + 1
-        lines = int(nl.size)
-    sample = gaf_np[:end]
-    with tempfile.TemporaryDirectory() as d:
-        gp = os.path.join(d, "g.gfa")
-        sg.write_gfa(gp)
-        with open(gp, "rb") as f:
-            gfa = f.read()
+        return 0, 0
+    k = min(n_lines_target, int(nl.size))
+    return int(nl[k - 1]) + 1, k
+
+
+def port_loop(og, sample: np.ndarray, threads: int):
+    """The C port's GAF loop (REF:138-371) over `sample`, sharded over `threads` host threads at line boundaries, against one
+    shared parse of the GFA.  -> (max loop seconds over the threads, rejected)"""
+    from pantas_b200.shard import shard_bounds_bytes
+
     bounds = shard_bounds_bytes(sample, threads)
     results = [None] * threads
 
     def work(k):
-        results[k] = run_oracle(sample[bounds[k]:bounds[k + 1]], gfa, 20, write_output=False)
+        results[k] = og.run(sample[bounds[k]:bounds[k + 1]], 20, write_output=False)
 
-    t0 = time.time()
     ths = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
     for t in ths:
         t.start()
     for t in ths:
         t.join()
-    wall = time.time() - t0
     assert all(r.rc == 0 for r in results), [r.err for r in results]
-    secs = max(r.gaf_seconds for r in results)          # GAF loop only; GFA load excluded
-    return {"lines": lines, "bytes": end, "gaf_loop_s": secs, "wall_s": wall,
-            "rej": sum(r.rej for r in results)}
+    return max(r.gaf_seconds for r in results), sum(r.rej for r in results)
+
+
+def reference_script_time(gfa_path: str, gaf_np: np.ndarray, n_lines: int):
+    """The reference script itself (1 core: it has no parallelism) on the first n_lines records; the GFA passes are
+    timed apart with an empty GAF, so that the figure is the GAF loop like everything else here."""
+    from oracle.oracle import reference_script
+
+    script = reference_script()
+    if script is None:
+        return None
+    end, lines = cut_lines(gaf_np, n_lines)
+    if lines == 0:
+        return None
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
+        ap, ep = os.path.join(d, "a.gaf"), os.path.join(d, "empty.gaf")
+        gaf_np[:end].tofile(ap)
+        open(ep, "wb").close()
+
+        def run(gaf):
+            t0 = time.time()
+            p = subprocess.run([sys.executable, "-W", "ignore", script, gaf, gfa_path], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+            assert p.returncode == 0, p.stderr.decode()[-500:]
+            return time.time() - t0
+
+        t_empty = run(ep)
+        t_full = run(ap)
+    loop_s = max(t_full - t_empty, 1e-9)
+    return {"lines": lines, "bytes": end, "gaf_loop_s": loop_s, "gfa_passes_s": t_empty, "wall_s": t_full}
 
 
 def run_reference_arm(args):
-    """CPU port of the reference's augment loop on all host cores; rank 0 only."""
+    """The reference's CPU implementation of the path on the box's host cores; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    from pantas_b200.synth import SynthGraph
+    from oracle.oracle import OracleGraph
 
-    preset, pairs, seed = WORKLOADS[args.workload]
-    sg = SynthGraph(preset, seed=seed)
     cores = os.cpu_count() or 1
-    per_step_pairs = max(10_000, min(pairs, args.cpu_sample_lines * cores // 2 // 2))
-    buf, n_lines = sg.gaf(per_step_pairs, first_pair=0, threads=cores)
+    sg, buf, nbytes, n_lines = make_inputs(args.workload, 0, world, pinned=False)
+    with tempfile.TemporaryDirectory() as d:
+        gp = os.path.join(d, "g.gfa")
+        sg.write_gfa(gp)
+        with open(gp, "rb") as f:
+            gfa = f.read()
+        ref = None if args.no_cpu_baseline else reference_script_time(gp, buf, args.ref_sample_lines)
+    og = OracleGraph(gfa)                                     # ONE parse of the GFA, shared by every thread and step
+    assert og.rc == 0, og.err
+    per_step = max(20_000, min(n_lines, 100_000 * cores))     # a bounded sample: ~0.3 s of loop per step and core
+    end, lines = cut_lines(buf, per_step)
+    sample = buf[:end]
     times = []
-    res = None
     for i in range(args.warmup + args.steps):
-        res = cpu_baseline(sg, buf, n_lines, cores)
+        secs, _ = port_loop(og, sample, cores)
         if i >= args.warmup:
-            times.append(res["gaf_loop_s"])
+            times.append(secs)
+    og.close()
     t = float(np.mean(times))
-    value = res["lines"] / t
-    sample = (f"first {res['lines']} records of the {args.workload} GAF per step, sharded over {cores} threads at line "
-              "boundaries (GAF loop only; GFA load/write and the cross-shard merge excluded)")
+    value = lines / t
+    cfg = config_of(args.workload, world, sg.n_nodes, sg.n_links, n_lines, nbytes)
+    sample_txt = (f"first {lines} records of the {args.workload} GAF per step, byte-range sharded over {cores} host threads "
+                  "(C port of the reference's loop, one shared GFA parse; GAF loop only, cross-shard merge excluded)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "alignments/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": args.workload, "note": "CPU oracle port of the Python reference (reference itself is "
-                   "not on the GPU box; BASELINE.md has its measured speed)"},
-        "gaf_gb_per_s": res["bytes"] / t / 1e9,
-        "cpu_baseline": {"value": value, "unit": "alignments/s", "cores": cores, "kind": "port", "sample": sample},
+        "scaling": "strong" if args.workload.endswith("-strong") else "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": cfg, "gaf_gb_per_s": end / t / 1e9,
+        "cpu_baseline": {"value": value, "unit": "alignments/s", "cores": cores, "kind": "port", "sample": sample_txt},
         "e2e": {"value": value, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if ref:
+        line["reference_script"] = {"value": ref["lines"] / ref["gaf_loop_s"], "unit": "alignments/s", "cores": 1, "kind": "reference",
+                                    "sample": f"the unmodified reference script (oracle/_ref) on the first {ref['lines']} records, 1 core; "
+                                              f"GAF loop {ref['gaf_loop_s']:.1f} s, its two GFA passes {ref['gfa_passes_s']:.1f} s"}
     print(json.dumps(line))
 
 
@@ -242,14 +293,24 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
 
+    from pantas_b200.dist import reduce_results
     from pantas_b200.engine import AugmentEngine
+    from pantas_b200.gfa_device import DeviceGfa
 
     K, W = args.steps, max(args.warmup, 3)
     sg, pinned, nbytes, n_lines = make_inputs(args.workload, rank, world)
-    graph = sg.graph()
+    tmp = tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    gfa_path = os.path.join(tmp.name, f"g{rank}.gfa")
+    sg.write_gfa(gfa_path)
     eng = AugmentEngine(local_rank)
-    eng.set_graph(graph)
+    t0 = time.perf_counter()
+    dg = DeviceGfa.load(eng, gfa_path)                        # GFA pass 1 on the device (REF:121-126)
+    dg.set_graph()
+    torch.cuda.synchronize()
+    gfa_load_ms = 1e3 * (time.perf_counter() - t0)
+    graph = dg.graph
     eng.profile(True)
+    n, e = graph.n_nodes, graph.n_edges
 
     # global file offset of this rank's shard
     file_off = 0
@@ -257,29 +318,39 @@ def main():
         sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
         dist.all_gather(sizes, torch.tensor([nbytes], dtype=torch.int64, device=dev))
         file_off = int(sum(int(s.item()) for s in sizes[:rank]))
-        total_lines_t = torch.tensor([n_lines, nbytes], dtype=torch.int64, device=dev)
-        dist.all_reduce(total_lines_t)
-        total_lines, total_bytes = int(total_lines_t[0].item()), int(total_lines_t[1].item())
+        tot = torch.tensor([n_lines, nbytes], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot)
+        total_lines, total_bytes = int(tot[0].item()), int(tot[1].item())
     else:
         total_lines, total_bytes = n_lines, nbytes
 
     gaf_dev = torch.empty(((nbytes + 15) // 16) * 16 + 16, dtype=torch.uint8, device=dev)
     gaf_dev[:nbytes].copy_(pinned[:nbytes], non_blocking=True)
     torch.cuda.synchronize()
-    n, e = graph.n_nodes, graph.n_edges
 
-    def reduce_step():
-        """the one-shot counter reduction that ends a multi-GPU job"""
+    def finish_step():
+        """fold + export in the C-ABI layout, then (N > 1) the one-shot reduction to rank 0"""
         sums, stamps, novel, sparse = eng.export_device()
         if world > 1:
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-            dist.all_reduce(stamps, op=dist.ReduceOp.MIN)
+            return reduce_results(sums, stamps, novel, sparse, n, dst=0)
         return sums, stamps, novel, sparse
 
+    # chunks of at most 3 GiB (one launch each; pt_process_chunk takes < 3.75 GiB), cut at line ends
+    chunks = []
+    view_all = pinned.numpy()
+    pos = 0
+    while pos < nbytes:
+        end = min(pos + (3 << 30), nbytes)
+        if end < nbytes:
+            w = view_all[end - (1 << 16):end]
+            end = end - (1 << 16) + int(np.flatnonzero(w == 10)[-1]) + 1
+        chunks.append((pos, end))
+        pos = end
+
     def device_step():
-        eng.process_device(gaf_dev, nbytes, file_off, 20)
-        if world > 1:
-            reduce_step()
+        for a, b in chunks:
+            eng.process_device(gaf_dev[a:], b - a, file_off + a, 20)
+        return finish_step()
 
     pinned_out = {}
 
@@ -305,13 +376,17 @@ def main():
                 end = max(pos, end - (1 << 16)) + int(nlp[-1]) + 1
             eng.process_host(base + pos, end - pos, file_off + pos, 20)
             pos = end
-        if world > 1:
-            out = reduce_step()
-            out = tuple(pin_out(k, t) for k, t in enumerate(out))           # D2H of the step's (reduced) result
-            torch.cuda.synchronize()
-        else:
-            out = eng.export_host()                                         # D2H of the step's result, pinned host buffers
-        return sum(t.numel() * t.element_size() for t in out)
+        out = finish_step()
+        d2h = 0
+        if rank == 0:                                          # D2H of the step's (reduced) result into pinned host buffers
+            for k, t in enumerate(out):
+                if isinstance(t, torch.Tensor):
+                    pin_out(k, t)
+                    d2h += t.numel() * t.element_size()
+                else:
+                    d2h += t.nbytes                            # (side rows: already on the host)
+        torch.cuda.synchronize()
+        return d2h
 
     def barrier():
         if world > 1:
@@ -348,7 +423,7 @@ def main():
     barrier()
     t_wall1 = time.time()
     kern_ms, slow_ms, kern_n = eng.kernel_time_split()                # the fast-path kernel alone / the per-record kernel
-    launches = eng.stats()["kernel_launches"] - launches0 - 4 * K      # minus the reset kernels
+    launches = eng.stats()["kernel_launches"] - launches0 - 5 * K      # minus the reset kernels
     step_ms = float(np.mean(ms))
     if world > 1:
         t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
@@ -370,7 +445,6 @@ def main():
             barrier()
             t0 = time.perf_counter()
             d2h = host_step()
-            torch.cuda.synchronize()
             ms2.append(1e3 * (time.perf_counter() - t0))
         e2e_ms = float(np.mean(ms2))
         if world > 1:
@@ -378,31 +452,77 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms = float(t.item())
         e2e = {"value": total_lines / (e2e_ms / 1e3), "unit": "alignments/s", "h2d_bytes_per_step": int(nbytes),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "gaf_gb_per_s": total_bytes / e2e_ms / 1e6}
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "gaf_gb_per_s": total_bytes / e2e_ms / 1e6,
+               "h2d_gb_per_s_aggregate": total_bytes / e2e_ms / 1e6}
         eng.check_data_error()
     clocks = sampler.window(t_wall0, t_wall1) if sampler else None
     if sampler:
         sampler.stop()
 
+    # ---- parity of what was just timed: a prefix of this rank's GAF, reduced over the ranks, against the CPU oracle
+    parity = None
+    if not args.no_parity:
+        from oracle.oracle import OracleGraph
+
+        pre_lines = args.cpu_sample_lines if world == 1 else 200_000
+        end, lines = cut_lines(pinned.numpy()[:nbytes], pre_lines)
+        pre_off = 0
+        if world > 1:
+            sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+            dist.all_gather(sizes, torch.tensor([end], dtype=torch.int64, device=dev))
+            sizes = [int(s.item()) for s in sizes]
+            pre_off = sum(sizes[:rank])
+        eng.reset()
+        eng.process_device(gaf_dev, end, pre_off, 20)
+        eng.check_data_error()
+        sums, stamps, novel, sparse = finish_step()
+        if world > 1:
+            m = max(sizes)
+            mine = torch.zeros(m, dtype=torch.uint8, device=dev)
+            mine[:end] = gaf_dev[:end]
+            parts = [torch.empty(m, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+            dist.gather(mine, parts, dst=0)
+            novel_h, sparse_h = novel, sparse
+            if rank == 0:
+                prefix = np.concatenate([p[:s].cpu().numpy() for p, s in zip(parts, sizes)])
+        else:
+            prefix = pinned.numpy()[:end]
+            novel_h = novel.cpu().numpy().view(np.uint64).reshape(-1, 3)
+            sparse_h = sparse.cpu().numpy().view(np.uint64).reshape(-1, 3)
+        if rank == 0:
+            got = dg.render(sums, stamps, novel_h, sparse_h).numpy()
+            with open(gfa_path, "rb") as f:
+                og = OracleGraph(f.read())
+            want = og.run(prefix, 20, write_output=True)
+            og.close()
+            assert want.rc == 0, want.err
+            ref = np.frombuffer(want.out, dtype=np.uint8)
+            same = got.shape == ref.shape and bool(np.array_equal(got, ref))
+            parity = {"checked": same, "records": int(want.n_lines), "gfa_bytes": int(ref.shape[0]), "rejected": int(want.rej),
+                      "what": "augmented GFA (GFA passes on the device) of a prefix of every rank's GAF, reduced to rank 0, "
+                              "byte-compared with the CPU oracle (oracle/augment_oracle.c)"}
+            assert same, "PARITY FAILURE: the benchmarked path does not reproduce the oracle's GFA"
+            port_secs = want.gaf_seconds
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         kern_avg_ms = kern_ms / max(kern_n, 1)
         achieved = nbytes / (kern_avg_ms / 1e3) / 1e9
+        cfg = config_of(args.workload, world, n, e, n_lines, nbytes)
         line = {
             "metric": METRIC, "value": total_lines / (step_ms / 1e3), "unit": "alignments/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": args.workload, "graph_nodes": n, "graph_links": e,
-                       "alignments_per_gpu": n_lines, "gaf_bytes_per_gpu": nbytes,
-                       "bytes_per_alignment": nbytes / n_lines, "partition": f"byte-range x{world}",
-                       "l2": "input (GAF bytes per GPU) is larger than L2; no flush needed",
-                       "timing": "per-step CUDA events on the launching stream; counter reset outside the events"},
+            "steps": K, "warmup": W, "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "strong" if args.workload.endswith("-strong") else "weak",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": cfg,
             "gaf_gb_per_s": total_bytes / step_ms / 1e6,
             "wall_ms_per_step_incl_reset": 1e3 * (t_wall1 - t_wall0) / K,
             "gpu_launches": int(launches),
             "deferred_records": st["deferred_lines"],
+            "gfa_pass1_device_ms": gfa_load_ms,
             "clocks": clocks,
             "e2e": e2e,
+            "parity_checked": bool(parity and parity["checked"]),
+            "parity": parity,
             "roofline": {"bound": "hbm", "kernel": "augment_team_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(args.workload) if world == 1 else None,
@@ -410,17 +530,55 @@ def main():
                          "algorithmic_bytes_per_launch": int(nbytes)},
         }
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_baseline(sg, pinned.numpy()[:nbytes], args.cpu_sample_lines, 1)
-            if cb:
+            gaf_np = pinned.numpy()[:nbytes]
+            port = None
+            if parity:
+                port = {"value": parity["records"] / port_secs, "unit": "alignments/s", "cores": 1, "kind": "port",
+                        "sample": f"first {parity['records']} records of the same GAF, GAF loop only "
+                                  f"(oracle/augment_oracle.c, {port_secs:.2f} s)"}
+            ref = reference_script_time(gfa_path, gaf_np, args.ref_sample_lines)
+            if ref:
                 line["cpu_baseline"] = {
-                    "value": cb["lines"] / cb["gaf_loop_s"], "unit": "alignments/s", "cores": 1, "kind": "port",
-                    "sample": f"first {cb['lines']} records of the same GAF, GAF loop only (oracle/augment_oracle.c, "
-                              f"{cb['gaf_loop_s']:.2f} s); host has {os.cpu_count()} cores",
-                    "gaf_gb_per_s": cb["bytes"] / cb["gaf_loop_s"] / 1e9}
+                    "value": ref["lines"] / ref["gaf_loop_s"], "unit": "alignments/s", "cores": 1, "kind": "reference",
+                    "sample": f"the unmodified reference script (oracle/_ref) on the first {ref['lines']} records of the same GAF, "
+                              f"1 core (it is single-threaded): GAF loop {ref['gaf_loop_s']:.1f} s; its two GFA passes over the "
+                              f"{n}-node graph {ref['gfa_passes_s']:.1f} s; host has {os.cpu_count()} cores",
+                    "gfa_passes_s": ref["gfa_passes_s"], "port": port}
+            elif port:
+                line["cpu_baseline"] = port
+        if world == 1 and not args.no_cli:
+            line["cli"] = cli_wall_times(gfa_path, pinned.numpy()[:nbytes], tmp.name, n_lines)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    tmp.cleanup()
+
+
+def cli_wall_times(gfa_path: str, gaf_np: np.ndarray, tmpdir: str, n_lines: int):
+    """Wall time of the drop-in script (pantas:132 runs it), GAF + GFA files -> augmented GFA on stdout: with both GFA passes
+    on the device (the product) and with the host passes of pantas_b200/gfa.py (what round 1 shipped)."""
+    script = os.path.join(ROOT, "scripts", "alignments_augmentation_from_gaf.py")
+    ap = os.path.join(tmpdir, "bench.gaf")
+    gaf_np.tofile(ap)
+    out = {"alignments": n_lines, "gaf_bytes": int(gaf_np.shape[0]), "gfa_bytes": os.path.getsize(gfa_path)}
+    for name, env in (("device_gfa_passes_s", {}), ("python_gfa_passes_s", {"PANTAS_GFA_PASSES": "host"})):
+        t0 = time.time()
+        with open(os.path.join(tmpdir, name + ".gfa"), "wb") as fo:
+            p = subprocess.run([sys.executable, script, ap, gfa_path], stdout=fo, stderr=subprocess.PIPE, env=dict(os.environ, **env))
+        out[name] = time.time() - t0
+        if p.returncode != 0:
+            out[name] = None
+            out["error"] = p.stderr.decode()[-300:]
+    try:
+        a = open(os.path.join(tmpdir, "device_gfa_passes_s.gfa"), "rb").read()
+        b = open(os.path.join(tmpdir, "python_gfa_passes_s.gfa"), "rb").read()
+        out["outputs_identical"] = a == b
+        out["out_bytes"] = len(a)
+    except OSError:
+        pass
+    os.remove(ap)
+    return out
 
 
 if __name__ == "__main__":

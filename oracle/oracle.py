@@ -48,6 +48,19 @@ def _load():
         ]
         lib.oracle_free_buf.argtypes = [ctypes.c_void_p]
         lib.oracle_free_buf.restype = None
+        lib.oracle_graph_load.restype = ctypes.c_void_p
+        lib.oracle_graph_load.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_char_p, ctypes.c_size_t]
+        lib.oracle_graph_free.argtypes = [ctypes.c_void_p]
+        lib.oracle_graph_free.restype = None
+        lib.oracle_graph_nodes.argtypes = [ctypes.c_void_p]
+        lib.oracle_graph_nodes.restype = ctypes.c_longlong
+        lib.oracle_augment_graph.restype = ctypes.c_int
+        lib.oracle_augment_graph.argtypes = [
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_longlong, ctypes.c_int,
+            ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t),
+            ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong),
+            ctypes.POINTER(ctypes.c_double), ctypes.c_char_p, ctypes.c_size_t,
+        ]
         _lib = lib
     return _lib
 
@@ -94,6 +107,63 @@ def run_oracle(gaf, gfa, thr: int = 20, write_output: bool = True) -> OracleResu
         lib.oracle_free_buf(out)
     del k1, k2
     return OracleResult(rc, data, rej.value, nl.value, secs.value, err.value.decode("ascii", "replace"))
+
+
+class OracleGraph:
+    """A GFA parsed once by the oracle (REF:121-126); ``run`` is the GAF loop (+ the writer) against it with private
+    counters, so several host threads can time the loop on their own byte ranges without re-reading the GFA."""
+
+    def __init__(self, gfa):
+        lib = _load()
+        fp, fn, keep = _as_ptr(gfa)
+        rc = ctypes.c_int()
+        err = ctypes.create_string_buffer(256)
+        self._h = lib.oracle_graph_load(fp, fn, ctypes.byref(rc), err, 256)
+        del keep
+        self.rc = rc.value
+        self.err = err.value.decode("ascii", "replace")
+        self.n_nodes = int(lib.oracle_graph_nodes(self._h))
+
+    def run(self, gaf, thr: int = 20, write_output: bool = True) -> OracleResult:
+        lib = _load()
+        gp, gn, keep = _as_ptr(gaf)
+        out = ctypes.c_void_p()
+        out_n = ctypes.c_size_t()
+        rej = ctypes.c_longlong()
+        nl = ctypes.c_longlong()
+        secs = ctypes.c_double()
+        err = ctypes.create_string_buffer(256)
+        rc = lib.oracle_augment_graph(self._h, gp, gn, thr, 1 if write_output else 0, ctypes.byref(out), ctypes.byref(out_n),
+                                      ctypes.byref(rej), ctypes.byref(nl), ctypes.byref(secs), err, 256)
+        data = b""
+        if rc == 0 and out.value:
+            data = ctypes.string_at(out.value, out_n.value)
+            lib.oracle_free_buf(out)
+        del keep
+        return OracleResult(rc, data, rej.value, nl.value, secs.value, err.value.decode("ascii", "replace"))
+
+    def close(self):
+        if self._h:
+            _load().oracle_graph_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+REF_COPY = os.path.join(_HERE, "_ref", "alignments_augmentation_from_gaf.py")
+
+
+def reference_script():
+    """The reference script itself: /root/reference in the build container, the copy `make -C oracle ref` put under
+    oracle/_ref/ (git-ignored; it travels to the GPU box with the snapshot) elsewhere.  None if neither exists."""
+    for p in (REFERENCE_SCRIPT, REF_COPY):
+        if os.path.exists(p):
+            return p
+    return None
 
 
 def reference_available() -> bool:

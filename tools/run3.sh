@@ -1,3 +1,4 @@
 set -x
 mkdir -p gpurun_out
-for L in 0 1; do for g in 8192 8193 7168 6144; do PANTAS_LOOSE=$L PANTAS_TEAM_TILE=$g python tools/prof_step.py --pairs 5000000 --steps 4 2>&1 | grep -E "fast kernel" | sed "s/^/loose $L geo $g: /"; done; done
+(time python bench.py --steps 5 --warmup 3) > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 4000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+(time python bench.py --impl reference --steps 3 --warmup 1) > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 2500 gpurun_out/bench_ref.json; tail -4 gpurun_out/bench_ref.err
