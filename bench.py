@@ -293,7 +293,7 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
 
-    from pantas_b200.dist import reduce_results
+    from pantas_b200.dist import reduce_results, rows_to_host
     from pantas_b200.engine import AugmentEngine
     from pantas_b200.gfa_device import DeviceGfa
 
@@ -380,11 +380,8 @@ def main():
         d2h = 0
         if rank == 0:                                          # D2H of the step's (reduced) result into pinned host buffers
             for k, t in enumerate(out):
-                if isinstance(t, torch.Tensor):
-                    pin_out(k, t)
-                    d2h += t.numel() * t.element_size()
-                else:
-                    d2h += t.nbytes                            # (side rows: already on the host)
+                pin_out(k, t)
+                d2h += t.numel() * t.element_size()
         torch.cuda.synchronize()
         return d2h
 
@@ -482,7 +479,7 @@ def main():
             mine[:end] = gaf_dev[:end]
             parts = [torch.empty(m, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
             dist.gather(mine, parts, dst=0)
-            novel_h, sparse_h = novel, sparse
+            novel_h, sparse_h = rows_to_host(novel), rows_to_host(sparse)
             if rank == 0:
                 prefix = np.concatenate([p[:s].cpu().numpy() for p, s in zip(parts, sizes)])
         else:

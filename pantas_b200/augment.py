@@ -86,14 +86,79 @@ def stream_gaf_range(engine, gaf_file: str, lo: int, hi: int, thr: int) -> None:
     engine.sync()
 
 
+def is_stream(gaf_file: str) -> bool:
+    """gzip / bgzip files and stdin ("-") cannot be split by byte range: they are read front to back."""
+    return gaf_file == "-" or gaf_file.endswith((".gz", ".bgz"))
+
+
+def stream_gaf_sequential(engine, gaf_file: str, thr: int, rank: int = 0, world: int = 1) -> None:
+    """Compressed / piped GAF (`vg mpmap ... | gzip`): the stream is inflated on the host into
+    the two pinned staging buffers, cut at line ends, and chunk k goes to rank k % world (every rank reads the whole
+    stream, which has no byte ranges to seek to, and skips the chunks of the others; file offsets are offsets of the
+    INFLATED text, so stamps -- and the output -- are the same as for the plain file)."""
+    import gzip
+
+    import torch
+
+    stage = engine.stage_bytes
+    bufs = [torch.empty(stage, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    views = [b.numpy() for b in bufs]
+    tickets = [None, None]
+    if gaf_file == "-":
+        f = sys.stdin.buffer
+        if f.peek(2)[:2] == b"\x1f\x8b":
+            f = gzip.GzipFile(fileobj=f, mode="rb")
+    else:
+        f = gzip.open(gaf_file, "rb")
+    carry = np.zeros(0, dtype=np.uint8)
+    k = 0
+    chunk_no = 0
+    pos = 0
+    eof = False
+    while not eof or carry.size:
+        if tickets[k] is not None:
+            engine.wait_copy(tickets[k])
+            tickets[k] = None
+        v = views[k]
+        c = carry.size
+        if c:
+            v[:c] = carry
+        got = 0
+        while c + got < stage and not eof:
+            r = f.readinto(memoryview(v[c + got:stage]))
+            if not r:
+                eof = True
+                break
+            got += r
+        n = c + got
+        if n == 0:
+            break
+        if not eof:
+            cut = _last_newline(v, n) + 1
+            if cut <= 0:
+                raise UnsupportedInput(f"GAF record longer than the {stage >> 20} MiB staging buffer (raise PANTAS_STAGE_MB)")
+        else:
+            cut = n
+        carry = v[cut:n].copy()
+        if chunk_no % world == rank:
+            tickets[k] = engine.process_host(bufs[k].data_ptr(), cut, pos, thr)
+            k ^= 1
+        pos += cut
+        chunk_no += 1
+    engine.sync()
+
+
 def augment_file(graph: Graph, gaf_file: str, thr: int = 20, device: int = 0, lo: int | None = None,
-                 hi: int | None = None, engine=None):
-    """GAF loop on one GPU over [lo, hi) of the file -> (engine, error word)."""
+                 hi: int | None = None, engine=None, rank: int = 0, world: int = 1):
+    """GAF loop on one GPU over [lo, hi) of the file (plain files) or over this rank's chunks (streams) -> engine."""
     from .engine import AugmentEngine
 
     eng = engine or AugmentEngine(device)
     if eng.graph is not graph:
         eng.set_graph(graph)
+    if is_stream(gaf_file):
+        stream_gaf_sequential(eng, gaf_file, thr, rank, world)
+        return eng
     size = os.path.getsize(gaf_file)
     stream_gaf_range(eng, gaf_file, 0 if lo is None else lo, size if hi is None else hi, thr)
     return eng
@@ -152,13 +217,16 @@ def main(argv, out=None, err=None) -> int:
         novel_h = novel.cpu().numpy().view(np.uint64).reshape(-1, 3)
         sparse_h = sparse.cpu().numpy().view(np.uint64).reshape(-1, 3)
     else:
-        from .dist import ERR_HOST, ERR_NONE, reduce_error, reduce_results
+        from .dist import ERR_HOST, ERR_NONE, reduce_error, reduce_results, rows_to_host
 
         # every rank reaches the collectives below, whatever happens to its own share of the GAF
         word = ERR_NONE
         try:
-            b = shard_bounds(gaf_file, world)
-            augment_file(graph, gaf_file, thr, engine=eng, lo=b[rank], hi=b[rank + 1])
+            if is_stream(gaf_file):
+                augment_file(graph, gaf_file, thr, engine=eng, rank=rank, world=world)
+            else:
+                b = shard_bounds(gaf_file, world)
+                augment_file(graph, gaf_file, thr, engine=eng, lo=b[rank], hi=b[rank + 1])
             eng.check_data_error()
         except (PantasDataError, UnsupportedInput) as e:
             word = ((e.offset or 0) << 8) | (e.code or ERR_HOST)
@@ -174,9 +242,10 @@ def main(argv, out=None, err=None) -> int:
             exc = PantasDataError if code < 20 else UnsupportedInput
             raise exc(f"GAF byte offset {off}: {text}", code, off)
         sums, stamps, novel, sparse = eng.export_device()
-        sums, stamps, novel_h, sparse_h = reduce_results(sums, stamps, novel, sparse, graph.n_nodes, dst=0)
+        sums, stamps, novel, sparse = reduce_results(sums, stamps, novel, sparse, graph.n_nodes, dst=0)
         if rank != 0:
             return 0
+        novel_h, sparse_h = rows_to_host(novel), rows_to_host(sparse)
 
     n, e = graph.n_nodes, graph.n_edges
     rej = int(sums[3 * n + e].item())

@@ -54,8 +54,9 @@ def allreduce_results(sums, stamps, novel, sparse, n_nodes: int, n_edges: int, g
                       gather_rows(novel), gather_rows(sparse))
 
 
-def gather_side(rows, group=None) -> np.ndarray:
-    """All ranks' {key, count, stamp} rows, merged by key (counts add, stamps take the minimum), on every rank."""
+def gather_side(rows, group=None):
+    """All ranks' {key, count, stamp} rows merged by key (counts add, stamps take the minimum), as a tensor on the rows'
+    device, on every rank.  Everything stays on the device: one host read (the row counts) sizes the exchange."""
     import torch
     import torch.distributed as dist
 
@@ -64,37 +65,48 @@ def gather_side(rows, group=None) -> np.ndarray:
     n = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
     sizes = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    sizes = torch.cat(sizes).tolist()
     m = max(max(sizes), 1)
     pad = torch.zeros((m, 3), dtype=rows.dtype, device=rows.device)
     pad[: rows.shape[0]] = rows
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad, group=group)
-    parts = [b[:s].cpu().numpy().view(np.uint64).reshape(-1, 3) for b, s in zip(bufs, sizes)]
-    return merge_side(parts)
+    allr = torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
+    if allr.shape[0] == 0:
+        return allr
+    uniq, inv = torch.unique(allr[:, 0], return_inverse=True)
+    cnt = torch.zeros_like(uniq).scatter_add_(0, inv, allr[:, 1])
+    st = torch.full_like(uniq, (1 << 63) - 1).scatter_reduce_(0, inv, allr[:, 2], "amin", include_self=True)
+    return torch.stack([uniq, cnt, st], dim=1)
 
 
 def reduce_results(sums, stamps, novel, sparse, n_nodes: int, dst: int = 0, group=None):
     """The one-shot reduction that ends a multi-GPU job, to rank `dst` only (it alone writes the GFA):
 
-    * the two small side tables are gathered and merged first;
+    * the two small side tables are gathered and merged first (on the device);
     * ``reduce(SUM)`` of the counter buffer (not all_reduce: nobody else needs it);
     * first-touch stamps are only ever read for nodes that also have a deletion-derived key (the writer orders a
       node's IL / OL entries by them), so only those nodes' stamps are reduced (MIN) -- a few thousand values instead
       of 2 x n_nodes.
 
-    -> (sums, stamps, novel rows, sparse rows); sums / stamps are valid on `dst` only."""
+    -> (sums, stamps, novel rows, sparse rows), tensors on the inputs' device (rows as int64 bit patterns of the uint64
+    layout); sums / stamps are valid on `dst` only."""
     import torch
     import torch.distributed as dist
 
-    novel_h = gather_side(novel, group)
-    sparse_h = gather_side(sparse, group)
+    novel_m = gather_side(novel, group)
+    sparse_m = gather_side(sparse, group)
     dist.reduce(sums, dst=dst, op=dist.ReduceOp.SUM, group=group)
-    if sparse_h.shape[0]:
-        nodes = np.unique((sparse_h[:, 0] >> np.uint64(32)).astype(np.int64))      # the same list on every rank
-        idx = torch.from_numpy(np.concatenate([nodes, nodes + n_nodes])).to(stamps.device)
+    if sparse_m.shape[0]:
+        nodes = torch.unique((sparse_m[:, 0] >> 32) & 0xFFFFFFFF)   # key = idx << 32 | ...; the same list on every rank
+        idx = torch.cat([nodes, nodes + n_nodes])
         sub = stamps[idx].contiguous()
         dist.reduce(sub, dst=dst, op=dist.ReduceOp.MIN, group=group)
         if dist.get_rank(group) == dst:
             stamps[idx] = sub
-    return sums, stamps, novel_h, sparse_h
+    return sums, stamps, novel_m, sparse_m
+
+
+def rows_to_host(rows) -> np.ndarray:
+    """{key, count, stamp} rows (int64 bit patterns, any device) -> uint64[n, 3] on the host."""
+    return rows.cpu().numpy().view(np.uint64).reshape(-1, 3)

@@ -26,7 +26,7 @@ def _worker(rank, world, port, gfa_path, gaf_path, out_path, to_root=False):
     from hostsim_util import run_hostsim
     from pantas_b200.counts import Counts
     from pantas_b200.counts import FlatResult
-    from pantas_b200.dist import ERR_NONE, allreduce_results, reduce_error, reduce_results
+    from pantas_b200.dist import ERR_NONE, allreduce_results, reduce_error, reduce_results, rows_to_host
     from pantas_b200.gfa import load_graph, write_augmented
     from pantas_b200.shard import shard_bounds
 
@@ -51,7 +51,7 @@ def _worker(rank, world, port, gfa_path, gaf_path, out_path, to_root=False):
             torch.from_numpy(flat.sparse.view(np.int64)))
     if to_root:        # the product's reduction: to rank 0 only, stamps only where the writer reads them
         sums, stamps, novel, sparse = reduce_results(*args, graph.n_nodes, dst=0)
-        res = FlatResult(graph.n_nodes, graph.n_edges, sums.numpy(), stamps.numpy(), novel, sparse)
+        res = FlatResult(graph.n_nodes, graph.n_edges, sums.numpy(), stamps.numpy(), rows_to_host(novel), rows_to_host(sparse))
     else:
         res = allreduce_results(*args, graph.n_nodes, graph.n_edges)
     if rank == 0:

@@ -67,3 +67,38 @@ def test_cli_two_gpus_byte_range_shards(tmp_path):
     assert p.returncode == 0, p.stderr.decode()[-3000:]
     assert p.stdout == want.out
     assert f"Rejected alignments: {want.rej}".encode() in p.stderr
+
+
+def test_cli_gzip_and_stdin_streams(tmp_path):
+    """Compressed / piped GAF: same bytes as for the plain file."""
+    import gzip
+
+    gfa, gaf = fuzzgen.make_case(6003, n_nodes=60, n_reads=6000, weird=True)
+    want = run_oracle(gaf.encode(), gfa.encode())
+    (tmp_path / "g.gfa").write_bytes(gfa.encode())
+    with gzip.open(tmp_path / "a.gaf.gz", "wb") as f:
+        f.write(gaf.encode())
+    p = run_cli(tmp_path / "a.gaf.gz", tmp_path / "g.gfa", env={"PANTAS_STAGE_MB": "1"})
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    assert p.stdout == want.out
+    e = dict(os.environ, PANTAS_STAGE_MB="1")
+    p = subprocess.run([sys.executable, SCRIPT, "-", str(tmp_path / "g.gfa")], input=gaf.encode(), capture_output=True, env=e, timeout=600)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    assert p.stdout == want.out
+
+
+def test_batch_of_samples_on_one_graph(tmp_path):
+    """Several GAFs against one resident graph: each output equals the one-sample result."""
+    gfa, gaf1 = fuzzgen.make_case(6004, n_nodes=50, n_reads=3000, weird=True)
+    gaf2 = "".join(gaf1.splitlines(keepends=True)[::2])               # another sample over the same graph
+    (tmp_path / "g.gfa").write_bytes(gfa.encode())
+    (tmp_path / "s1.gaf").write_bytes(gaf1.encode())
+    (tmp_path / "s2.gaf").write_bytes(gaf2.encode())
+    p = subprocess.run([sys.executable, "-m", "pantas_b200.batch", str(tmp_path / "g.gfa"), str(tmp_path / "out"),
+                        str(tmp_path / "s1.gaf"), str(tmp_path / "s2.gaf"), str(tmp_path / "s1.gaf")],
+                       capture_output=True, cwd=ROOT, timeout=600)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    for name, gaf in (("s1", gaf1), ("s2", gaf2)):
+        want = run_oracle(gaf.encode(), gfa.encode())
+        assert want.rc == 0
+        assert (tmp_path / "out" / f"{name}.gfa").read_bytes() == want.out
