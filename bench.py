@@ -45,6 +45,8 @@ WORKLOADS = {
     "hs-chr1-10M": ("hs-chr1", 5_000_000, 1003),
     "hs-chr1-100M-strong": ("hs-chr1", 50_000_000, 1003),       # BASELINE.json configs[2]: 100 M alignments in total, split over the ranks
     "gene-panel-10M": ("gene-panel", 5_000_000, 1005),
+    "gene-panel-100M": ("gene-panel", 50_000_000, 1005),         # BASELINE.json configs[4] at a fifth of its 500 M reads: Zipf-skewed coverage
+    "hs-wg-25M": ("hs-wg", 12_500_000, 1004),                    # BASELINE.json configs[3] graph (2e8 nodes), 25 M alignments per GPU
     "tiny-20k": ("tiny", 10_000, 7),
 }
 
@@ -62,6 +64,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cli", action="store_true", help="skip the drop-in script wall-time measurement")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--tables", action="store_true", help="graph tables straight from the generator (no GFA text: for graphs whose "
+                    "GFA would be tens of GB); implies --no-parity --no-cli")
     return ap.parse_args()
 
 
@@ -111,7 +115,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -126,7 +130,7 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, line in self.rows:
-            if ts < t0 - 0.15 or ts > t1 + 0.15:
+            if ts < t0 - 0.3 or ts > t1 + 0.3:
                 continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
@@ -157,14 +161,25 @@ def make_inputs(workload: str, rank: int, world: int, pinned: bool = True):
     if workload.endswith("-strong"):
         pairs //= world
     sg = SynthGraph(preset, seed=seed)
-    buf, n_lines = sg.gaf(pairs, first_pair=rank * pairs, threads=max(1, (os.cpu_count() or 8) // max(world, 1)))
-    n = int(buf.shape[0])
+    threads = max(1, (os.cpu_count() or 8) // max(world, 1))
+    piece = 2_500_000                                       # pairs per generator call: bounds the generator's own buffers
+    parts, n_lines = [], 0
+    for p0 in range(0, pairs, piece):
+        b, nl = sg.gaf(min(piece, pairs - p0), first_pair=rank * pairs + p0, threads=threads)
+        parts.append(b)
+        n_lines += nl
+    n = int(sum(b.shape[0] for b in parts))
     if not pinned:
-        return sg, buf, n, n_lines
+        return sg, (np.concatenate(parts) if len(parts) > 1 else parts[0]), n, n_lines
     import torch
 
-    t = torch.empty(n + 64, dtype=torch.uint8).pin_memory()
-    t[:n] = torch.from_numpy(buf)
+    t = torch.empty(n + 64, dtype=torch.uint8)
+    if n <= (6 << 30):                                      # (larger inputs stay pageable: the host-buffer leg is skipped for them)
+        t = t.pin_memory()
+    pos = 0
+    for b in parts:
+        t[pos:pos + b.shape[0]] = torch.from_numpy(b)
+        pos += b.shape[0]
     return sg, t, n, n_lines
 
 
@@ -299,16 +314,26 @@ def main():
 
     K, W = args.steps, max(args.warmup, 3)
     sg, pinned, nbytes, n_lines = make_inputs(args.workload, rank, world)
+    if args.tables:
+        args.no_parity = args.no_cli = True
+    if not pinned.is_pinned():
+        args.no_e2e = args.no_cli = True
     tmp = tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     gfa_path = os.path.join(tmp.name, f"g{rank}.gfa")
-    sg.write_gfa(gfa_path)
     eng = AugmentEngine(local_rank)
     t0 = time.perf_counter()
-    dg = DeviceGfa.load(eng, gfa_path)                        # GFA pass 1 on the device (REF:121-126)
-    dg.set_graph()
+    if args.tables:
+        dg = None
+        graph = sg.graph()
+        eng.set_graph(graph)
+    else:
+        sg.write_gfa(gfa_path)
+        t0 = time.perf_counter()
+        dg = DeviceGfa.load(eng, gfa_path)                    # GFA pass 1 on the device (REF:121-126)
+        dg.set_graph()
+        graph = dg.graph
     torch.cuda.synchronize()
     gfa_load_ms = 1e3 * (time.perf_counter() - t0)
-    graph = dg.graph
     eng.profile(True)
     n, e = graph.n_nodes, graph.n_edges
 
@@ -324,18 +349,8 @@ def main():
     else:
         total_lines, total_bytes = n_lines, nbytes
 
-    gaf_dev = torch.empty(((nbytes + 15) // 16) * 16 + 16, dtype=torch.uint8, device=dev)
-    gaf_dev[:nbytes].copy_(pinned[:nbytes], non_blocking=True)
-    torch.cuda.synchronize()
-
-    def finish_step():
-        """fold + export in the C-ABI layout, then (N > 1) the one-shot reduction to rank 0"""
-        sums, stamps, novel, sparse = eng.export_device()
-        if world > 1:
-            return reduce_results(sums, stamps, novel, sparse, n, dst=0)
-        return sums, stamps, novel, sparse
-
-    # chunks of at most 3 GiB (one launch each; pt_process_chunk takes < 3.75 GiB), cut at line ends
+    # chunks of at most 3 GiB (one launch each; pt_process_chunk takes < 3.75 GiB), cut at line ends; every chunk in its own
+    # (16-byte aligned) device buffer
     chunks = []
     view_all = pinned.numpy()
     pos = 0
@@ -344,12 +359,25 @@ def main():
         if end < nbytes:
             w = view_all[end - (1 << 16):end]
             end = end - (1 << 16) + int(np.flatnonzero(w == 10)[-1]) + 1
-        chunks.append((pos, end))
+        t = torch.empty(((end - pos + 15) // 16) * 16 + 16, dtype=torch.uint8, device=dev)
+        for a in range(pos, end, 1 << 30):
+            b = min(a + (1 << 30), end)
+            t[a - pos:b - pos].copy_(pinned[a:b], non_blocking=True)
+        chunks.append((pos, end, t))
         pos = end
+    torch.cuda.synchronize()
+    gaf_dev = chunks[0][2]
+
+    def finish_step():
+        """fold + export in the C-ABI layout, then (N > 1) the one-shot reduction to rank 0"""
+        sums, stamps, novel, sparse = eng.export_device()
+        if world > 1:
+            return reduce_results(sums, stamps, novel, sparse, n, dst=0)
+        return sums, stamps, novel, sparse
 
     def device_step():
-        for a, b in chunks:
-            eng.process_device(gaf_dev[a:], b - a, file_off + a, 20)
+        for a, b, t in chunks:
+            eng.process_device(t, b - a, file_off + a, 20)
         return finish_step()
 
     pinned_out = {}
@@ -503,8 +531,8 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        kern_avg_ms = kern_ms / max(kern_n, 1)
-        achieved = nbytes / (kern_avg_ms / 1e3) / 1e9
+        kern_avg_ms = kern_ms / max(kern_n, 1)                 # per launch (one launch per <= 3 GiB chunk)
+        achieved = nbytes * K / (kern_ms / 1e3) / 1e9          # GAF bytes of the K timed passes / time inside the kernel
         cfg = config_of(args.workload, world, n, e, n_lines, nbytes)
         line = {
             "metric": METRIC, "value": total_lines / (step_ms / 1e3), "unit": "alignments/s", "n_gpus": world,
@@ -524,7 +552,7 @@ def main():
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(args.workload) if world == 1 else None,
                          "peak_source": peak_src, "kernel_ms": kern_avg_ms,
-                         "algorithmic_bytes_per_launch": int(nbytes)},
+                         "algorithmic_bytes_per_launch": int(nbytes // len(chunks)), "launches_per_step": len(chunks)},
         }
         if world == 1 and not args.no_cpu_baseline:
             gaf_np = pinned.numpy()[:nbytes]
