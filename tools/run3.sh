@@ -1,7 +1,9 @@
 set -x
 mkdir -p gpurun_out
-python bench.py --workload tiny-20k --steps 3 --warmup 3 2>&1 | tail -c 1500
-python bench.py --workload gene-panel-100M --steps 3 --warmup 3 --no-cli --no-cpu-baseline > gpurun_out/bench_genepanel_100M.json 2> gpurun_out/bench_gp.err; tail -c 2500 gpurun_out/bench_genepanel_100M.json; tail -3 gpurun_out/bench_gp.err
-ncu --metrics gpu__time_duration.sum,lts__t_sectors_op_red.sum,lts__t_sectors_op_atom.sum,lts__t_sectors_srcunit_tex_op_red.sum,lts__t_requests_srcunit_tex_op_red.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,lts__t_sector_hit_rate.pct,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed_op_global_red.sum,l1tex__t_requests_pipe_lsu_mem_global_op_red.sum,lts__throughput.avg.pct_of_peak_sustained_elapsed,lts__t_sectors_srcunit_tex_op_red_lookup_hit.sum,lts__t_sectors_srcunit_tex_op_red_lookup_miss.sum --clock-control none -k regex:augment_team -s 1 -c 1 --csv --log-file gpurun_out/atomics_genepanel.csv python tools/prof_step.py --preset gene-panel --seed 1005 --pairs 5000000 --steps 2 > gpurun_out/atomics_gp.log 2>&1
-ncu --metrics gpu__time_duration.sum,lts__t_sectors_op_red.sum,lts__t_sectors_op_atom.sum,lts__t_sectors_srcunit_tex_op_red.sum,lts__t_requests_srcunit_tex_op_red.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,lts__t_sector_hit_rate.pct,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed_op_global_red.sum,l1tex__t_requests_pipe_lsu_mem_global_op_red.sum,lts__throughput.avg.pct_of_peak_sustained_elapsed,lts__t_sectors_srcunit_tex_op_red_lookup_hit.sum,lts__t_sectors_srcunit_tex_op_red_lookup_miss.sum --clock-control none -k regex:augment_team -s 1 -c 1 --csv --log-file gpurun_out/atomics_dmfull.csv python tools/prof_step.py --pairs 5000000 --steps 2 > gpurun_out/atomics_dm.log 2>&1
-tail -4 gpurun_out/atomics_genepanel.csv gpurun_out/atomics_dmfull.csv | cut -c1-400
+N=${N:-8}
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
+$TR bench.py --gpus $N --workload hs-chr1-100M-strong --steps 3 --warmup 3 --no-cli --no-cpu-baseline > gpurun_out/bench_hschr1_100M_n$N.json 2> gpurun_out/bench_hs_n$N.err; tail -c 1800 gpurun_out/bench_hschr1_100M_n$N.json; tail -3 gpurun_out/bench_hs_n$N.err
+$TR bench.py --gpus $N --steps 5 --warmup 3 --no-cli --no-cpu-baseline > gpurun_out/bench_dmfull_n$N.json 2> gpurun_out/bench_dm_n$N.err; tail -c 1800 gpurun_out/bench_dmfull_n$N.json; tail -3 gpurun_out/bench_dm_n$N.err
+if [ "$N" = "8" ]; then
+$TR bench.py --gpus $N --workload hs-wg-25M --tables --steps 2 --warmup 3 > gpurun_out/bench_hswg_n$N.json 2> gpurun_out/bench_wg_n$N.err; tail -c 1800 gpurun_out/bench_hswg_n$N.json; tail -3 gpurun_out/bench_wg_n$N.err
+fi
