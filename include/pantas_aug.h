@@ -178,10 +178,7 @@ int pt_stats(pt_ctx* ctx, uint64_t* kernel_launches, uint64_t* deferred_lines, u
 /* Why records were handed from the fast path to the exact per-record path since the last reset
  * (diagnostics): out[0..n) = long record / look-ahead, columns not 12 single tabs, integer syntax,
  * tag order or content, cs class, path column, step list full, walk (duplicate / unknown id, node
- * without bases, cs too short), record list full, round-1a tile kernel (out[0..16)); then, when the
- * environment has PANTAS_PHASE_CLOCKS=1, cycles per phase of the fast-path kernel summed over CTAs
- * (out[16..32): waiting for the TMA copy, scan, records, ids, walk 1, walk 2, count, end of tile).
- * n <= 32.  Synchronises. */
+ * without bases, cs too short), record list full; the rest of out[0..n) is zero.  n <= 32.  Synchronises. */
 int pt_debug_counters(pt_ctx* ctx, uint64_t* out, int n);
 
 #ifdef __cplusplus

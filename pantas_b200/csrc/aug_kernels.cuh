@@ -79,7 +79,7 @@ struct ChunkArgs {
 };
 
 // why a record is handed to the slow path (pt_debug_counters)
-enum { WHY_LONG = 0, WHY_COLUMNS, WHY_INTS, WHY_TAGS, WHY_CS, WHY_PATH, WHY_STEPS_FULL, WHY_WALK, WHY_LINES_FULL, WHY_V1 };
+enum { WHY_LONG = 0, WHY_COLUMNS, WHY_INTS, WHY_TAGS, WHY_CS, WHY_PATH, WHY_STEPS_FULL, WHY_WALK, WHY_LINES_FULL, WHY_OTHER };
 
 __device__ __noinline__ void defer_line_impl(unsigned long long* sc, uint32_t* deferred, uint64_t deferred_cap, uint64_t chunk_pos,
                                             int64_t file_off, int why) {
@@ -88,7 +88,7 @@ __device__ __noinline__ void defer_line_impl(unsigned long long* sc, uint32_t* d
     if (j < deferred_cap) deferred[j] = (uint32_t)chunk_pos;
     else report_error_sc(sc, pt::PT_X_DEFER_FULL, file_off + (int64_t)chunk_pos);
 }
-__device__ __forceinline__ void defer_line(const Tables& T, uint64_t chunk_pos, int64_t file_off, int why = WHY_V1) {
+__device__ __forceinline__ void defer_line(const Tables& T, uint64_t chunk_pos, int64_t file_off, int why = WHY_OTHER) {
     defer_line_impl(T.sc, T.deferred, T.deferred_cap, chunk_pos, file_off, why);
 }
 

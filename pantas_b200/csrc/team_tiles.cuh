@@ -4,16 +4,20 @@
 //
 // Reference loop body: /root/reference/scripts/alignments_augmentation_from_gaf.py:142-363 (REF:n).
 //
-// The unit of execution is a TEAM: one CTA of two warps that owns 8 KiB tiles of the GAF chunk (+ 1 KiB of look-ahead:
-// a record belongs to the tile it starts in), ten such CTAs per SM.  Teams share nothing but the global tables, so a
-// phase that leaves lanes idle only idles its own two warps while the other 18 warps of the SM are in other phases; the
-// barriers are 64-thread barriers.  One elected thread moves the tile with a 1-D TMA bulk copy (UBLKCP, L2 evict-first);
+// The unit of execution is a TEAM: two warps that own 8 KiB tiles of the GAF chunk (+ 1 KiB of look-ahead: a record
+// belongs to the tile it starts in) and their own slice of shared memory.  G::NT teams form one CTA (default: the ten
+// teams of an SM are ONE 640-thread CTA) and share nothing but the global tables and ONE CTA-wide barrier per tile,
+// after `scan`: it keeps every team of the SM in (nearly) the same phase, so that the SM's instruction caches hold one
+// or two phases of this 100 KB kernel instead of all of them (independent 64-thread CTAs starved on instruction fetch).
+// Inside a tile the phases are separated by team-level named barriers (bar.sync team + 1, 64; ChunkArgs::loose = 0 makes
+// every barrier CTA-wide).  One elected thread per team moves the tile with a 1-D TMA bulk copy (UBLKCP, L2 evict-first);
 // the copy of the team's next tile is issued as soon as the bytes are dead (after `ids`).  Phases over a tile:
 //
-//   scan     one thread per 64 bytes (4 x LDS.128, lane-rotated: no bank conflicts), branch-free SWAR: a 64-bit
-//            whitespace mask (bytes <= 0x20) and a 64-bit mask of path separators ('>' '<') OR non-tab whitespace
-//            ('\n' rides along for free: sep & ws = record-end candidates).  Record starts are ranked with one ballot per
-//            warp iteration (no atomics) into the warp's own list.
+//   scan     every thread takes 4 x 16 bytes per round (LDS.128, conflict-free), branch-free SWAR on 32-bit words: per
+//            16-byte vector a 16-bit whitespace mask (bytes <= 0x20) and a 16-bit mask of path separators ('>' '<') OR
+//            non-tab whitespace ('\n' rides along for free: sep & ws = record-end candidates).  Record starts are read
+//            back from the mask words and ranked with a warp scan (no atomics) into a two-ended list: warp 0 fills it
+//            from the front, warp 1 from the back.
 //   records  warp 0 = role B for every record, warp 1 = role A (a warp takes as long for one record as for 32; ~27
 //            records per tile keep both warps' lanes busy):
 //              B  the 12 column boundaries (single tabs, no empty column), MAPQ and '*' filters (REF:143-148), the three
@@ -22,17 +26,18 @@
 //              A  skips ten boundaries by popcount; first cs token, first dv:f: token (REF:154-160,172-180), dv filter,
 //                 cs string parsed into the tile's op pool (REF:10-50, incl. cigar_clipping).
 //            Anything unusual hands the record to the exact per-record path (line_core.cuh, augment_deferred_kernel).
-//   ids      one thread per path step: SWAR decimal parse of the id out of shared memory -> node index -> ONE 16-byte
-//            load of the node's hot record (four in flight per thread); keeps index, meta word and the node's share
-//            of the query (REF:215-218: first / last node shortened) in shared memory.
-//   walk     warp 0, one thread per record, a short loop over the record's steps: duplicate / unknown ids, the sum of
-//            the node shares against the cs length (IndexError REF:227), and -- only for records whose cs string has
-//            several ops -- the prefix sums the merge walk needs (REF:205-255).  Warp 1 meanwhile drains the previous
-//            tile's list of links that are not inline (hash probes).
-//   fold     one thread per step of a multi-op record: clear_align / compact_align (REF:63-107) folded over the op
-//            pieces that overlap the node: dropped or not, counting ops, deletion-derived IL/OL keys.
-//   count    one thread per surviving step, no loads from the tables: ONE 32-bit RED (tables.cuh), stamps only while
-//            the node's settled bit is clear.  Links that are not inline are listed for the next tile's walk phase.
+//   ids      one thread per path step: SWAR decimal parse of the id out of shared memory -> node index -> the node's
+//            meta word from the L2 (four loads in flight per thread); keeps index, meta word and the node's length in
+//            shared memory, flags consecutive duplicates (REF:190-196) and adds the length to the record's sum.
+//   walk     warp 0 the even records, warp 1 the odd ones, O(1) for a record whose cs string is one op: first / last node
+//            shortened (REF:215-218), the sum of the node shares against the cs length (IndexError REF:227), dropped
+//            ends.  Records with several ops get the prefix sums the merge walk needs (REF:205-255) from a warp scan and
+//            are listed for `fold`.  Warp 1 first drains the previous tile's list of links that are not inline (hash probes).
+//   fold     the listed steps of multi-op records, half of them per warp: clear_align / compact_align (REF:63-107) folded
+//            over the op pieces that overlap the node: dropped or not, counting ops, deletion-derived IL/OL keys.
+//   count    one thread per surviving step, no dependent loads from the tables: ONE 32-bit RED (tables.cuh), stamps only
+//            while the node's settled bit is clear.  Links that are not inline are listed for the next tile's walk phase.
+//            No barrier closes the tile: a warp that is done starts scanning the next one.
 #pragma once
 
 namespace teamp {

@@ -34,6 +34,7 @@ class AugmentEngine:
         self.graph: Graph | None = None
         self._pinned = {}
         self.tdev = torch.device("cuda", self.device)
+        self._torch_stream = bool(use_torch_stream)
         if use_torch_stream:
             with torch.cuda.device(self.tdev):
                 self._check(self.lib.pt_set_stream(self._ctx, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
@@ -104,21 +105,24 @@ class AugmentEngine:
 
     # -- results
     def export_device(self):
-        """(sums, stamps, novel, sparse) as CUDA tensors in the pantas_aug.h layout."""
+        """(sums, stamps, novel, sparse) as CUDA tensors in the pantas_aug.h layout.  Stream-ordered when the context runs
+        on torch's current stream (the default): no host synchronisation after the last kernel is enqueued."""
         torch = self.torch
         g = self.graph
-        n_novel, n_sparse = ctypes.c_uint64(), ctypes.c_uint64()
-        self._check(self.lib.pt_finalize(self._ctx, ctypes.byref(n_novel), ctypes.byref(n_sparse)))
         n, e = g.n_nodes, g.n_edges
         sums = torch.empty(3 * n + e + 4, dtype=torch.int64, device=self.tdev)
         stamps = torch.empty(2 * n, dtype=torch.int64, device=self.tdev)
-        novel = torch.empty((max(n_novel.value, 1), 3), dtype=torch.int64, device=self.tdev)
-        sparse = torch.empty((max(n_sparse.value, 1), 3), dtype=torch.int64, device=self.tdev)
+        # the dense export needs no host-side number: enqueue it first, the row counts' round trip overlaps it
         self._check(self.lib.pt_export_dense(self._ctx, ctypes.c_void_p(sums.data_ptr()), sums.numel(),
                                              ctypes.c_void_p(stamps.data_ptr()), stamps.numel()))
+        n_novel, n_sparse = ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self.lib.pt_finalize(self._ctx, ctypes.byref(n_novel), ctypes.byref(n_sparse)))
+        novel = torch.empty((max(n_novel.value, 1), 3), dtype=torch.int64, device=self.tdev)
+        sparse = torch.empty((max(n_sparse.value, 1), 3), dtype=torch.int64, device=self.tdev)
         self._check(self.lib.pt_export_side(self._ctx, ctypes.c_void_p(novel.data_ptr()), n_novel.value,
                                             ctypes.c_void_p(sparse.data_ptr()), n_sparse.value))
-        self.sync()
+        if not self._torch_stream:
+            self.sync()
         return sums, stamps, novel[: n_novel.value], sparse[: n_sparse.value]
 
     def export_host(self):
@@ -163,21 +167,13 @@ class AugmentEngine:
         self._check(self.lib.pt_kernel_time(self._ctx, ctypes.byref(ms), ctypes.byref(n)))
         return float(ms.value), int(n.value)
 
-    WHY = ("long", "columns", "ints", "tags", "cs", "path", "steps_full", "walk", "lines_full", "v1")
+    WHY = ("long", "columns", "ints", "tags", "cs", "path", "steps_full", "walk", "lines_full", "other")
 
     def handover_reasons(self) -> dict:
         """Why records left the fast path (diagnostics)."""
         out = (ctypes.c_uint64 * 16)()
         self._check(self.lib.pt_debug_counters(self._ctx, out, 16))
         return {k: int(out[i]) for i, k in enumerate(self.WHY)}
-
-    PHASES = ("wait_tma", "scan", "records", "ids", "walk1", "walk2", "count", "lists_end")
-
-    def phase_cycles(self) -> dict:
-        """Cycles per phase of the fast path summed over CTAs (diagnostics; needs PANTAS_PHASE_CLOCKS=1)."""
-        out = (ctypes.c_uint64 * 32)()
-        self._check(self.lib.pt_debug_counters(self._ctx, out, 32))
-        return {k: int(out[16 + i]) for i, k in enumerate(self.PHASES)}
 
     def kernel_time_split(self):
         """(ms fast-path kernel, ms per-record kernel, launches) since the last call."""
