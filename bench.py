@@ -47,6 +47,8 @@ WORKLOADS = {
     "gene-panel-10M": ("gene-panel", 5_000_000, 1005),
     "gene-panel-100M": ("gene-panel", 50_000_000, 1005),         # BASELINE.json configs[4] at a fifth of its 500 M reads: Zipf-skewed coverage
     "hs-wg-25M": ("hs-wg", 12_500_000, 1004),                    # BASELINE.json configs[3] graph (2e8 nodes), 25 M alignments per GPU
+    "hs-wg-125M": ("hs-wg", 62_500_000, 1004),                   # BASELINE.json configs[3] itself at 8 GPUs: 8 x 125 M = 1 G alignments
+    "gene-panel-500M": ("gene-panel", 250_000_000, 1005),        # BASELINE.json configs[4] at its full 500 M reads (153 GB of GAF in HBM)
     "tiny-20k": ("tiny", 10_000, 7),
 }
 
@@ -153,8 +155,12 @@ class ClockSampler:
             self.proc.terminate()
 
 
-def make_inputs(workload: str, rank: int, world: int, pinned: bool = True):
-    """-> (SynthGraph, uint8 GAF of this rank's shard (pinned torch tensor or numpy), nbytes, n_lines)"""
+def make_inputs(workload: str, rank: int, world: int, pinned: bool = True, device=None):
+    """-> (SynthGraph, uint8 GAF of this rank's shard (pinned torch tensor or numpy), nbytes, n_lines, chunks)
+
+    Inputs beyond 6 GB (configs 3 and 4) are streamed when `device` is given: every generator piece goes straight into its
+    own device buffer and only the first piece stays on the host (parity prefix), so host memory stays bounded;
+    chunks = [(first byte, end byte, device tensor)], else None."""
     from pantas_b200.synth import SynthGraph
 
     preset, pairs, seed = WORKLOADS[workload]
@@ -163,16 +169,33 @@ def make_inputs(workload: str, rank: int, world: int, pinned: bool = True):
     sg = SynthGraph(preset, seed=seed)
     threads = max(1, (os.cpu_count() or 8) // max(world, 1))
     piece = 2_500_000                                       # pairs per generator call: bounds the generator's own buffers
-    parts, n_lines = [], 0
+    stream = device is not None and pairs * 2 * 330 > (6 << 30)
+    parts, chunks, n_lines, n = [], [], 0, 0
+    t_gen = time.perf_counter()
     for p0 in range(0, pairs, piece):
         b, nl = sg.gaf(min(piece, pairs - p0), first_pair=rank * pairs + p0, threads=threads)
-        parts.append(b)
         n_lines += nl
-    n = int(sum(b.shape[0] for b in parts))
+        if stream:
+            import torch
+
+            m = int(b.shape[0])
+            t = torch.empty(((m + 15) // 16) * 16 + 16, dtype=torch.uint8, device=device)
+            t[:m].copy_(torch.from_numpy(b))
+            chunks.append((n, n + m, t))
+            if not parts:
+                parts.append(b)
+        else:
+            parts.append(b)
+        n += int(b.shape[0])
+    if rank == 0:
+        print(f"[bench] generator: {n_lines} records, {n / 1e9:.2f} GB per rank in {time.perf_counter() - t_gen:.1f} s "
+              f"({threads} threads per rank)", file=sys.stderr)
     if not pinned:
-        return sg, (np.concatenate(parts) if len(parts) > 1 else parts[0]), n, n_lines
+        return sg, (np.concatenate(parts) if len(parts) > 1 else parts[0]), n, n_lines, None
     import torch
 
+    if stream:
+        return sg, torch.from_numpy(parts[0]), n, n_lines, chunks
     t = torch.empty(n + 64, dtype=torch.uint8)
     if n <= (6 << 30):                                      # (larger inputs stay pageable: the host-buffer leg is skipped for them)
         t = t.pin_memory()
@@ -180,7 +203,7 @@ def make_inputs(workload: str, rank: int, world: int, pinned: bool = True):
     for b in parts:
         t[pos:pos + b.shape[0]] = torch.from_numpy(b)
         pos += b.shape[0]
-    return sg, t, n, n_lines
+    return sg, t, n, n_lines, None
 
 
 def cut_lines(gaf_np: np.ndarray, n_lines_target: int):
@@ -250,7 +273,7 @@ def run_reference_arm(args):
     from oracle.oracle import OracleGraph
 
     cores = os.cpu_count() or 1
-    sg, buf, nbytes, n_lines = make_inputs(args.workload, 0, world, pinned=False)
+    sg, buf, nbytes, n_lines, _ = make_inputs(args.workload, 0, world, pinned=False)
     with tempfile.TemporaryDirectory() as d:
         gp = os.path.join(d, "g.gfa")
         sg.write_gfa(gp)
@@ -313,7 +336,7 @@ def main():
     from pantas_b200.gfa_device import DeviceGfa
 
     K, W = args.steps, max(args.warmup, 3)
-    sg, pinned, nbytes, n_lines = make_inputs(args.workload, rank, world)
+    sg, pinned, nbytes, n_lines, chunks = make_inputs(args.workload, rank, world, device=dev)
     if args.tables:
         args.no_parity = args.no_cli = True
     if not pinned.is_pinned():
@@ -351,9 +374,12 @@ def main():
 
     # chunks of at most 3 GiB (one launch each; pt_process_chunk takes < 3.75 GiB), cut at line ends; every chunk in its own
     # (16-byte aligned) device buffer
-    chunks = []
     view_all = pinned.numpy()
     pos = 0
+    if chunks is None:
+        chunks = []
+    else:
+        pos = nbytes                                          # (streamed input: the chunks are on the device already)
     while pos < nbytes:
         end = min(pos + (3 << 30), nbytes)
         if end < nbytes:

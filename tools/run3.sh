@@ -1,5 +1,4 @@
 set -x
 mkdir -p gpurun_out
-N=${N:-4}
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 tools/prof_reduce.py > gpurun_out/prof_reduce_n$N.log 2>&1
-grep -v "^W\|OMP" gpurun_out/prof_reduce_n$N.log | tail -20
+nproc; free -g | head -2
+timeout 800 python bench.py --workload gene-panel-500M --steps 2 --warmup 3 --no-cli --no-cpu-baseline > gpurun_out/bench_genepanel_500M.json 2> gpurun_out/bench_gp500.err; tail -c 1500 gpurun_out/bench_genepanel_500M.json; tail -5 gpurun_out/bench_gp500.err
