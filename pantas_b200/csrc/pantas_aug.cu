@@ -50,9 +50,9 @@ struct pt_ctx {
     uint64_t n_edges;
     uint64_t novel_cap, sparse_cap, ovf_cap;
     bool epoch_open;             // 32-bit epoch state may be non-zero
+    bool have_totals;            // an epoch has been folded into the 64-bit totals since the last reset
     uint64_t epoch_end;          // highest file offset seen in the open epoch
     uint64_t folds;
-    unsigned long long* cursor;         // 2 compaction cursors
     uint8_t* stage[2];
     uint64_t stage_bytes;
     int64_t next_ticket;
@@ -104,10 +104,10 @@ static int grid_for(uint64_t n, int threads, int cap_blocks) {
 static void free_graph_tables(pt_ctx* ctx) {
     Tables& T = ctx->T;
     cudaFree(T.nodes); cudaFree(T.st32); cudaFree(T.len_full); cudaFree(T.il_ex32); cudaFree(T.ol_ex32); cudaFree(T.ovf);
-    cudaFree(T.ovf_edge); cudaFree(T.inl_edge); cudaFree(T.novel); cudaFree(T.sparse); cudaFree(T.t64); cudaFree(T.il_ex64);
+    cudaFree(T.ovf_edge); cudaFree(T.inl_edge); cudaFree(T.novel); cudaFree(T.sparse); cudaFree(T.novel_list); cudaFree(T.sparse_list); cudaFree(T.t64); cudaFree(T.il_ex64);
     cudaFree(T.ol_ex64); cudaFree(T.il_st64); cudaFree(T.ol_st64); cudaFree(T.rc64);
     T.nodes = NULL; T.st32 = NULL; T.len_full = NULL; T.il_ex32 = T.ol_ex32 = NULL; T.ovf = NULL; T.ovf_edge = T.inl_edge = NULL;
-    T.novel = T.sparse = NULL; T.t64 = T.il_ex64 = T.ol_ex64 = NULL; T.il_st64 = T.ol_st64 = NULL; T.rc64 = NULL;
+    T.novel = T.sparse = NULL; T.novel_list = T.sparse_list = NULL; T.t64 = T.il_ex64 = T.ol_ex64 = NULL; T.il_st64 = T.ol_st64 = NULL; T.rc64 = NULL;
 }
 
 // Keep the node table in the L2: persisting access-policy window on the context's stream (the GAF stream itself is
@@ -143,6 +143,7 @@ static int fold_epoch(pt_ctx* ctx) {
     ctx->launches += 1;
     ctx->folds += 1;
     ctx->epoch_open = false;
+    ctx->have_totals = true;
     return 0;
 }
 
@@ -211,7 +212,7 @@ const char* pt_strerror(int code) {
 }
 
 static void destroy_ctx_objects(pt_ctx* ctx) {
-    cudaFree(ctx->T.sc); cudaFree(ctx->T.deferred); cudaFree(ctx->T.team_tile); cudaFree(ctx->cursor);
+    cudaFree(ctx->T.sc); cudaFree(ctx->T.deferred); cudaFree(ctx->T.team_tile);
     cudaFree(ctx->stage[0]); cudaFree(ctx->stage[1]);
     for (int k = 0; k < 2; k++) {
         if (ctx->ev_copied[k]) cudaEventDestroy(ctx->ev_copied[k]);
@@ -251,7 +252,6 @@ int pt_create(int device, pt_ctx** out) {
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_t0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_t1);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->T.sc, SC_COUNT * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->cursor, 2 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->T.team_tile, ctx->T.team_cap * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(ctx->T.team_tile, 0, ctx->T.team_cap * sizeof(uint32_t));
     if (e != cudaSuccess) {
@@ -314,6 +314,7 @@ static int reset_counts_impl(pt_ctx* ctx) {
     CK(cudaGetLastError());
     ctx->launches += 5;
     ctx->epoch_open = false;
+    ctx->have_totals = false;
     ctx->epoch_end = 0;
     T.epoch_base = 0;
     return 0;
@@ -350,6 +351,8 @@ static int set_graph_impl(pt_ctx* ctx, const uint32_t* node_len, uint64_t n_node
     CK(cudaMalloc(&T.rc64, (n_edges ? n_edges : 1) * sizeof(long long)));
     CK(cudaMalloc(&T.novel, ctx->novel_cap * sizeof(SideSlot)));
     CK(cudaMalloc(&T.sparse, ctx->sparse_cap * sizeof(SideSlot)));
+    CK(cudaMalloc(&T.novel_list, ctx->novel_cap * sizeof(uint32_t)));
+    CK(cudaMalloc(&T.sparse_list, ctx->sparse_cap * sizeof(uint32_t)));
 
     CK(cudaMalloc(d_len, n_nodes * sizeof(uint32_t)));
     CK(cudaMalloc(d_keys, (n_edges ? n_edges : 1) * sizeof(uint64_t)));
@@ -568,13 +571,13 @@ int pt_export_dense(pt_ctx* ctx, int64_t* sums_dev, uint64_t sums_len, int64_t* 
     if (!sums_dev || !stamps_dev || sums_len < 3 * N + E + 4 || stamps_len < 2 * N)
         return fail_msg(ctx, PT_ERR_ARG, "pt_export_dense: buffers too small");
     CK(cudaSetDevice(ctx->device));
-    int rc = fold_epoch(ctx);
-    if (rc) return rc;
+    // (no fold: the export kernels add the open epoch's 32-bit state to the 64-bit totals on the fly, the tables stay as they are)
+    const uint32_t flags = (ctx->have_totals ? EXP_TOTALS : 0u) | (ctx->epoch_open ? EXP_LIVE : 0u);
     const int cap = ctx->sm_count * 8;
-    export_nodes_kernel<<<grid_for(N > E ? N : E, 256, cap), 256, 0, ctx->stream>>>(ctx->T, (long long*)sums_dev, (long long*)stamps_dev, E);
-    export_inline_kernel<<<grid_for(N, 256, cap), 256, 0, ctx->stream>>>(ctx->T, (long long*)sums_dev);
+    export_nodes_kernel<<<grid_for(N > E ? N : E, 256, cap), 256, 0, ctx->stream>>>(ctx->T, (long long*)sums_dev, (long long*)stamps_dev, E, flags);
+    export_inline_kernel<<<grid_for(N, 256, cap), 256, 0, ctx->stream>>>(ctx->T, (long long*)sums_dev, flags);
     export_ovf_kernel<<<grid_for(ctx->ovf_cap, 256, cap), 256, 0, ctx->stream>>>(ctx->T, (long long*)sums_dev);
-    export_novel_ends_kernel<<<grid_for(ctx->novel_cap, 256, cap), 256, 0, ctx->stream>>>(ctx->T, (long long*)sums_dev);
+    export_novel_ends_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(ctx->T, (long long*)sums_dev);
     CK(cudaGetLastError());
     ctx->launches += 4;
     return 0;
@@ -584,15 +587,17 @@ int pt_export_side(pt_ctx* ctx, uint64_t* novel_dev, uint64_t novel_rows, uint64
     if (!ctx || !ctx->have_graph) return fail_msg(ctx, PT_ERR_STATE, "pt_export_side: no graph");
     CK(cudaSetDevice(ctx->device));
     const int cap = ctx->sm_count * 8;
-    CK(cudaMemsetAsync(ctx->cursor, 0, 2 * sizeof(unsigned long long), ctx->stream));
-    if (novel_rows && novel_dev)
-        compact_side_kernel<<<grid_for(ctx->novel_cap, 256, cap), 256, 0, ctx->stream>>>(
-            ctx->T.novel, ctx->novel_cap, (unsigned long long*)novel_dev, novel_rows, ctx->cursor);
-    if (sparse_rows && sparse_dev)
-        compact_side_kernel<<<grid_for(ctx->sparse_cap, 256, cap), 256, 0, ctx->stream>>>(
-            ctx->T.sparse, ctx->sparse_cap, (unsigned long long*)sparse_dev, sparse_rows, ctx->cursor + 1);
+    if (novel_rows && novel_dev) {
+        compact_side_kernel<<<grid_for(novel_rows, 256, cap), 256, 0, ctx->stream>>>(
+            ctx->T.novel, ctx->T.novel_list, novel_rows, (unsigned long long*)novel_dev, novel_rows);
+        ctx->launches += 1;
+    }
+    if (sparse_rows && sparse_dev) {
+        compact_side_kernel<<<grid_for(sparse_rows, 256, cap), 256, 0, ctx->stream>>>(
+            ctx->T.sparse, ctx->T.sparse_list, sparse_rows, (unsigned long long*)sparse_dev, sparse_rows);
+        ctx->launches += 1;
+    }
     CK(cudaGetLastError());
-    ctx->launches += 2;
     return 0;
 }
 

@@ -86,6 +86,8 @@ struct Tables {
     uint32_t* inl_edge;            // [2N] inline slot -> edge index (fold only)
     SideSlot* novel;
     SideSlot* sparse;
+    uint32_t* novel_list;          // [novel cap] slots in use, in claim order (export walks these instead of the whole table)
+    uint32_t* sparse_list;
     unsigned long long* sc;
     uint32_t* deferred;            // chunk-relative starts of records redone from global memory
     uint32_t* team_tile;           // [team_cap] tile every team of the running fast kernel works on (low-water mark)
@@ -120,7 +122,7 @@ __device__ __forceinline__ void report_error(const Tables& T, int code, int64_t 
 
 // insert-or-increment in a 64-bit-key open-addressing table (linear probing, CAS claim); out of line: rare, and the hot
 // loops stay small
-__device__ __noinline__ void side_add(SideSlot* tab, uint64_t mask, unsigned long long* used, uint64_t key,
+__device__ __noinline__ void side_add(SideSlot* tab, uint64_t mask, unsigned long long* used, uint32_t* list, uint64_t key,
                                       uint64_t stamp, unsigned long long* sc, int full_code) {
     uint64_t h = mix64(key) & mask;
     for (uint64_t probes = 0; probes <= mask; probes++) {
@@ -129,6 +131,7 @@ __device__ __noinline__ void side_add(SideSlot* tab, uint64_t mask, unsigned lon
             k = atomicCAS(&tab[h].key, KEY_EMPTY, (unsigned long long)key);
             if (k == KEY_EMPTY) {
                 unsigned long long n = atomicAdd(used, 1ull);
+                if (n <= mask) list[n] = (uint32_t)h;
                 if (n * 4 >= (mask + 1) * 3) report_error_sc(sc, full_code, (int64_t)(stamp >> 2));
                 k = key;
             }
@@ -202,7 +205,7 @@ struct DevSink {
             if (k == KEY_EMPTY) break;
             h = (h + 1) & T.ovf_mask;
         }
-        side_add(T.novel, T.novel_mask, &T.sc[SC_NOVEL_USED], key, stamp, T.sc, pt::PT_X_NOVEL_FULL);
+        side_add(T.novel, T.novel_mask, &T.sc[SC_NOVEL_USED], T.novel_list, key, stamp, T.sc, pt::PT_X_NOVEL_FULL);
     }
     // (counting ops - 1) of a node occurrence that has an in-link (il) / an out-link (ol) in its read
     __device__ __forceinline__ void extras(uint32_t idx, int32_t il_ex, int32_t ol_ex) {
@@ -240,7 +243,7 @@ struct DevSink {
         const int64_t bias = 1ll << 30;
         if (pos < -bias || pos >= bias) { report_error(T, pt::PT_U_POSITION, (int64_t)(stamp >> 2)); return; }
         const uint64_t key = ((uint64_t)idx << 32) | ((uint64_t)dir << 31) | (uint64_t)(pos + bias);
-        side_add(T.sparse, T.sparse_mask, &T.sc[SC_SPARSE_USED], key, stamp, T.sc, pt::PT_X_SPARSE_FULL);
+        side_add(T.sparse, T.sparse_mask, &T.sc[SC_SPARSE_USED], T.sparse_list, key, stamp, T.sc, pt::PT_X_SPARSE_FULL);
     }
     // count_node(a) was called for this occurrence already: move its 1 from t to the link's counter
     __device__ __forceinline__ void edge(uint32_t a, uint32_t b, uint64_t stamp, const EdgePf& pf) {
@@ -399,19 +402,44 @@ __global__ void reset_teams_kernel(Tables T) {
 // ---- export.  Flat layout of include/pantas_aug.h: sums = [nc | il_adj | ol_adj | rc | rej, n_lines, 0, 0] with
 // IL[v][0] = nc + il_adj, OL[v][len] = nc + ol_adj; stamps = [il | ol].  Step 1 writes the per-node terms, steps 2..4
 // scatter every link's count to its two ends (header comment: NC, IL, OL as sums of RC).
-__global__ void export_nodes_kernel(Tables T, long long* sums, long long* stamps, uint64_t n_edges) {
+// The export reads, it does not fold: a value is its 64-bit total (EXP_TOTALS: at least one epoch has been folded since the
+// reset -- the arrays are all zero / unset otherwise and are not read) plus the open epoch's 32-bit state (EXP_LIVE).
+enum : uint32_t { EXP_TOTALS = 1u, EXP_LIVE = 2u };
+__global__ void export_nodes_kernel(Tables T, long long* sums, long long* stamps, uint64_t n_edges, uint32_t flags) {
     const uint64_t N = T.n_nodes;
+    const bool totals = (flags & EXP_TOTALS) != 0u, live = (flags & EXP_LIVE) != 0u;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
-        const long long t = T.t64[i];
+        long long t = 0, il_ex = 0, ol_ex = 0;
+        unsigned long long il_st = STAMP_UNSET, ol_st = STAMP_UNSET;
+        if (totals) {
+            t = T.t64[i];
+            il_ex = T.il_ex64[i];
+            ol_ex = T.ol_ex64[i];
+            il_st = T.il_st64[i];
+            ol_st = T.ol_st64[i];
+        }
+        if (live) {
+            t += (long long)(int32_t)T.nodes[i].t;         // the exact path moves a count out of t again (DevSink::edge)
+            il_ex += T.il_ex32[i];
+            ol_ex += T.ol_ex32[i];
+            const Stamp32 s = T.st32[i];
+            if (s.il != UNSET32) {
+                const unsigned long long v = ((unsigned long long)(T.epoch_base + (int64_t)s.il) << 2) | 1ull;
+                if (v < il_st) il_st = v;
+            }
+            if (s.ol != UNSET32) {
+                const unsigned long long v = ((unsigned long long)(T.epoch_base + (int64_t)s.ol) << 2) | 1ull;
+                if (v < ol_st) ol_st = v;
+            }
+        }
         sums[i] = t;                                       // + links leaving i
-        sums[N + i] = T.il_ex64[i] - t;                    // + links entering i - links leaving i
-        sums[2 * N + i] = T.ol_ex64[i] - t;
-        stamps[i] = (long long)T.il_st64[i];
-        stamps[N + i] = (long long)T.ol_st64[i];
+        sums[N + i] = il_ex - t;                           // + links entering i - links leaving i
+        sums[2 * N + i] = ol_ex - t;
+        stamps[i] = (long long)il_st;
+        stamps[N + i] = (long long)ol_st;
     }
-    long long* rc = sums + 3 * N;
-    for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < n_edges; e += (uint64_t)gridDim.x * blockDim.x)
-        rc[e] = T.rc64[e];
+    long long* rc = sums + 3 * N;                          // (every link is written again by the kernel that owns its counter)
+    for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < n_edges; e += (uint64_t)gridDim.x * blockDim.x) rc[e] = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         long long* tail = sums + 3 * N + n_edges;
         tail[0] = (long long)T.sc[SC_REJ];
@@ -427,14 +455,24 @@ __device__ __forceinline__ void export_link_ends(long long* sums, uint64_t N, ui
     atomicAdd(&s[N + from], 0ull - c);                     // il_adj[from] = IL - NC
     atomicAdd(&s[N + to], c);                              // IL[to][0]
 }
-// after export_nodes_kernel (same stream): inline links (their 64-bit totals are in rc64 after the fold)
-__global__ void export_inline_kernel(Tables T, long long* sums) {
+// after export_nodes_kernel (same stream): inline links -- folded epochs in rc64, the open epoch in the node's rc0 / rc1
+__global__ void export_inline_kernel(Tables T, long long* sums, uint32_t flags) {
     const uint64_t N = T.n_nodes;
+    const bool totals = (flags & EXP_TOTALS) != 0u, live = (flags & EXP_LIVE) != 0u;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t meta = T.nodes[i].meta;
-        const uint32_t e0 = T.inl_edge[2 * i], e1 = T.inl_edge[2 * i + 1];
-        if (e0 != NO_EDGE) export_link_ends(sums, N, i, (uint64_t)((int64_t)i + sext10((meta >> META_D0_SHIFT) & META_D_MASK)), (unsigned long long)T.rc64[e0]);
-        if (e1 != NO_EDGE) export_link_ends(sums, N, i, (uint64_t)((int64_t)i + sext10((meta >> META_D1_SHIFT) & META_D_MASK)), (unsigned long long)T.rc64[e1]);
+        const uint2 ee = *reinterpret_cast<const uint2*>(&T.inl_edge[2 * i]);
+        if ((ee.x & ee.y) == NO_EDGE) continue;
+        const NodeHot r = T.nodes[i];
+        if (ee.x != NO_EDGE) {
+            const unsigned long long c = (totals ? (unsigned long long)T.rc64[ee.x] : 0ull) + (live ? (unsigned long long)r.rc0 : 0ull);
+            sums[3 * N + ee.x] = (long long)c;
+            export_link_ends(sums, N, i, (uint64_t)((int64_t)i + sext10((r.meta >> META_D0_SHIFT) & META_D_MASK)), c);
+        }
+        if (ee.y != NO_EDGE) {
+            const unsigned long long c = (totals ? (unsigned long long)T.rc64[ee.y] : 0ull) + (live ? (unsigned long long)r.rc1 : 0ull);
+            sums[3 * N + ee.y] = (long long)c;
+            export_link_ends(sums, N, i, (uint64_t)((int64_t)i + sext10((r.meta >> META_D1_SHIFT) & META_D_MASK)), c);
+        }
     }
 }
 // links held by the ovf table
@@ -448,24 +486,22 @@ __global__ void export_ovf_kernel(Tables T, long long* sums) {
         export_link_ends(sums, N, v.key >> 32, v.key & 0xFFFFFFFFull, v.count);
     }
 }
-// links that are not in the GFA
+// links that are not in the GFA (the slots in use are listed: no scan of the whole table)
 __global__ void export_novel_ends_kernel(Tables T, long long* sums) {
     const uint64_t N = T.n_nodes;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i <= T.novel_mask; i += (uint64_t)gridDim.x * blockDim.x) {
-        const SideSlot v = T.novel[i];
-        if (v.key != KEY_EMPTY) export_link_ends(sums, N, v.key >> 32, v.key & 0xFFFFFFFFull, v.count);
+    const uint64_t used = min((uint64_t)T.sc[SC_NOVEL_USED], T.novel_mask + 1);
+    for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < used; j += (uint64_t)gridDim.x * blockDim.x) {
+        const SideSlot v = T.novel[T.novel_list[j]];
+        export_link_ends(sums, N, v.key >> 32, v.key & 0xFFFFFFFFull, v.count);
     }
 }
-__global__ void compact_side_kernel(const SideSlot* s, uint64_t cap, unsigned long long* out, uint64_t rows,
-                                    unsigned long long* cursor) {
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
-        const SideSlot v = s[i];
-        if (v.key == KEY_EMPTY) continue;
-        const unsigned long long j = atomicAdd(cursor, 1ull);
-        if (j < rows) {
-            out[3 * j] = v.key;
-            out[3 * j + 1] = v.count;
-            out[3 * j + 2] = v.stamp;
-        }
+// rows {key, count, stamp} of the slots in use, in claim order
+__global__ void compact_side_kernel(const SideSlot* s, const uint32_t* list, uint64_t used, unsigned long long* out, uint64_t rows) {
+    const uint64_t n = used < rows ? used : rows;
+    for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x) {
+        const SideSlot v = s[list[j]];
+        out[3 * j] = v.key;
+        out[3 * j + 1] = v.count;
+        out[3 * j + 2] = v.stamp;
     }
 }

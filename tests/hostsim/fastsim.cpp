@@ -75,6 +75,8 @@ int fastsim_run(const uint8_t* gaf, uint64_t nbytes, uint64_t file_off, int64_t 
     T.rc64 = zalloc<long long>(E);
     T.novel = zalloc<SideSlot>(novel_cap);
     T.sparse = zalloc<SideSlot>(sparse_cap);
+    T.novel_list = zalloc<uint32_t>(novel_cap);
+    T.sparse_list = zalloc<uint32_t>(sparse_cap);
     T.sc = zalloc<unsigned long long>(SC_COUNT);
     T.deferred_cap = nbytes / 2 + 4096;
     T.deferred = zalloc<uint32_t>(T.deferred_cap);
@@ -106,11 +108,12 @@ int fastsim_run(const uint8_t* gaf, uint64_t nbytes, uint64_t file_off, int64_t 
     memset(&A, 0, sizeof A);
     A.loose = (geo + grid) & 1u;      // both barrier modes get exercised
     if (getenv("FASTSIM_ABLATE")) A.ablate = (uint32_t)atoi(getenv("FASTSIM_ABLATE"));
-    A.gaf = dev;
-    A.nbytes = nbytes;
-    A.file_off = (int64_t)file_off;
     A.thr = thr;
-    if (nbytes) {
+    auto run_chunk = [&](const uint8_t* p, uint64_t n, uint64_t off) {
+        if (!n) return;
+        A.gaf = p;
+        A.nbytes = n;
+        A.file_off = (int64_t)off;
         typedef teamp::Geo<1024, 256, 96, 2, 1> G0;
         typedef teamp::Geo<4096, 512, 256, 3, 1> G1;
         typedef teamp::Geo<8192, 1024, 512, 10, 1> G2;
@@ -119,22 +122,49 @@ int fastsim_run(const uint8_t* gaf, uint64_t nbytes, uint64_t file_off, int64_t 
         else run_fast<G2>(grid, A, T);
         emu::launch(2, 128, 0, [&] { augment_deferred_kernel(A, T); });
         emu::launch(2, 64, 0, [&] { end_chunk_kernel(T); });
+    };
+    // every third run is two chunks with an epoch fold between them (what launch_chunk does every < 4 GiB of GAF): the
+    // export below then has to add the open epoch's 32-bit state to the folded 64-bit totals
+    uint64_t mid = 0;
+    if ((geo + grid) % 3u == 0u && nbytes > 2) {
+        const void* nl = memchr(gaf + nbytes / 2, '\n', nbytes - nbytes / 2 - 1);
+        if (nl) mid = (uint64_t)((const uint8_t*)nl - gaf) + 1;
+    }
+    bool folded = false;
+    uint8_t* raw2 = NULL;
+    if (mid) {
+        run_chunk(dev, mid, file_off);
+        emu::launch(KG, KB, 0, [&] { fold_epoch_kernel(T); });
+        folded = true;
+        T.epoch_base = (int64_t)(file_off + mid);
+        raw2 = (uint8_t*)malloc(nbytes - mid + 96);
+        uint8_t* dev2 = (uint8_t*)(((uintptr_t)raw2 + 15) & ~(uintptr_t)15);
+        memset(dev2, 0xEE, nbytes - mid + 64);
+        memcpy(dev2, gaf + mid, nbytes - mid);
+        run_chunk(dev2, nbytes - mid, file_off + mid);
+    } else {
+        run_chunk(dev, nbytes, file_off);
     }
     // ---- pt_export_dense / pt_export_side
-    emu::launch(KG, KB, 0, [&] { fold_epoch_kernel(T); });
+    // (every other run folds the epoch first, like a chunk that opens a new epoch would: the export then reads the 64-bit
+    // totals instead of the open epoch's 32-bit state)
+    uint32_t flags = EXP_LIVE | (folded ? EXP_TOTALS : 0u);
+    if ((geo + grid) & 4u) {
+        emu::launch(KG, KB, 0, [&] { fold_epoch_kernel(T); });
+        flags = EXP_TOTALS;
+    }
     out->sums = (int64_t*)calloc(3 * N + E + 4, sizeof(int64_t));
     out->stamps = (int64_t*)calloc(2 * N + 1, sizeof(int64_t));
-    emu::launch(KG, KB, 0, [&] { export_nodes_kernel(T, (long long*)out->sums, (long long*)out->stamps, E); });
-    emu::launch(KG, KB, 0, [&] { export_inline_kernel(T, (long long*)out->sums); });
+    emu::launch(KG, KB, 0, [&] { export_nodes_kernel(T, (long long*)out->sums, (long long*)out->stamps, E, flags); });
+    emu::launch(KG, KB, 0, [&] { export_inline_kernel(T, (long long*)out->sums, flags); });
     emu::launch(KG, KB, 0, [&] { export_ovf_kernel(T, (long long*)out->sums); });
     emu::launch(KG, KB, 0, [&] { export_novel_ends_kernel(T, (long long*)out->sums); });
-    unsigned long long cursor[2] = {0, 0};
+    out->n_novel = T.sc[SC_NOVEL_USED] < novel_cap ? T.sc[SC_NOVEL_USED] : novel_cap;
+    out->n_sparse = T.sc[SC_SPARSE_USED] < sparse_cap ? T.sc[SC_SPARSE_USED] : sparse_cap;
     out->novel = (uint64_t*)calloc(3 * novel_cap + 1, sizeof(uint64_t));
     out->sparse = (uint64_t*)calloc(3 * sparse_cap + 1, sizeof(uint64_t));
-    emu::launch(KG, KB, 0, [&] { compact_side_kernel(T.novel, novel_cap, (unsigned long long*)out->novel, novel_cap, &cursor[0]); });
-    emu::launch(KG, KB, 0, [&] { compact_side_kernel(T.sparse, sparse_cap, (unsigned long long*)out->sparse, sparse_cap, &cursor[1]); });
-    out->n_novel = cursor[0];
-    out->n_sparse = cursor[1];
+    emu::launch(KG, KB, 0, [&] { compact_side_kernel(T.novel, T.novel_list, out->n_novel, (unsigned long long*)out->novel, novel_cap); });
+    emu::launch(KG, KB, 0, [&] { compact_side_kernel(T.sparse, T.sparse_list, out->n_sparse, (unsigned long long*)out->sparse, sparse_cap); });
     out->n_deferred = T.sc[SC_DEFERRED_TOTAL];
     for (int k = 0; k < 16; k++) out->why[k] = T.sc[SC_WHY + k];
     if (T.sc[SC_ERR] != ~0ull) {
@@ -145,8 +175,9 @@ int fastsim_run(const uint8_t* gaf, uint64_t nbytes, uint64_t file_off, int64_t 
         out->err_code = 0;
     }
     free(raw);
+    free(raw2);
     free(T.nodes); free(T.st32); free(T.len_full); free(T.il_ex32); free(T.ol_ex32); free(T.inl_edge); free(T.t64); free(T.il_ex64);
-    free(T.ol_ex64); free(T.il_st64); free(T.ol_st64); free(T.rc64); free(T.novel); free(T.sparse); free(T.sc); free(T.deferred);
+    free(T.ol_ex64); free(T.il_st64); free(T.ol_st64); free(T.rc64); free(T.novel); free(T.sparse); free(T.novel_list); free(T.sparse_list); free(T.sc); free(T.deferred);
     free(T.ovf); free(T.ovf_edge); free(T.team_tile);
     return 0;
 }
