@@ -330,6 +330,13 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
+    numa = None
+    if world > 1 and os.environ.get("PANTAS_NUMA", "1") != "0":
+        # a rank's pinned buffers belong on its GPU's socket (first touch): bind before anything is allocated.  Not at N = 1:
+        # the CPU baseline of that run wants every core.
+        from pantas_b200.numa import bind_to_gpu_node
+
+        numa = bind_to_gpu_node(local_rank)
 
     from pantas_b200.dist import reduce_results, rows_to_host
     from pantas_b200.engine import AugmentEngine
@@ -568,6 +575,7 @@ def main():
             "gaf_gb_per_s": total_bytes / step_ms / 1e6,
             "wall_ms_per_step_incl_reset": 1e3 * (t_wall1 - t_wall0) / K,
             "gpu_launches": int(launches),
+            "numa": numa,
             "deferred_records": st["deferred_lines"],
             "gfa_pass1_device_ms": gfa_load_ms,
             "clocks": clocks,

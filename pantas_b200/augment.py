@@ -195,9 +195,14 @@ def main(argv, out=None, err=None) -> int:
         torch.cuda.set_device(local_rank)
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        eng = AugmentEngine(local_rank)
+        device = local_rank
     else:
-        eng = AugmentEngine(int(os.environ.get("PANTAS_DEVICE", "0")))
+        device = int(os.environ.get("PANTAS_DEVICE", "0"))
+    if os.environ.get("PANTAS_NUMA", "1") != "0":
+        from .numa import bind_to_gpu_node
+
+        bind_to_gpu_node(device)                           # before the first pinned allocation (first touch places the pages)
+    eng = AugmentEngine(device)
 
     print("Read GFA", file=err) if rank == 0 else None    # REF:120
     dg = None
