@@ -418,7 +418,7 @@ def main():
     def pin_out(k, t):
         h = pinned_out.get(k)
         if h is None or h.numel() < t.numel():
-            h = torch.empty(max(t.numel(), 1), dtype=t.dtype).pin_memory()
+            h = torch.empty(max(t.numel(), 1), dtype=t.dtype, pin_memory=True)
             pinned_out[k] = h
         v = h[: t.numel()].view(t.shape)
         v.copy_(t, non_blocking=True)

@@ -73,6 +73,7 @@ struct ChunkArgs {
     int64_t file_off;
     int64_t thr;
     uint32_t n_tiles;
+    uint32_t tile_bytes;    // bytes per tile of the fast path: a multiple of 16, <= the geometry's TILE
     uint32_t stream_hint;   // bit 0: load the GAF with an L2 evict-first policy
     uint32_t loose;         // 1: team-level barriers inside a tile, one CTA-wide barrier per tile (PANTAS_LOOSE)
     uint32_t ablate;        // diagnostics (PANTAS_ABLATE): 0 = the whole pass, k = every tile stops after phase k (timing only)

@@ -60,6 +60,9 @@ struct pt_ctx {
     uint32_t geo;                // tile bytes of the fast path (PANTAS_TEAM_TILE)
     int teams_per_sm;
     uint32_t ablate;             // PANTAS_ABLATE (diagnostics)
+    uint32_t tile_bytes_env;     // PANTAS_TILE_BYTES: fixed tile length (0: from the record length)
+    double rec_len_hint;         // average bytes per GAF record seen so far (0: unknown)
+    uint64_t bytes_since_reset;  // GAF bytes enqueued since the last reset
     bool l2_window;              // an access-policy window over the node table is set on `stream`
     size_t persist_max, window_max;
     bool profile;
@@ -148,12 +151,14 @@ static int fold_epoch(pt_ctx* ctx) {
 }
 
 // the fast path's geometries: Geo<tile, look-ahead, step-list entries, teams per CTA, CTAs per SM>
-typedef teamp::Geo<8192, 1024, 512, 10, 1> GeoP;     // production: one CTA of ten teams per SM (measured best, profiles/r02_geometry_sweep.txt)
+typedef teamp::Geo<9216, 1024, 512, 10, 1> GeoP;     // production: one CTA of ten teams per SM, tiles of up to 9 KiB (measured best, profiles/r02_geometry_sweep.txt)
 typedef teamp::Geo<7168, 1024, 448, 5, 2> GeoQ;
 typedef teamp::Geo<6144, 1024, 384, 6, 2> GeoR;
 typedef teamp::Geo<12288, 1024, 768, 7, 1> GeoS;
 typedef teamp::Geo<8192, 1024, 512, 5, 2> GeoU;      // two CTAs of five teams per SM
 typedef teamp::Geo<1024, 256, 96, 2, 1> GeoT;        // tests: many tile boundaries, records longer than the look-ahead
+
+static const double RECORDS_PER_TILE = 30.0;     // measured optimum on two record lengths (274 B, 300 B): 29.9 - 30.9
 
 template <class G>
 static int launch_team(pt_ctx* ctx, ChunkArgs A, const Tables& T) {
@@ -169,7 +174,16 @@ static int launch_team(pt_ctx* ctx, ChunkArgs A, const Tables& T) {
         if (want && (int)want < occ) occ = (int)want;
         ctx->teams_per_sm = occ;                           // CTAs of G::NT teams
     }
-    const uint64_t nt = (A.nbytes + G::TILE - 1) / G::TILE;
+    // Tile length: `records` and `walk` give every record of a tile one lane of one warp, so the best tile carries just under
+    // 32 records (measured: profiles/r02_geometry_sweep.txt).  The record length comes from the host buffer (pt_process_host)
+    // or from the counters of what this context has processed so far; until either is known, 8 KiB.
+    uint32_t tb = ctx->tile_bytes_env;
+    if (!tb) tb = ctx->rec_len_hint > 0.0 ? (uint32_t)(ctx->rec_len_hint * RECORDS_PER_TILE) : 8192u;
+    tb = (tb + 15u) & ~15u;
+    if (tb > (uint32_t)G::TILE) tb = (uint32_t)G::TILE;
+    if (tb < 1024u) tb = (uint32_t)G::TILE < 1024u ? (uint32_t)G::TILE : 1024u;
+    A.tile_bytes = tb;
+    const uint64_t nt = (A.nbytes + tb - 1) / tb;
     if (nt > 0xFFFFFFF0ull) return fail_msg(ctx, PT_ERR_ARG, "chunk too large");
     A.n_tiles = (uint32_t)nt;
     uint64_t g = (uint64_t)ctx->sm_count * ctx->teams_per_sm;
@@ -262,6 +276,7 @@ int pt_create(int device, pt_ctx** out) {
     ctx->stage_bytes = (uint64_t)env_u32("PANTAS_STAGE_MB", 256) << 20;
     ctx->geo = env_u32("PANTAS_TEAM_TILE", 8192);
     ctx->ablate = env_u32("PANTAS_ABLATE", 0);
+    ctx->tile_bytes_env = env_u32("PANTAS_TILE_BYTES", 0);
     *out = ctx;
     return 0;
 }
@@ -315,6 +330,7 @@ static int reset_counts_impl(pt_ctx* ctx) {
     ctx->launches += 5;
     ctx->epoch_open = false;
     ctx->have_totals = false;
+    ctx->bytes_since_reset = 0;
     ctx->epoch_end = 0;
     T.epoch_base = 0;
     return 0;
@@ -429,6 +445,7 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
         ctx->epoch_end = file_offset;
     }
     if (file_offset + nbytes > ctx->epoch_end) ctx->epoch_end = file_offset + nbytes;
+    ctx->bytes_since_reset += nbytes;
     // second-pass list: records the fast path hands over.  The shortest record the reference accepts has 12 one-byte
     // columns, 11 separators and a line break (24 bytes), so this holds every record of the chunk.
     const uint64_t want = nbytes / 24 + 4096;
@@ -509,6 +526,15 @@ int64_t pt_process_host(pt_ctx* ctx, const uint8_t* gaf_host, uint64_t nbytes, u
         CK(cudaMalloc(&ctx->stage[0], ctx->stage_bytes + 16));
         CK(cudaMalloc(&ctx->stage[1], ctx->stage_bytes + 16));
     }
+    if (ctx->rec_len_hint <= 0.0 && nbytes) {                   // record length from the head of the host buffer
+        const uint64_t peek = nbytes < (256u << 10) ? nbytes : (256u << 10);
+        uint64_t lines = 0, last = 0;
+        for (const uint8_t* p = gaf_host; (p = (const uint8_t*)memchr(p, '\n', (size_t)(gaf_host + peek - p))) != NULL; p++) {
+            lines++;
+            last = (uint64_t)(p - gaf_host) + 1;
+        }
+        if (lines >= 8) ctx->rec_len_hint = (double)last / (double)lines;
+    }
     const int64_t ticket = ctx->next_ticket++;
     const int k = (int)(ticket & 1);
     if (ticket >= 2) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[k], 0));   // stage k is free again
@@ -560,6 +586,8 @@ int pt_finalize(pt_ctx* ctx, uint64_t* n_novel, uint64_t* n_sparse) {
     CK(cudaMemcpyAsync(sc, ctx->T.sc, sizeof sc, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
+    if (sc[SC_LINES] >= 1000ull && ctx->bytes_since_reset)      // average record length: sizes the tiles of later chunks
+        ctx->rec_len_hint = (double)ctx->bytes_since_reset / (double)sc[SC_LINES];
     if (n_novel) *n_novel = sc[SC_NOVEL_USED];
     if (n_sparse) *n_sparse = sc[SC_SPARSE_USED];
     return 0;

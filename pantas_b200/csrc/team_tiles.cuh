@@ -325,10 +325,13 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
     uint32_t my_real = 0;                        // records this thread has listed
     int64_t far_base = 0;                        // file offset of buf[0] of the tile that filled the far-link list
 
+    // bytes per tile: G::TILE is what the shared-memory layout holds, the host picks the length (a multiple of 16) so that a
+    // tile carries just under 32 records -- one lane each in `records` and `walk`
+    const uint32_t tile_b = A.tile_bytes;
     auto issue_load = [&](uint32_t tile) {
-        const uint64_t t0 = (uint64_t)tile * G::TILE;
+        const uint64_t t0 = (uint64_t)tile * tile_b;
         const uint64_t lo = tile ? t0 - 16 : 0;
-        const uint64_t hi = min(t0 + G::TILE + G::OV, nbytes16);
+        const uint64_t hi = min(t0 + tile_b + G::OV, nbytes16);
         const uint32_t bytes = (uint32_t)(hi - lo);
         fence_async_smem();
         mbar_expect_tx(&mbar, bytes);
@@ -352,9 +355,9 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
     for (uint32_t round = 0; round < rounds; round++) {
         const uint32_t tile = gteam + round * nteams;
         const bool active = tile < A.n_tiles;
-        const uint64_t t0 = (uint64_t)tile * G::TILE;
-        const uint32_t owned = active ? (uint32_t)min((uint64_t)G::TILE, A.nbytes - t0) : 0u;
-        const uint64_t hi = min(t0 + G::TILE + G::OV, nbytes16);
+        const uint64_t t0 = (uint64_t)tile * tile_b;
+        const uint32_t owned = active ? (uint32_t)min((uint64_t)tile_b, A.nbytes - t0) : 0u;
+        const uint64_t hi = min(t0 + tile_b + G::OV, nbytes16);
         const uint32_t lim = active ? 16u + (uint32_t)(min(hi, A.nbytes) - t0) : 0u;     // data ends here in the buffer
         const int64_t base_off = A.file_off + (int64_t)t0 - 16;            // file offset of buf[0]
         const uint32_t own_end = active ? 16u + owned : 0u;                 // records starting before this are ours
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
         if (tid == 0 && active) {
             // low-water mark of the running kernel (tables.cuh): every tile below it is complete
             const unsigned long long lw = *(volatile unsigned long long*)&T.sc[SC_LWM];
-            const int64_t rel = A.file_off - T.epoch_base + (int64_t)(lw * (unsigned long long)G::TILE);
+            const int64_t rel = A.file_off - T.epoch_base + (int64_t)(lw * (unsigned long long)tile_b);
             s_lwm = rel <= 0 ? 0u : (rel > 0xFFFFFFF0ll ? 0xFFFFFFF0u : (uint32_t)rel);
         }
         if (active) {

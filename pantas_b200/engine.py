@@ -133,7 +133,7 @@ class AugmentEngine:
         for k, t in enumerate(dev):
             h = self._pinned.get(k)
             if h is None or h.numel() < t.numel():
-                h = torch.empty(max(t.numel(), 1), dtype=t.dtype).pin_memory()
+                h = torch.empty(max(t.numel(), 1), dtype=t.dtype, pin_memory=True)
                 self._pinned[k] = h
             v = h[: t.numel()].view(t.shape)
             v.copy_(t, non_blocking=True)

@@ -55,18 +55,11 @@ class DeviceGfa:
         import torch
 
         self = cls(engine)
-        n = os.path.getsize(gfa_file)
-        host = torch.empty(max(n, 1), dtype=torch.uint8).pin_memory()
-        if n:
-            with open(gfa_file, "rb", buffering=0) as f:
-                view = memoryview(host.numpy())
-                got = 0
-                while got < n:
-                    r = f.readinto(view[got:n])
-                    if not r:
-                        break
-                    got += r
-                n = got
+        # (a plain read + one pageable copy: pinning a buffer of the file's size first costs more than it saves for a
+        # file that is read once)
+        arr = np.fromfile(gfa_file, dtype=np.uint8)
+        n = int(arr.shape[0])
+        host = torch.from_numpy(arr) if n else torch.empty(1, dtype=torch.uint8)
         return self._load_from_host(host, n, gfa_file, max_span_factor)
 
     @classmethod
@@ -75,9 +68,7 @@ class DeviceGfa:
 
         self = cls(engine)
         n = len(data)
-        host = torch.empty(max(n, 1), dtype=torch.uint8).pin_memory()
-        if n:
-            host[:n] = torch.frombuffer(bytearray(data), dtype=torch.uint8)
+        host = torch.frombuffer(bytearray(data), dtype=torch.uint8) if n else torch.empty(1, dtype=torch.uint8)
         return self._load_from_host(host, n, "<memory>", max_span_factor)
 
     def _load_from_host(self, host, n: int, name: str, max_span_factor: float) -> "DeviceGfa":
@@ -86,7 +77,7 @@ class DeviceGfa:
         lib, ctx = self.eng.lib, self.eng._ctx
         with torch.cuda.device(dev):
             buf = torch.zeros(n + 64, dtype=torch.uint8, device=dev)
-            buf[:n].copy_(host[:n], non_blocking=True)
+            buf[:n].copy_(host[:n])
             b = buf[:n]
             # ---- line index: universal newlines ('\n', '\r\n', lone '\r'), like `for line in open(path, "r")`
             if n:
@@ -271,7 +262,7 @@ class DeviceGfa:
                 for r in order:
                     k = int(novel[r, 0])
                     extra += f"L\t{(k >> 32) + self.min_id}\t+\t{(k & 0xFFFFFFFF) + self.min_id}\t+\t*\tRC:i:{int(novel[r, 1])}\tID:Z:N\n".encode()
-            host = torch.empty(total + len(extra), dtype=torch.uint8).pin_memory() if total + len(extra) else torch.empty(0, dtype=torch.uint8)
+            host = torch.empty(total + len(extra), dtype=torch.uint8, pin_memory=True) if total + len(extra) else torch.empty(0, dtype=torch.uint8)
             if total:
                 host[:total].copy_(out[:total], non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
