@@ -95,26 +95,63 @@ __device__ __forceinline__ void defer_line(const Tables& T, uint64_t chunk_pos, 
 
 #include "team_tiles.cuh"
 
-// Records that did not fit a tile's look-ahead window: same logic, bytes from global memory.
+// Records the fast path hands over (longer than a tile's look-ahead, or anything unusual): the exact per-record code.  A warp
+// takes a record (the usual case: a handful per chunk, their latency is what counts): all lanes copy its first DEF_STAGE bytes into shared memory with 16-byte loads, lane 0 parses from there
+// (byte-serial parsing straight from global memory pays one L2 round trip per byte); a record that is longer than the stage is
+// parsed again from global memory (LINE_DEFER: nothing was emitted).
+#ifdef PT_EMU
+constexpr int DEF_STAGE = 512;          // (small in the CPU tests: both paths run)
+#else
+constexpr int DEF_STAGE = 2048;
+#endif
 __global__ void __launch_bounds__(128) augment_deferred_kernel(ChunkArgs A, Tables T) {
+    __shared__ __align__(16) uint8_t stage[4][DEF_STAGE];
     DevSink sink(T);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const unsigned long long n = min(T.sc[SC_NDEFER], (unsigned long long)T.deferred_cap);
-    for (unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; j < n;
-         j += (unsigned long long)gridDim.x * blockDim.x) {
+    if (n > 4ull * 4ull * gridDim.x) {
+        // many records (an input the fast path does not like): one record per THREAD, latency hidden by numbers
+        for (unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; j < n;
+             j += (unsigned long long)gridDim.x * blockDim.x) {
+            const uint64_t a = T.deferred[j];
+            const uint64_t a16 = a & ~15ull;
+            pt::LineCtx cx;
+            cx.s = A.gaf + a16;
+            const uint64_t rest = A.nbytes - a16;
+            cx.lim = rest > 0x7ffffff0ull ? 0x7ffffff0 : (int)rest;
+            cx.lim_final = true;
+            cx.base_off = A.file_off + (int64_t)a16;
+            pt::process_line(cx, (int)(a - a16), A.thr, sink);
+        }
+    } else
+    for (unsigned long long j = blockIdx.x * 4ull + warp; j < n; j += (unsigned long long)gridDim.x * 4ull) {
         const uint64_t a = T.deferred[j];
         const uint64_t a16 = a & ~15ull;                     // word loads need an aligned base
-        pt::LineCtx cx;
-        cx.s = A.gaf + a16;
         const uint64_t rest = A.nbytes - a16;
-        cx.lim = rest > 0x7ffffff0ull ? 0x7ffffff0 : (int)rest;
-        cx.lim_final = true;
-        cx.base_off = A.file_off + (int64_t)a16;
-        pt::process_line(cx, (int)(a - a16), A.thr, sink);
+        const uint32_t m = rest < (uint64_t)DEF_STAGE ? (uint32_t)rest : (uint32_t)DEF_STAGE;
+        const uint4* src = reinterpret_cast<const uint4*>(A.gaf + a16);      // (the chunk is readable up to nbytes rounded up to 16)
+        uint4* dst = reinterpret_cast<uint4*>(stage[warp]);
+        for (uint32_t v = lane; v * 16u < m; v += 32u) dst[v] = src[v];
+        __syncwarp();
+        if (lane == 0) {
+            pt::LineCtx cx;
+            cx.s = stage[warp];
+            cx.lim = (int)m;
+            cx.lim_final = (uint64_t)m == rest;
+            cx.base_off = A.file_off + (int64_t)a16;
+            if (pt::process_line(cx, (int)(a - a16), A.thr, sink) == pt::LINE_DEFER) {
+                cx.s = A.gaf + a16;
+                cx.lim = rest > 0x7ffffff0ull ? 0x7ffffff0 : (int)rest;
+                cx.lim_final = true;
+                pt::process_line(cx, (int)(a - a16), A.thr, sink);
+            }
+        }
+        __syncwarp();
     }
     uint32_t r = sink.rej;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-    if ((threadIdx.x & 31) == 0 && r) atomicAdd(&T.sc[SC_REJ], (unsigned long long)r);
+    if (lane == 0 && r) atomicAdd(&T.sc[SC_REJ], (unsigned long long)r);
 }
 
 // After both kernels of a chunk: fold the per-chunk scalars, reset the fast kernel's low-water mark.
