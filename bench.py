@@ -621,11 +621,14 @@ def cli_wall_times(gfa_path: str, gaf_np: np.ndarray, tmpdir: str, n_lines: int)
     ap = os.path.join(tmpdir, "bench.gaf")
     gaf_np.tofile(ap)
     out = {"alignments": n_lines, "gaf_bytes": int(gaf_np.shape[0]), "gfa_bytes": os.path.getsize(gfa_path)}
-    for name, env in (("device_gfa_passes_s", {}), ("python_gfa_passes_s", {"PANTAS_GFA_PASSES": "host"})):
+    for name, env in (("device_gfa_passes_s", {"PANTAS_TIMING": "1"}), ("python_gfa_passes_s", {"PANTAS_GFA_PASSES": "host"})):
         t0 = time.time()
         with open(os.path.join(tmpdir, name + ".gfa"), "wb") as fo:
             p = subprocess.run([sys.executable, script, ap, gfa_path], stdout=fo, stderr=subprocess.PIPE, env=dict(os.environ, **env))
         out[name] = time.time() - t0
+        for ln in p.stderr.decode(errors="replace").splitlines():
+            if ln.startswith("timing: "):
+                out["device_stages"] = ln[8:]              # the rest of the wall clock is interpreter start-up and exit
         if p.returncode != 0:
             out[name] = None
             out["error"] = p.stderr.decode()[-300:]

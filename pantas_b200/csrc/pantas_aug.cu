@@ -273,7 +273,7 @@ int pt_create(int device, pt_ctx** out) {
         free(ctx);
         return PT_ERR_CUDA;
     }
-    ctx->stage_bytes = (uint64_t)env_u32("PANTAS_STAGE_MB", 256) << 20;
+    ctx->stage_bytes = (uint64_t)env_u32("PANTAS_STAGE_MB", 64) << 20;
     ctx->geo = env_u32("PANTAS_TEAM_TILE", 8192);
     ctx->ablate = env_u32("PANTAS_ABLATE", 0);
     ctx->tile_bytes_env = env_u32("PANTAS_TILE_BYTES", 0);

@@ -192,9 +192,10 @@ class DeviceGfa:
         eng.graph = self.graph
 
     # ------------------------------------------------------------------ pass 2
-    def render(self, sums, stamps, novel: np.ndarray, sparse: np.ndarray):
-        """-> pinned uint8 tensor with the augmented GFA (REF:377-427).  sums / stamps: device tensors in the pt_export_dense
-        layout (after the cross-rank reduction, if any); novel / sparse: host rows {key, count, stamp}."""
+    def render_device(self, sums, stamps, novel: np.ndarray, sparse: np.ndarray):
+        """The augmented GFA (REF:377-427) as (uint8 device tensor, its length, bytes of the novel-link lines that follow it).
+        sums / stamps: device tensors in the pt_export_dense layout (after the cross-rank reduction, if any); novel / sparse:
+        host rows {key, count, stamp}."""
         torch = self.torch
         dev = self.dev
         lib, ctx = self.eng.lib, self.eng._ctx
@@ -262,25 +263,57 @@ class DeviceGfa:
                 for r in order:
                     k = int(novel[r, 0])
                     extra += f"L\t{(k >> 32) + self.min_id}\t+\t{(k & 0xFFFFFFFF) + self.min_id}\t+\t*\tRC:i:{int(novel[r, 1])}\tID:Z:N\n".encode()
-            host = torch.empty(total + len(extra), dtype=torch.uint8, pin_memory=True) if total + len(extra) else torch.empty(0, dtype=torch.uint8)
-            if total:
-                host[:total].copy_(out[:total], non_blocking=True)
-            torch.cuda.current_stream(dev).synchronize()
-            if extra:
-                host[total:] = torch.frombuffer(extra, dtype=torch.uint8)
+        return out, total, bytes(extra)
+
+    def render(self, sums, stamps, novel: np.ndarray, sparse: np.ndarray):
+        """-> pinned uint8 tensor with the whole augmented GFA (tests, bench parity check)."""
+        torch = self.torch
+        out, total, extra = self.render_device(sums, stamps, novel, sparse)
+        n = total + len(extra)
+        host = torch.empty(n, dtype=torch.uint8, pin_memory=True) if n else torch.empty(0, dtype=torch.uint8)
+        if total:
+            host[:total].copy_(out[:total], non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        if extra:
+            host[total:] = torch.frombuffer(bytearray(extra), dtype=torch.uint8)
         return host
 
+    PIECE = 32 << 20
+
     def write(self, sums, stamps, novel, sparse, out=None) -> None:
-        host = self.render(sums, stamps, novel, sparse)
+        """Render on the device and stream to `out` through two small pinned buffers: the copy of piece i + 1 runs while
+        piece i is written (no pinned buffer of the whole output, whose allocation alone costs more than the copy)."""
+        torch = self.torch
+        dev_out, total, extra = self.render_device(sums, stamps, novel, sparse)
         out = out or sys.stdout
-        data = memoryview(host.numpy())
         raw = getattr(out, "buffer", None)
-        if raw is not None:
-            out.flush()
-            raw.write(data)
-            raw.flush()
-        else:
-            out.write(bytes(data).decode("ascii"))
+        if raw is None:                                    # a text-only stream (tests): one copy
+            host = dev_out[:total].cpu().numpy().tobytes() + extra
+            out.write(host.decode("ascii"))
+            return
+        out.flush()
+        with torch.cuda.device(self.dev):
+            piece = self.PIECE
+            bufs = [torch.empty(min(piece, max(total, 1)), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+            evs = [torch.cuda.Event(), torch.cuda.Event()]
+            n_pieces = (total + piece - 1) // piece
+
+            def issue(i):
+                a, b = i * piece, min((i + 1) * piece, total)
+                bufs[i & 1][: b - a].copy_(dev_out[a:b], non_blocking=True)
+                evs[i & 1].record()
+
+            if n_pieces:
+                issue(0)
+            for i in range(n_pieces):
+                evs[i & 1].synchronize()
+                if i + 1 < n_pieces:
+                    issue(i + 1)                           # (buffer (i + 1) & 1 was written out in the previous iteration)
+                a, b = i * piece, min((i + 1) * piece, total)
+                raw.write(memoryview(bufs[i & 1].numpy())[: b - a])
+        if extra:
+            raw.write(extra)
+        raw.flush()
 
 
 class _LazyHost:
