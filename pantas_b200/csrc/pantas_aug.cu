@@ -152,9 +152,6 @@ static int fold_epoch(pt_ctx* ctx) {
 
 // the fast path's geometries: Geo<tile, look-ahead, step-list entries, teams per CTA, CTAs per SM>
 typedef teamp::Geo<9216, 1024, 512, 10, 1> GeoP;     // production: one CTA of ten teams per SM, tiles of up to 9 KiB (measured best, profiles/r02_geometry_sweep.txt)
-typedef teamp::Geo<7168, 1024, 448, 5, 2> GeoQ;
-typedef teamp::Geo<6144, 1024, 384, 6, 2> GeoR;
-typedef teamp::Geo<12288, 1024, 768, 7, 1> GeoS;
 typedef teamp::Geo<8192, 1024, 512, 5, 2> GeoU;      // two CTAs of five teams per SM
 typedef teamp::Geo<1024, 256, 96, 2, 1> GeoT;        // tests: many tile boundaries, records longer than the look-ahead
 
@@ -483,9 +480,6 @@ static int launch_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, ui
     int rc;
     switch (ctx->geo) {
         case 1024: rc = launch_team<GeoT>(ctx, A, T); break;
-        case 7168: rc = launch_team<GeoQ>(ctx, A, T); break;
-        case 6144: rc = launch_team<GeoR>(ctx, A, T); break;
-        case 12288: rc = launch_team<GeoS>(ctx, A, T); break;
         case 8193: rc = launch_team<GeoU>(ctx, A, T); break;
         default: rc = launch_team<GeoP>(ctx, A, T); break;
     }

@@ -201,11 +201,16 @@ def test_golden_cases_host_buffers(tmp_path):
         check_golden(case, gpu_pipeline(tmp_path, case["gfa"], case["gaf"], thr, eng=eng, via_host=True))
 
 
-@pytest.mark.parametrize("team_tile", [1024, 6144, 7168, 8192, 12288])
-def test_golden_team_geometries(team_tile, tmp_path):
-    """The fast path gives the same bytes for every tile size (1 KiB tiles: many tile boundaries, records longer than
-    the look-ahead, full lists -- all of which hand records to the exact per-record kernel)."""
-    eng = _engine(PANTAS_TEAM_TILE=team_tile)
+GEOS = [dict(PANTAS_TEAM_TILE=8192), dict(PANTAS_TEAM_TILE=1024), dict(PANTAS_TEAM_TILE=8193),
+        dict(PANTAS_TEAM_TILE=8192, PANTAS_TILE_BYTES=6144), dict(PANTAS_TEAM_TILE=8192, PANTAS_TILE_BYTES=2000),
+        dict(PANTAS_TEAM_TILE=8193, PANTAS_TILE_BYTES=7168), dict(PANTAS_TEAM_TILE=8192, PANTAS_TILE_BYTES=9216)]
+
+
+@pytest.mark.parametrize("geo", range(len(GEOS)))
+def test_golden_team_geometries(geo, tmp_path):
+    """The fast path gives the same bytes for every layout and tile length (1 KiB tiles: many tile boundaries, records
+    longer than the look-ahead, full lists -- all of which hand records to the exact per-record kernel)."""
+    eng = _engine(**GEOS[geo])
     for case in GOLDEN:
         thr = 20 if case["thr"] is None else case["thr"]
         check_golden(case, gpu_pipeline(tmp_path, case["gfa"], case["gaf"], thr, eng=eng))
@@ -217,16 +222,16 @@ def test_fuzz_vs_oracle(seed, tmp_path):
                                  crlf=(seed % 6 == 0), trailing_newline=(seed % 4 != 0))
     orc = run_oracle(gaf.encode(), gfa.encode())
     assert orc.rc == 0
-    eng = _engine(PANTAS_TEAM_TILE=[8192, 1024, 7168, 12288, 6144][seed % 5])
+    eng = _engine(**GEOS[seed % len(GEOS)])
     res = gpu_pipeline(tmp_path, gfa, gaf, eng=eng, chunks=1 + seed % 3, via_host=(seed % 5 == 0))
     assert res[0] == "ok", res
     assert res[1] == orc.out
     assert res[2] == orc.rej
 
 
-@pytest.mark.parametrize("preset,pairs,team_tile", [("tiny", 20000, 8192), ("dm-chr4", 100000, 8192), ("dm-chr4", 50000, 7168),
-                                                    ("tiny", 20000, 1024), ("gene-panel", 50000, 12288), ("tiny", 20000, 6144)])
-def test_synthetic_workload_matches_oracle(preset, pairs, team_tile, tmp_path):
+@pytest.mark.parametrize("preset,pairs,geo", [("tiny", 20000, 0), ("dm-chr4", 100000, 0), ("dm-chr4", 50000, 5),
+                                              ("tiny", 20000, 1), ("gene-panel", 50000, 6), ("tiny", 20000, 3)])
+def test_synthetic_workload_matches_oracle(preset, pairs, geo, tmp_path):
     """The bench workload's generator (vg-mpmap-shaped records, mostly fast-path) at a size the CPU oracle
     finishes in seconds: the augmented GFA is byte-identical."""
     import torch
@@ -242,7 +247,7 @@ def test_synthetic_workload_matches_oracle(preset, pairs, team_tile, tmp_path):
     want = run_oracle(gaf, gp.read_bytes())
     assert want.rc == 0, want.err
     graph = load_graph(str(gp))
-    eng = _engine(PANTAS_TEAM_TILE=team_tile)
+    eng = _engine(**GEOS[geo])
     eng.set_graph(graph)
     n = int(gaf.shape[0])
     d = torch.zeros(n + 32, dtype=torch.uint8, device="cuda")
@@ -256,7 +261,7 @@ def test_synthetic_workload_matches_oracle(preset, pairs, team_tile, tmp_path):
     write_augmented(str(gp), graph, counts, out)
     assert out.getvalue().encode() == want.out
     st = eng.stats()
-    if team_tile >= 4096:
+    if GEOS[geo]["PANTAS_TEAM_TILE"] >= 4096:
         assert st["deferred_lines"] < 0.02 * n_lines, st      # the fast path really is the path taken
 
 
@@ -306,7 +311,7 @@ def test_full_size_graphs_are_linear_in_the_gaf(preset, pairs):
     bounds = shard_bounds_bytes(gaf, 3)
     parts = []
     for k, (lo, hi) in enumerate(zip(bounds, bounds[1:])):
-        e2 = _engine(PANTAS_TEAM_TILE=[8192, 7168, 12288][k])
+        e2 = _engine(**GEOS[[0, 5, 3][k]])
         e2.set_graph(graph)
         piece = torch.zeros(hi - lo + 32, dtype=torch.uint8, device="cuda")
         piece[: hi - lo] = d[lo:hi]
@@ -365,7 +370,7 @@ def test_far_links_vs_oracle(seed, tmp_path):
     gfa, gaf = fuzzgen.spread_ids(gfa, gaf, pivot=15, shift=50000)
     orc = run_oracle(gaf.encode(), gfa.encode())
     assert orc.rc == 0
-    eng = _engine(PANTAS_TEAM_TILE=[8192, 1024, 7168, 6144][seed % 4])
+    eng = _engine(**GEOS[seed % 4])
     res = gpu_pipeline(tmp_path, gfa, gaf, eng=eng, chunks=1 + seed % 2)
     assert res[0] == "ok", res
     assert res[1] == orc.out
