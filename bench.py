@@ -49,6 +49,7 @@ WORKLOADS = {
     "hs-wg-25M": ("hs-wg", 12_500_000, 1004),                    # BASELINE.json configs[3] graph (2e8 nodes), 25 M alignments per GPU
     "hs-wg-125M": ("hs-wg", 62_500_000, 1004),                   # BASELINE.json configs[3] itself at 8 GPUs: 8 x 125 M = 1 G alignments
     "gene-panel-500M": ("gene-panel", 250_000_000, 1005),        # BASELINE.json configs[4] at its full 500 M reads (153 GB of GAF in HBM)
+    "dm-full-10M-bq": ("dm-full", 5_000_000, 1002),               # the default workload with a bq:Z: quality tag per record (FASTQ reads)
     "tiny-20k": ("tiny", 10_000, 7),
 }
 
@@ -166,6 +167,8 @@ def make_inputs(workload: str, rank: int, world: int, pinned: bool = True, devic
     preset, pairs, seed = WORKLOADS[workload]
     if workload.endswith("-strong"):
         pairs //= world
+    if workload.endswith("-bq"):
+        os.environ["PANTAS_SYNTH_BQ"] = "1"                  # (read when the generator is created)
     sg = SynthGraph(preset, seed=seed)
     threads = max(1, (os.cpu_count() or 8) // max(world, 1))
     piece = 2_500_000                                       # pairs per generator call: bounds the generator's own buffers

@@ -5,11 +5,11 @@
 // Data flow on the device (DESIGN.md has the full picture):
 //
 //   GAF bytes in HBM --cp.async.bulk (TMA 1-D, L2 evict-first)--> a team's shared-memory tile
-//     team_tiles.cuh   the fast path: persistent two-warp teams, ten per SM, phases over an 8 KiB tile (byte-parallel
-//                      SWAR scan, records by role warps, one thread per path step for ids / fold / count)
+//     team_tiles.cuh   the fast path: persistent two-warp teams, ten per SM, phases over a tile of about 30 records, up to
+//                      9 KiB (byte-parallel SWAR scan, records by role warps, one thread per path step for ids / fold / count)
 //     line_core.cuh    exact thread-per-record path for every record the fast path declines
 //                      (augment_deferred_kernel, bytes from global memory)
-//     tables.cuh       NodeHot[idx] = 16 bytes per node (meta word + three counters): one 16-byte load and
+//     tables.cuh       NodeHot[idx] = 16 bytes per node (meta word + three counters): one 4-byte load and
 //                      one 32-bit RED per path step, the table stays in the L2; 64-bit-key open-addressing
 //                      tables for the remaining links (known: ovf, unknown: novel) and for deletion-derived
 //                      IL/OL keys (sparse)

@@ -4,8 +4,8 @@
 //
 // Reference loop body: /root/reference/scripts/alignments_augmentation_from_gaf.py:142-363 (REF:n).
 //
-// The unit of execution is a TEAM: two warps that own 8 KiB tiles of the GAF chunk (+ 1 KiB of look-ahead: a record
-// belongs to the tile it starts in) and their own slice of shared memory.  G::NT teams form one CTA (default: the ten
+// The unit of execution is a TEAM: two warps that own tiles of the GAF chunk -- ChunkArgs::tile_bytes each, about 30 records,
+// at most G::TILE = 9 KiB (+ 1 KiB of look-ahead: a record belongs to the tile it starts in) -- and their own slice of shared memory.  G::NT teams form one CTA (default: the ten
 // teams of an SM are ONE 640-thread CTA) and share nothing but the global tables and ONE CTA-wide barrier per tile,
 // after `scan`: it keeps every team of the SM in (nearly) the same phase, so that the SM's instruction caches hold one
 // or two phases of this 100 KB kernel instead of all of them (independent 64-thread CTAs starved on instruction fetch).
@@ -136,9 +136,39 @@ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
 #endif
 }
 
-// no "s:" / "v:" byte pair inside: neither regex of REF:154-156,172-174 can start in this token
+// no "s:" / "v:" byte pair inside: neither regex of REF:154-156,172-174 can start in this token.  Short tokens are checked
+// byte by byte; a long one (bq:Z:<one quality character per base>, what vg writes for FASTQ reads) a word at a time for a
+// sufficient condition: no byte in 0x60..0x7F after the "xx:T:" prefix, i.e. no lower-case letter at all (Phred+33 qualities
+// end at '~' = Q93, real ones far below 's' = Q82).
 __device__ __forceinline__ bool token_is_inert(const uint8_t* s, uint32_t a, uint32_t b) {
-    if (b - a > 48u) return false;
+    if (b - a > 48u) {
+        if (b - a > 4096u) return false;
+        // the tag's own name is lower case ("bq:Z:"): its first bytes get the exact pair test, the rest the word test
+        uint32_t prev = 0;
+        for (uint32_t q = a; q < a + 8u; q++) {
+            const uint32_t c = s[q];
+            if (c == ':' && (prev == 's' || prev == 'v')) return false;
+            prev = c;
+        }
+        a += 5u;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(s);
+        const uint32_t wa = a >> 2, wb = (b - 1u) >> 2;                       // first / last word holding a token byte
+        uint32_t acc = 0;
+        {
+            const uint32_t x = w[wa] & (0xFFFFFFFFu << (8u * (a & 3u)));        // bytes before a: dropped
+            acc |= x & (x << 1);
+        }
+        for (uint32_t i = wa + 1u; i < wb; i++) {
+            const uint32_t x = w[i];
+            acc |= x & (x << 1);
+        }
+        {
+            uint32_t x = w[wb] & (0xFFFFFFFFu >> (8u * (3u - ((b - 1u) & 3u))));   // bytes from b on: dropped
+            if (wb == wa) x &= 0xFFFFFFFFu << (8u * (a & 3u));
+            acc |= x & (x << 1);
+        }
+        return (acc & 0x40404040u) == 0u;                                    // bit 6 and bit 5 of one byte both set
+    }
     uint32_t prev = 0;
     for (uint32_t q = a; q < b; q++) {
         const uint32_t c = s[q];

@@ -103,6 +103,36 @@ def test_synthetic_reads_stay_on_the_fast_path(tmp_path):
         assert st["deferred"] <= n // 50, st
 
 
+def test_records_with_base_qualities_stay_on_the_fast_path(tmp_path, monkeypatch):
+    """What vg mpmap writes for FASTQ reads: a bq:Z: tag (one quality character per base, ':' '<' '>' among them) between
+    AS and cs.  A long token like that must not send the record to the per-record kernel."""
+    from pantas_b200.synth import SynthGraph
+
+    monkeypatch.setenv("PANTAS_SYNTH_BQ", "1")
+    sg = SynthGraph("tiny", seed=12)
+    gp = tmp_path / "g.gfa"
+    sg.write_gfa(str(gp))
+    buf, n = sg.gaf(300, first_pair=0)
+    gaf = bytes(buf)
+    assert gaf.count(b"\tbq:Z:") == n - gaf.count(b"\t*\t0\t0\t0")      # (unmapped mates carry no tags)
+    orc = run_oracle(gaf, gp.read_bytes())
+    assert orc.rc == 0
+    for geo in (1, 2):
+        st = {}
+        res = pipeline(tmp_path, gp.read_text(), gaf.decode(), geo=geo, grid=3, stats=st)
+        assert res[0] == "ok" and res[1] == orc.out and res[2] == orc.rej
+        assert st["lines"] == n
+        assert st["deferred"] <= n // 50, st
+    # a lower-case letter in the quality string (never from a sequencer): the exact path decides, same bytes
+    weird = gaf.replace(b"\tbq:Z:#", b"\tbq:Z:s", 5).replace(b"\tbq:Z:$", b"\tbq:Z:cs:Z::3", 2)
+    orc2 = run_oracle(weird, gp.read_bytes())
+    res = pipeline(tmp_path, gp.read_text(), weird.decode(), geo=2, grid=3)
+    if orc2.rc == 0:
+        assert res[0] == "ok" and res[1] == orc2.out and res[2] == orc2.rej
+    else:
+        assert res[0] in ("raise", "unsupported"), res
+
+
 def test_dense_short_records_overflow_the_tile_lists(tmp_path):
     """More records per tile than the record list holds: the whole tile takes the per-record kernel."""
     gfa = "H\tVN:Z:1.1\nS\t1\tACGTACGTAC\nS\t2\tGGGGG\nL\t1\t+\t2\t+\t*\n"
