@@ -64,11 +64,12 @@ __global__ void gfa_parse_kernel(const uint8_t* s, LineArrays L, uint64_t n_line
         if (ls < le && s[ls] == 'S') kind |= K_RAW_S;
         if (a < b && s[a] == 'S') kind |= K_STR_S;
         if (a < b && s[a] == 'L') kind |= K_STR_L;
-        // tokens of the stripped text
+        // tokens of the stripped text -- of S and L lines only: nothing reads them for other lines, and the P line of a
+        // reference path is one token of up to 100 MB
         uint64_t ta[4] = {0, 0, 0, 0}, tb[4] = {0, 0, 0, 0};
         uint32_t nt = 0;
         uint64_t q = a;
-        while (q < b && nt < 4u) {
+        while (kind != 0u && q < b && nt < 4u) {
             ta[nt] = q;
             while (q < b && !py_ws(s[q])) q++;
             tb[nt] = q;
@@ -134,6 +135,9 @@ __device__ __forceinline__ uint8_t* put_str(uint8_t* o, const char* t, int n) {
     return o + n;
 }
 
+// other lines (REF:424: echoed stripped) longer than this are copied by a whole block, not by the line's one thread
+constexpr uint32_t LONG_LINE = 4096;
+
 // bytes line i prints (0: the line is dropped); errors like the reference's second pass (REF:377-424)
 template <bool WRITE>
 __device__ __forceinline__ uint64_t gfa_line_out(const WriterArgs& W, uint64_t i, uint8_t* o, unsigned long long* err) {
@@ -191,7 +195,8 @@ __device__ __forceinline__ uint64_t gfa_line_out(const WriterArgs& W, uint64_t i
         return (uint64_t)slen + 6u + dec_digits(w) + 1u;
     }
     if (WRITE) {
-        for (uint32_t k = 0; k < slen; k++) o[k] = src[k];
+        if (slen <= LONG_LINE)                                           // (longer: gfa_format_kernel's second loop)
+            for (uint32_t k = 0; k < slen; k++) o[k] = src[k];
         o[slen] = '\n';
     }
     return (uint64_t)slen + 1u;                                          // REF:424
@@ -205,6 +210,25 @@ __global__ void gfa_measure_kernel(WriterArgs W, long long* out_len, unsigned lo
 __global__ void gfa_format_kernel(WriterArgs W, const long long* out_off, uint8_t* out, unsigned long long* err) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < W.n_lines; i += (uint64_t)gridDim.x * blockDim.x)
         gfa_line_out<true>(W, i, out + out_off[i], err);
+    // long echoed lines (the P line of a reference path can be 100 MB): the block that owns the line copies it together
+    __shared__ uint32_t long_n;
+    __shared__ uint32_t long_list[256];
+    for (uint64_t base = blockIdx.x * (uint64_t)blockDim.x; base < W.n_lines; base += (uint64_t)gridDim.x * blockDim.x) {
+        if (threadIdx.x == 0) long_n = 0;
+        __syncthreads();
+        const uint64_t i = base + threadIdx.x;
+        if (i < W.n_lines && (W.kind[i] & (K_STR_S | K_STR_L)) == 0u && W.slen[i] > LONG_LINE) long_list[atomicAdd(&long_n, 1u)] = threadIdx.x;
+        __syncthreads();
+        const uint32_t n = long_n;
+        for (uint32_t k = 0; k < n; k++) {
+            const uint64_t j = base + long_list[k];
+            const uint8_t* src = W.s + (uint64_t)W.start[j] + W.a_rel[j];
+            uint8_t* dst = out + out_off[j];
+            const uint32_t len = W.slen[j];
+            for (uint32_t q = threadIdx.x; q < len; q += blockDim.x) dst[q] = src[q];
+        }
+        __syncthreads();
+    }
 }
 
 }  // namespace gfa

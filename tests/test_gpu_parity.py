@@ -146,6 +146,25 @@ def test_golden_cases_device_gfa_passes():
         check_golden(case, gpu_pipeline_device_gfa(case["gfa"], case["gaf"], thr, eng=eng))
 
 
+def test_device_gfa_passes_long_path_lines():
+    """The P line of a reference path is one token of up to 100 MB: pass 1 must not tokenise it, the writer copies it with
+    a whole block.  Lengths around the 4096-byte switch, leading / trailing blanks (the reference echoes the stripped line)."""
+    gfa, gaf = fuzzgen.make_case(9300, n_nodes=40, n_reads=300, weird=False)
+    lines = gfa.splitlines(keepends=True)
+    extra = []
+    for k, n in enumerate((4090, 4096, 4097, 5000, 70001, 300000)):
+        body = ",".join(f"{1 + (i % 40)}+" for i in range(n // 3))[:n - 10]
+        extra.append(f"{'  ' if k % 2 else ''}P\tref{k}\t{body}\t*{'  ' if k % 3 == 0 else ''}\n")
+    extra.append("#" + "x" * 9000 + " \t \n")
+    gfa2 = "".join(lines[:3] + extra[:3] + lines[3:] + extra[3:])
+    orc = run_oracle(gaf.encode(), gfa2.encode())
+    assert orc.rc == 0
+    res = gpu_pipeline_device_gfa(gfa2, gaf)
+    assert res[0] == "ok", res
+    assert res[1] == orc.out
+    assert res[2] == orc.rej
+
+
 @pytest.mark.parametrize("seed", range(9200, 9212))
 def test_fuzz_device_gfa_passes_vs_oracle(seed):
     gfa, gaf = fuzzgen.make_case(seed, n_nodes=10 + seed % 40, n_reads=300, weird=(seed % 2 == 0), crlf=(seed % 6 == 0),
