@@ -1,3 +1,4 @@
 set -x
-mkdir -p gpurun_out
-python -m pytest tests/test_gpu_parity.py -x -q -k "device_gfa or bench_scale" 2>&1 | tail -3
+for m in 1 17 18 20 19; do
+  echo "== PANTAS_LOOSE=$m"; PANTAS_LOOSE=$m PANTAS_TILE_BYTES=8992 python tools/prof_step.py --pairs 5000000 --steps 4 2>&1 | grep -E "fast kernel"
+done
