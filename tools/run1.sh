@@ -1,4 +1,5 @@
 set -x
-for m in 1 17 18 20 19; do
-  echo "== PANTAS_LOOSE=$m"; PANTAS_LOOSE=$m PANTAS_TILE_BYTES=8992 python tools/prof_step.py --pairs 5000000 --steps 4 2>&1 | grep -E "fast kernel"
-done
+mkdir -p gpurun_out
+(time python -m pytest tests -m gpu -x -q) > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+(time python bench.py) > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 600 gpurun_out/bench.json; tail -2 gpurun_out/bench.err
