@@ -216,6 +216,21 @@ def make_case(seed: int, n_nodes: int = 12, n_reads: int = 40, weird: bool = Fal
     return gfa, gaf
 
 
+def add_quality_tags(gaf: str, seed: int, share: float = 0.7) -> str:
+    """Insert a bq:Z: tag (Phred+33 characters '!'..'K', ':' '<' '>' among them, 20-300 of them) somewhere among the tags
+    of `share` of the records: what vg mpmap writes for FASTQ reads, inert for both regexes of the reference."""
+    rng = random.Random(seed ^ 0xB9B9)
+    out = []
+    for line in gaf.split("\n"):
+        end = "\r" if line.endswith("\r") else ""
+        t = (line[:-1] if end else line).split("\t")
+        if len(t) >= 12 and rng.random() < share:
+            q = "".join(chr(rng.randint(33, 75)) for _ in range(rng.randint(20, 300)))
+            t.insert(rng.randint(12, len(t)), "bq:Z:" + q)
+        out.append("\t".join(t) + end)
+    return "\n".join(out)
+
+
 def make_risky_case(seed: int):
     """Small graph, one safe prefix and one possibly-crashing record at the end."""
     rng = random.Random(seed ^ 0x5EED)

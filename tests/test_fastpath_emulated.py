@@ -150,6 +150,18 @@ def test_dense_short_records_overflow_the_tile_lists(tmp_path):
             assert st["deferred"] > 0
 
 
+@pytest.mark.parametrize("seed", range(7600, 7606))
+def test_fuzz_with_quality_tags(seed, tmp_path):
+    """Long inert tags anywhere among the tags (before, between and after cs / dv), CRLF line ends included."""
+    gfa, gaf = fuzzgen.make_case(seed, n_nodes=25, n_reads=300, weird=(seed % 2 == 0), crlf=(seed % 3 == 0))
+    gaf = fuzzgen.add_quality_tags(gaf, seed)
+    orc = run_oracle(gaf.encode(), gfa.encode())
+    assert orc.rc == 0
+    st = {}
+    res = pipeline(tmp_path, gfa, gaf, geo=1 + seed % 2, grid=1 + seed % 3, stats=st)
+    assert res[0] == "ok" and res[1] == orc.out and res[2] == orc.rej
+
+
 @pytest.mark.parametrize("seed", range(7500, 7506))
 def test_fuzz_production_geometry(seed, tmp_path):
     gfa, gaf = fuzzgen.make_case(seed, n_nodes=30, n_reads=400, weird=(seed % 2 == 0), crlf=(seed % 3 == 0))
