@@ -239,6 +239,8 @@ def test_golden_team_geometries(geo, tmp_path):
 def test_fuzz_vs_oracle(seed, tmp_path):
     gfa, gaf = fuzzgen.make_case(seed, n_nodes=10 + seed % 40, n_reads=400, weird=(seed % 2 == 0),
                                  crlf=(seed % 6 == 0), trailing_newline=(seed % 4 != 0))
+    if seed % 3 == 1:
+        gaf = fuzzgen.add_quality_tags(gaf, seed)      # bq:Z: tags of FASTQ reads: long inert tokens among the tags
     orc = run_oracle(gaf.encode(), gfa.encode())
     assert orc.rc == 0
     eng = _engine(**GEOS[seed % len(GEOS)])
