@@ -1,13 +1,13 @@
 #!/usr/bin/env python3
-"""Sweep fast-path geometries on the GPU box: python tools/sweep.py 24576 32768 ...  (PANTAS_FAST_T values)"""
+"""Sweep tile lengths of the fast path on the GPU box: python tools/sweep.py 8192 8704 8992 9216 ...  (PANTAS_TILE_BYTES values)"""
 import json
 import os
 import subprocess
 import sys
 
 for cfg in sys.argv[1:]:
-    env = dict(os.environ, PANTAS_FAST_T=cfg)
-    p = subprocess.run([sys.executable, "bench.py", "--no-cpu-baseline", "--no-e2e", "--steps", "4"], env=env,
+    env = dict(os.environ, PANTAS_TILE_BYTES=cfg)
+    p = subprocess.run([sys.executable, "bench.py", "--no-cpu-baseline", "--no-e2e", "--no-cli", "--steps", "4"], env=env,
                        capture_output=True, text=True)
     try:
         d = json.loads(p.stdout.strip().splitlines()[-1])
