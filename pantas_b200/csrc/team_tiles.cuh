@@ -32,7 +32,8 @@
 //   walk     warp 0 the even records, warp 1 the odd ones, O(1) for a record whose cs string is one op: first / last node
 //            shortened (REF:215-218), the sum of the node shares against the cs length (IndexError REF:227), dropped
 //            ends.  Records with several ops get the prefix sums the merge walk needs (REF:205-255) from a warp scan and
-//            are listed for `fold`.  Warp 1 first drains the previous tile's list of links that are not inline (hash probes).
+//            are listed for `fold`.  Warp 1 first drains the previous tile's list of links that are not inline (hash probes); warp 0
+//            takes what is left of it when its records are done.
 //   fold     the listed steps of multi-op records, half of them per warp: clear_align / compact_align (REF:63-107) folded
 //            over the op pieces that overlap the node: dropped or not, counting ops, deletion-derived IL/OL keys.
 //   count    one thread per surviving step, no dependent loads from the tables: ONE 32-bit RED (tables.cuh), stamps only
@@ -899,12 +900,7 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
         //     single-op record, the nodes an op boundary or a mismatch / indel falls into are listed for `fold`.
         if (warp == 1) {
             drain_far();
-            __syncwarp();
-            if (lane == 0) {
-                s_nfar = 0;
-                s_far_take = 0;
-                s_ndel = 0;
-            }
+            if (lane == 0) s_ndel = 0;
         }
         {
             constexpr uint32_t HALF = (uint32_t)G::HEAVY_CAP / 2u;          // every warp lists into its own half
@@ -988,8 +984,13 @@ __global__ void __launch_bounds__(THREADS * G::NT, G::CTAS) augment_team_kernel(
             }
             if (lane == 0) s_nheavy2[warp] = min(n_heavy_w, HALF);
         }
+        drain_far();                                                        // (whatever warp 1 has not taken yet: warp 0 is usually here first)
+        team_sync();                                                          // ---- B4: hand-over decisions of `walk`, prefix pool, heavy list; the far-link list is drained
         if (active) far_base = base_off;                                    // the list `count` fills below belongs to this tile
-        team_sync();                                                          // ---- B4: hand-over decisions of `walk`, prefix pool, heavy list
+        if (tid == 0) {                                                     // (`count` appends after B5)
+            s_nfar = 0;
+            s_far_take = 0;
+        }
         if (ablate == 5u) continue;
 
         // ================= fold: every step of a multi-op record folds the cs ops that overlap its node =================
