@@ -95,7 +95,8 @@ int pt_process_chunk(pt_ctx* ctx, const uint8_t* gaf_dev, uint64_t nbytes, uint6
 /* Same, from HOST memory (pinned for full speed): copies through two
  * library-owned device staging buffers so the copy of one chunk overlaps the
  * kernels of the previous one.  nbytes <= pt_stage_bytes().  Returns a ticket
- * >= 0; the host buffer may be reused once pt_wait_copy(ticket) returns. */
+ * >= 0; the host buffer may be reused once pt_wait_copy(ticket) returns.  (The first call looks at the head of the buffer
+ * for the average record length: the kernel's tiles are sized to carry about 30 records.) */
 int64_t pt_process_host(pt_ctx* ctx, const uint8_t* gaf_host, uint64_t nbytes, uint64_t file_offset,
                         int64_t mapq_thr);
 int pt_wait_copy(pt_ctx* ctx, int64_t ticket);

@@ -53,14 +53,16 @@ def gpu_numa_node(device: int, sysfs: str = "/sys") -> int | None:
     return node if node >= 0 else None
 
 
-def bind_to_gpu_node(device: int, sysfs: str = "/sys") -> dict:
-    """Restrict this process to the CPUs of the GPU's NUMA node.  -> what was done, for the logs / the bench line."""
+def bind_to_gpu_node(device: int, sysfs: str = "/sys", node: int | None = None) -> dict:
+    """Restrict this process to the CPUs of the GPU's NUMA node (`node`: skip the look-up, tests).  -> what was done, for
+    the logs / the bench line."""
     info = {"device": int(device), "node": None, "cpus": None, "bound": False}
     nodes = _read(os.path.join(sysfs, "devices", "system", "node", "online"))
     if nodes is None or len(parse_cpulist(nodes)) < 2:
         info["why"] = "one NUMA node"
         return info
-    node = gpu_numa_node(device, sysfs)
+    if node is None:
+        node = gpu_numa_node(device, sysfs)
     if node is None:
         info["why"] = "GPU's node not exposed"
         return info

@@ -32,3 +32,24 @@ def test_unknown_gpu_node_is_left_alone(tmp_path):
 def test_missing_sysfs_is_left_alone(tmp_path):
     info = numa.bind_to_gpu_node(0, sysfs=str(tmp_path / "nothing"))
     assert info["bound"] is False
+
+
+def test_binds_to_the_cpus_of_the_node(tmp_path):
+    """Two nodes in a fake sysfs tree; node 1 owns one of the CPUs this process may run on."""
+    before = os.sched_getaffinity(0)
+    mine = sorted(before)
+    nodes = tmp_path / "devices" / "system" / "node"
+    (nodes / "node0").mkdir(parents=True)
+    (nodes / "node1").mkdir(parents=True)
+    (nodes / "online").write_text("0-1\n")
+    (nodes / "node0" / "cpulist").write_text("100000-100003\n")               # CPUs this process does not have
+    (nodes / "node1" / "cpulist").write_text(f"{mine[0]},100004-100007\n")
+    try:
+        info = numa.bind_to_gpu_node(0, sysfs=str(tmp_path), node=1)
+        assert info["bound"] is True and info["node"] == 1 and info["cpus"] == 1
+        assert os.sched_getaffinity(0) == {mine[0]}
+        info = numa.bind_to_gpu_node(0, sysfs=str(tmp_path), node=0)             # nothing allowed there: left alone
+        assert info["bound"] is False
+        assert os.sched_getaffinity(0) == {mine[0]}
+    finally:
+        os.sched_setaffinity(0, before)
