@@ -160,6 +160,15 @@ def main():
         for s in range(80):
             gfa, gaf = fuzzgen.make_risky_case(2000 + s)
             cases.append(run_case(d, f"risky_{2000 + s}", gfa, gaf, None))
+        # records with a bq:Z: quality tag (what vg mpmap writes for FASTQ reads) somewhere among the tags
+        for s in range(24):
+            if s < 18:
+                gfa, gaf = fuzzgen.make_case(3000 + s, n_nodes=10 + s % 9, n_reads=30, weird=(s % 3 == 0),
+                                             crlf=(s % 7 == 0), trailing_newline=(s % 5 != 0))
+            else:
+                gfa, gaf = fuzzgen.make_risky_case(3000 + s)
+            gaf = fuzzgen.add_quality_tags(gaf, 3000 + s, share=0.8)
+            cases.append(run_case(d, f"quals_{3000 + s}", gfa, gaf, None))
     out = os.path.join(HERE, "cases.json.gz")
     with gzip.GzipFile(out, "wb", mtime=0) as f:
         f.write(json.dumps(cases, indent=0).encode("utf-8"))

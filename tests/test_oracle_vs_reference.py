@@ -17,6 +17,8 @@ def test_fuzz_against_reference(seed, tmp_path):
                                          trailing_newline=(seed % 3 != 0))
         else:
             gfa, gaf = fuzzgen.make_risky_case(seed)
+        if seed % 2 == 1:
+            gaf = fuzzgen.add_quality_tags(gaf, seed)      # bq:Z: tags (FASTQ reads): inert for both regexes of the reference
         gp, ap = tmp_path / f"{kind}.gfa", tmp_path / f"{kind}.gaf"
         gp.write_bytes(gfa.encode())
         ap.write_bytes(gaf.encode())
